@@ -1,0 +1,110 @@
+"""Pin the CPU oracle against fixtures produced by the UNMODIFIED reference
+(tests/golden/make_golden.py).  fp32 vs fp32: tolerance covers only summation-order noise."""
+import json
+import os
+
+import pytest
+import torch
+
+from helpers import GOLDEN, dims_from, load_golden, mask_from_valid, prefixed, regen_weights, sub_spec
+from live2diff_b200.weights import UNetDims, unet_param_spec
+from oracle import schedule_oracle as S
+from oracle import unet_oracle as O
+
+TOL = dict(rtol=1e-4, atol=2e-5)
+
+
+def odims(d: UNetDims) -> O.UNetDims:
+    return O.UNetDims(**d.__dict__)
+
+
+def schedule_frames(n_rows, window, warmup, frames):
+    ab, pe, up = S.init_schedule(n_rows, window, warmup)
+    for _ in range(frames):
+        yield ab.clone(), pe.clone(), up.clone()
+        S.update_schedule(ab, pe, up, window, warmup)
+
+
+@pytest.mark.parametrize("tag", ["c64_fill_wrap", "c320_hd40", "c128_L32_N4", "c64_N1_L4"])
+def test_stream_attention_matches_reference(tag):
+    g = load_golden(f"stream_attention_{tag}.pt")
+    d = UNetDims(block_out_channels=(g["ch"],), heads=g["heads"], window_size=g["window"], sink_size=g["warmup"],
+                 pe_max_len=g["pe_max"], down_has_attn=(False,), up_has_attn=(False,))
+    pre = "down_blocks.0.motion_modules.0.temporal_transformer.transformer_blocks.0.attention_blocks.0"
+    sd = prefixed(regen_weights(sub_spec(d, pre), g["seed"], g["fingerprint"]), "a")
+    cache = g["cache0"].clone()
+    frames = g["x"].shape[0]
+    for f, (mask, pe_idx, update_idx) in enumerate(schedule_frames(g["n_rows"], g["window"], g["warmup"], frames)):
+        y = O.stream_temporal_attention(sd, "a", g["x"][f], cache, mask, pe_idx, update_idx, odims(d))
+        torch.testing.assert_close(y, g["y"][f], **TOL)
+    torch.testing.assert_close(cache, g["cache_final"], **TOL)
+
+
+@pytest.mark.parametrize("tag", ["c64", "c320"])
+def test_temporal_transformer_matches_reference(tag):
+    g = load_golden(f"temporal_transformer_{tag}.pt")
+    d = UNetDims(block_out_channels=(g["ch"],), heads=g["heads"], window_size=g["window"], sink_size=g["warmup"],
+                 pe_max_len=g["pe_max"], down_has_attn=(False,), up_has_attn=(False,))
+    pre = "down_blocks.0.motion_modules.0.temporal_transformer"
+    sd = prefixed(regen_weights(sub_spec(d, pre), g["seed"], g["fingerprint"]), "t")
+    caches = [c.clone() for c in g["cache0"]]
+    for f, (mask, pe_idx, update_idx) in enumerate(schedule_frames(g["n_rows"], g["window"], g["warmup"], g["x"].shape[0])):
+        y = O.temporal_transformer(sd, "t", g["x"][f][:, :, 0], caches, mask, pe_idx, update_idx, odims(d))
+        torch.testing.assert_close(y, g["y"][f][:, :, 0], **TOL)
+    for c, cf in zip(caches, g["cache_final"]):
+        torch.testing.assert_close(c, cf, **TOL)
+
+
+def test_blocks_match_reference():
+    g = load_golden("blocks_small.pt")
+    d = dims_from(g["dims"])
+    od = odims(d)
+    for tag in ("res_same", "res_short"):
+        c = g[tag]
+        sd = prefixed(regen_weights(sub_spec(d, c["prefix"]), g["seed"], c["fingerprint"]), "r")
+        y = O.resnet_block(sd, "r", c["x"][:, :, 0], c["temb"], od)
+        torch.testing.assert_close(y, c["y"][:, :, 0], **TOL)
+    c = g["down"]
+    sd = prefixed(regen_weights(sub_spec(d, c["prefix"]), g["seed"], c["fingerprint"]), "s")
+    torch.testing.assert_close(O.downsample(sd, "s", c["x"][:, :, 0]), c["y"][:, :, 0], **TOL)
+    c = g["up"]
+    sd = prefixed(regen_weights(sub_spec(d, c["prefix"]), g["seed"], c["fingerprint"]), "s")
+    torch.testing.assert_close(O.upsample(sd, "s", c["x"][:, :, 0]), c["y"][:, :, 0], **TOL)
+    c = g["mapping"]
+    sd = prefixed(regen_weights(sub_spec(d, c["prefix"]), g["seed"], c["fingerprint"]), "m")
+    torch.testing.assert_close(O.mapping_network(sd, "m", c["x"][:, :, 0], 6), c["y"][:, :, 0], **TOL)
+    c = g["spatial"]
+    sd = prefixed(regen_weights(sub_spec(d, c["prefix"]), g["seed"], c["fingerprint"]), "t")
+    torch.testing.assert_close(O.spatial_transformer(sd, "t", c["x"][:, :, 0], c["ctx"], od), c["y"][:, :, 0], **TOL)
+
+
+def test_unet_tiny_stream_matches_reference():
+    g = load_golden("unet_tiny_stream.pt")
+    d = dims_from(g["dims"])
+    od = odims(d)
+    sd = regen_weights(unet_param_spec(d), g["seed"], g["fingerprint"])
+    kv = O.alloc_kv_cache(od, g["n_rows"], g["h"], g["w"])
+    gen = torch.Generator().manual_seed(g["seed"] + 1)
+    for c in kv:
+        c[:, :, :, : d.sink_size] = torch.randn(c[:, :, :, : d.sink_size].shape, generator=gen)
+    ctx = torch.randn(g["n_rows"], 77, d.cross_attention_dim, generator=gen)
+    torch.testing.assert_close(ctx, g["ctx"])
+    frames = g["x"].shape[0]
+    for f, (mask, pe_idx, update_idx) in enumerate(schedule_frames(g["n_rows"], d.window_size, d.sink_size, frames)):
+        y = O.unet_forward(sd, od, g["x"][f], g["timesteps"], ctx, mask, g["depth"][f], kv, pe_idx, update_idx)
+        torch.testing.assert_close(y, g["y"][f], rtol=2e-4, atol=5e-5)
+    sums = torch.tensor([float(c.double().sum()) for c in kv])
+    torch.testing.assert_close(sums, g["kv_sums"], rtol=1e-4, atol=1e-2)
+    torch.testing.assert_close(kv[12], g["kv_final_12"], **TOL)
+    torch.testing.assert_close(kv[39][0, :, :64], g["kv_final_39_row0"], **TOL)
+
+
+@pytest.mark.parametrize("tag", ["tiny", "sd15"])
+def test_param_spec_matches_reference_state_dict(tag):
+    ref = json.load(open(os.path.join(GOLDEN, f"state_dict_spec_{tag}.json")))
+    d = UNetDims() if tag == "sd15" else UNetDims(block_out_channels=(64, 128, 128, 128), cross_attention_dim=96)
+    mine = {k: list(v) for k, v in unet_param_spec(d).items()}
+    assert set(mine) == set(ref)
+    for k in ref:
+        assert mine[k] == ref[k], k
+    assert len(d.kv_cache_shapes(2, 64, 64)) == 40
