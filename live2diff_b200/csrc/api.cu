@@ -1,0 +1,22 @@
+// Error plumbing + misc exports of the C ABI (include/l2d_b200.h).
+#include <atomic>
+
+#include "common.cuh"
+
+namespace l2d {
+
+static thread_local std::string g_last_error;
+static std::atomic<int64_t> g_launches{0};
+
+void set_error(const std::string& msg) { g_last_error = msg; }
+int fail(int code, const std::string& msg) {
+  g_last_error = msg;
+  return code;
+}
+void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+}  // namespace l2d
+
+extern "C" int l2d_abi_version(void) { return L2D_ABI_VERSION; }
+extern "C" const char* l2d_last_error(void) { return l2d::g_last_error.c_str(); }
+extern "C" int64_t l2d_launch_count(void) { return l2d::g_launches.load(std::memory_order_relaxed); }

@@ -1,0 +1,98 @@
+// Shared device/host helpers for libl2d_b200 (sm_100a only).
+#pragma once
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+
+#include "../../include/l2d_b200.h"
+
+namespace l2d {
+
+// ---- error plumbing -------------------------------------------------------------------------
+void set_error(const std::string& msg);
+int fail(int code, const std::string& msg);
+void count_launch(int n = 1);
+
+#define L2D_CHECK_ARG(cond, msg)                                   \
+  do {                                                             \
+    if (!(cond)) return ::l2d::fail(L2D_ERR_INVALID, std::string(__func__) + ": " + (msg)); \
+  } while (0)
+
+#define L2D_CUDA(call)                                                                          \
+  do {                                                                                          \
+    cudaError_t _e = (call);                                                                    \
+    if (_e != cudaSuccess)                                                                      \
+      return ::l2d::fail(L2D_ERR_CUDA, std::string(__func__) + ": " #call ": " + cudaGetErrorString(_e)); \
+  } while (0)
+
+// kernel launch check (no sync): catches bad configs immediately
+#define L2D_LAUNCH_CHECK()                                                                      \
+  do {                                                                                          \
+    ::l2d::count_launch();                                                                      \
+    cudaError_t _e = cudaPeekAtLastError();                                                     \
+    if (_e != cudaSuccess) {                                                                    \
+      cudaGetLastError();                                                                       \
+      return ::l2d::fail(L2D_ERR_CUDA, std::string(__func__) + ": launch: " + cudaGetErrorString(_e)); \
+    }                                                                                           \
+  } while (0)
+
+inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+// ---- device helpers -------------------------------------------------------------------------
+struct __align__(16) half8 {
+  __half2 v[4];
+};
+
+__device__ __forceinline__ uint4 ldg_stream(const void* p) {  // read-once data: keep it out of L1
+  uint4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+               : "l"(p));
+  return r;
+}
+__device__ __forceinline__ uint4 ldg_cached(const void* p) { return __ldg(reinterpret_cast<const uint4*>(p)); }
+
+__device__ __forceinline__ __half2 u32_as_h2(uint32_t u) { return *reinterpret_cast<__half2*>(&u); }
+__device__ __forceinline__ uint32_t h2_as_u32(__half2 h) { return *reinterpret_cast<uint32_t*>(&h); }
+
+__device__ __forceinline__ void unpack8(const uint4& u, float (&f)[8]) {
+  float2 a = __half22float2(u32_as_h2(u.x)), b = __half22float2(u32_as_h2(u.y));
+  float2 c = __half22float2(u32_as_h2(u.z)), d = __half22float2(u32_as_h2(u.w));
+  f[0] = a.x; f[1] = a.y; f[2] = b.x; f[3] = b.y; f[4] = c.x; f[5] = c.y; f[6] = d.x; f[7] = d.y;
+}
+__device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
+  uint4 u;
+  u.x = h2_as_u32(__floats2half2_rn(f[0], f[1]));
+  u.y = h2_as_u32(__floats2half2_rn(f[2], f[3]));
+  u.z = h2_as_u32(__floats2half2_rn(f[4], f[5]));
+  u.w = h2_as_u32(__floats2half2_rn(f[6], f[7]));
+  return u;
+}
+// fp16 + fp16 -> fp16 (one rounding), the same value torch's half add produces
+__device__ __forceinline__ uint4 hadd8(const uint4& a, const uint4& b) {
+  uint4 r;
+  r.x = h2_as_u32(__hadd2(u32_as_h2(a.x), u32_as_h2(b.x)));
+  r.y = h2_as_u32(__hadd2(u32_as_h2(a.y), u32_as_h2(b.y)));
+  r.z = h2_as_u32(__hadd2(u32_as_h2(a.z), u32_as_h2(b.z)));
+  r.w = h2_as_u32(__hadd2(u32_as_h2(a.w), u32_as_h2(b.w)));
+  return r;
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+__device__ __forceinline__ float silu_f(float x) { return x / (1.0f + __expf(-x)); }
+__device__ __forceinline__ float gelu_erf_f(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
+
+}  // namespace l2d

@@ -1,0 +1,907 @@
+// Native runtime of the streaming UNet step: owns the repacked weights and the activation
+// workspace, walks the UNet topology and launches the kernels of this library on one stream, with
+// optional CUDA-graph capture of the whole step.  No device allocation, host synchronisation or
+// host<-device read happens inside a step (the ring schedule indices are consumed on the device).
+//
+// Topology restated from the reference (paths under live2diff/animatediff/models/):
+//   UNet3DConditionStreamingModel.forward       unet_depth_streaming.py:429-627
+//   CrossAttnDown/Down/Mid/CrossAttnUp/Up blocks unet_blocks_streaming.py:253-280,381-445,516-569,666-731,798-850
+//   ResnetBlock3D / Down/Upsample3D / MappingNetwork   resnet.py:17-259
+//   Transformer3DModel + BasicTransformerBlock  attention.py:91-135,221-270
+//   TemporalTransformer3DModel (+Block)         motion_module.py:256-299,401-435
+//   StreamTemporalAttention                     stream_motion_module.py:79-213
+// Activations are channels-last [N*h*w, C] fp16 end to end; the only layout changes are at the
+// 4-channel latent input and output (B1) or at the NCHW boundary of the stand-alone module (B2).
+#include <algorithm>
+#include <cstring>
+#include <map>
+#include <memory>
+#include <string>
+#include <utility>
+#include <vector>
+
+#include "ops.cuh"
+
+namespace l2d {
+
+#define RC(expr)                   \
+  do {                             \
+    int _rc = (expr);              \
+    if (_rc != L2D_OK) return _rc; \
+  } while (0)
+
+// ---------------------------------------------------------------------------------------------
+// small device kernels private to the engine
+// ---------------------------------------------------------------------------------------------
+// conv weight [Cout,Cin,3,3] -> [Cout_pad, Kpad] with k = (ky*3+kx)*Cin + cin; rows >= Cout / cols >= 9Cin zero
+__global__ void repack_conv3x3_kernel(const __half* __restrict__ w, __half* __restrict__ out, int cout, int cin,
+                                      int cout_pad, int kpad) {
+  const size_t total = (size_t)cout_pad * kpad;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int k = (int)(i % kpad), co = (int)(i / kpad);
+    __half v = __float2half(0.f);
+    if (co < cout && k < 9 * cin) {
+      const int tap = k / cin, ci = k - tap * cin;
+      v = w[((size_t)co * cin + ci) * 9 + tap];
+    }
+    out[i] = v;
+  }
+}
+__global__ void pad_vec_kernel(const __half* __restrict__ in, __half* __restrict__ out, int n, int n_pad) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n_pad) out[i] = i < n ? in[i] : __float2half(0.f);
+}
+// [M, ld] channels-last with >= 4 valid channels -> NCHW [N,4,hw]
+__global__ void nhwc_to_nchw4_kernel(const __half* __restrict__ x, __half* __restrict__ y, int n_img, int hw, int ld,
+                                     int c_out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_img * hw * c_out) return;
+  const int p = i % hw, c = (i / hw) % c_out, n = i / (hw * c_out);
+  y[i] = x[((size_t)n * hw + p) * ld + c];
+}
+
+// ---------------------------------------------------------------------------------------------
+// device memory bookkeeping
+// ---------------------------------------------------------------------------------------------
+struct DevPool {
+  std::vector<void*> blocks;
+  int64_t bytes = 0;
+  ~DevPool() {
+    for (void* p : blocks) cudaFree(p);
+  }
+  int alloc(void** out, size_t nbytes) {
+    if (nbytes == 0) nbytes = 16;
+    nbytes = (nbytes + 255) & ~size_t(255);
+    void* p = nullptr;
+    cudaError_t e = cudaMalloc(&p, nbytes);
+    if (e != cudaSuccess) return fail(L2D_ERR_CUDA, std::string("cudaMalloc(") + std::to_string(nbytes) + "): " + cudaGetErrorString(e));
+    blocks.push_back(p);
+    bytes += (int64_t)nbytes;
+    *out = p;
+    return L2D_OK;
+  }
+  int halfs(__half** out, size_t n) { return alloc(reinterpret_cast<void**>(out), n * sizeof(__half)); }
+};
+
+struct WeightTable {
+  std::map<std::string, const l2d_tensor*> by_name;
+  std::string prefix;  // error messages
+  int build(const l2d_tensor* w, int n) {
+    for (int i = 0; i < n; ++i) {
+      if (!w[i].name || !w[i].data) return fail(L2D_ERR_INVALID, "weights[" + std::to_string(i) + "] has a null name/data");
+      by_name[w[i].name] = &w[i];
+    }
+    return L2D_OK;
+  }
+  int get(const std::string& name, const __half** out, int64_t expect_numel) const {
+    auto it = by_name.find(name);
+    if (it == by_name.end()) return fail(L2D_ERR_MISSING, "missing weight tensor '" + name + "'");
+    int64_t numel = 1;
+    for (int d = 0; d < it->second->ndim; ++d) numel *= it->second->shape[d];
+    if (numel != expect_numel)
+      return fail(L2D_ERR_INVALID, "weight '" + name + "' has " + std::to_string(numel) + " elements, expected " +
+                                       std::to_string(expect_numel));
+    *out = static_cast<const __half*>(it->second->data);
+    return L2D_OK;
+  }
+};
+
+// ---------------------------------------------------------------------------------------------
+// parameter holders (device pointers into engine-owned memory)
+// ---------------------------------------------------------------------------------------------
+struct Lin {          // y = x W^T + b, W [n,k] (ldw = k)
+  __half* w = nullptr;
+  __half* b = nullptr;
+  int n = 0, k = 0;
+};
+struct Norm {
+  __half* g = nullptr;
+  __half* b = nullptr;
+};
+struct Conv3 {        // repacked [n_pad, kpad]
+  __half* w = nullptr;
+  __half* b = nullptr;
+  int cin = 0, cout = 0, n_pad = 0, kpad = 0;
+};
+struct ResnetP {
+  Norm norm1, norm2;
+  Conv3 conv1, conv2;
+  Lin shortcut;       // n == 0 when absent
+  int temb_off = 0;   // column offset into the stacked time_emb_proj output
+  int cin = 0, cout = 0;
+};
+struct SpatialP {
+  Norm norm, ln1, ln2, ln3;
+  Lin proj_in, qkv, out1, q2, out2, ff1, ff2, proj_out;
+  int kv2_off = 0;    // column offset of this block's [K|V] in the stacked cross-attention projection
+  int ff1_tile = 0;
+  int c = 0;
+};
+struct TemporalP {
+  Norm norm, ln[2], ff_norm;
+  Lin proj_in, qkv[2], out[2], ff1, ff2, proj_out;
+  __half* pe_tab[2] = {nullptr, nullptr};   // [L, 3C] = (q_pe | k_pe | v_pe)
+  int ff1_tile = 0;
+  int c = 0;
+};
+
+struct Scratch {
+  __half *cols = nullptr, *t = nullptr, *t0 = nullptr, *ln = nullptr, *att = nullptr, *qkv = nullptr, *ff = nullptr,
+         *q2 = nullptr, *h1 = nullptr, *sc = nullptr;
+  float* gn_ws = nullptr;
+};
+
+// Shared by the UNet engine and the stand-alone temporal module (B2)
+struct Core {
+  DevPool pool;
+  cudaStream_t st = nullptr;
+  int heads = 8, groups = 32, L = 16, n_rows = 2;
+  Scratch s;
+  int64_t launches_mark = 0;
+
+  int upload_copy(__half** dst, const __half* src, size_t n) {
+    RC(pool.halfs(dst, n));
+    L2D_CUDA(cudaMemcpyAsync(*dst, src, n * sizeof(__half), cudaMemcpyDeviceToDevice, st));
+    return L2D_OK;
+  }
+  int load_lin(const WeightTable& wt, const std::string& p, int n, int k, bool bias, Lin* out) {
+    const __half *w = nullptr, *b = nullptr;
+    RC(wt.get(p + ".weight", &w, (int64_t)n * k));
+    RC(upload_copy(&out->w, w, (size_t)n * k));
+    if (bias) {
+      RC(wt.get(p + ".bias", &b, n));
+      RC(upload_copy(&out->b, b, n));
+    }
+    out->n = n;
+    out->k = k;
+    return L2D_OK;
+  }
+  // concatenate several [n_i, k] matrices (no bias) into one [sum n_i, k]
+  int load_cat(const WeightTable& wt, const std::vector<std::string>& names, int n_each, int k, Lin* out) {
+    RC(pool.halfs(&out->w, (size_t)names.size() * n_each * k));
+    for (size_t i = 0; i < names.size(); ++i) {
+      const __half* w = nullptr;
+      RC(wt.get(names[i] + ".weight", &w, (int64_t)n_each * k));
+      L2D_CUDA(cudaMemcpyAsync(out->w + i * (size_t)n_each * k, w, (size_t)n_each * k * sizeof(__half),
+                               cudaMemcpyDeviceToDevice, st));
+    }
+    out->n = (int)names.size() * n_each;
+    out->k = k;
+    return L2D_OK;
+  }
+  int load_norm(const WeightTable& wt, const std::string& p, int c, Norm* out) {
+    const __half *g = nullptr, *b = nullptr;
+    RC(wt.get(p + ".weight", &g, c));
+    RC(wt.get(p + ".bias", &b, c));
+    RC(upload_copy(&out->g, g, c));
+    RC(upload_copy(&out->b, b, c));
+    return L2D_OK;
+  }
+  int load_conv3(const WeightTable& wt, const std::string& p, int cin, int cout, Conv3* out) {
+    const __half *w = nullptr, *b = nullptr;
+    RC(wt.get(p + ".weight", &w, (int64_t)cout * cin * 9));
+    RC(wt.get(p + ".bias", &b, cout));
+    out->cin = cin;
+    out->cout = cout;
+    out->n_pad = (cout + 7) / 8 * 8;
+    out->kpad = cin % 8 == 0 ? 9 * cin : 64;   // the 4-channel latent convs use the padded [.,64] im2col
+    if (cin % 8 != 0 && 9 * cin > 64) return fail(L2D_ERR_INVALID, "conv3x3 with Cin % 8 != 0 supports Cin <= 7 only");
+    RC(pool.halfs(&out->w, (size_t)out->n_pad * out->kpad));
+    RC(pool.halfs(&out->b, out->n_pad));
+    repack_conv3x3_kernel<<<256, 256, 0, st>>>(w, out->w, cout, cin, out->n_pad, out->kpad);
+    L2D_LAUNCH_CHECK();
+    pad_vec_kernel<<<ceil_div(out->n_pad, 128), 128, 0, st>>>(b, out->b, cout, out->n_pad);
+    L2D_LAUNCH_CHECK();
+    return L2D_OK;
+  }
+  // GEGLU projection: rows interleaved for the N tile the GEMM will pick for (m, 8C, C)
+  int load_geglu(const WeightTable& wt, const std::string& p, int c, int m, Lin* out, int* tile) {
+    const __half *w = nullptr, *b = nullptr;
+    RC(wt.get(p + ".weight", &w, (int64_t)8 * c * c));
+    RC(wt.get(p + ".bias", &b, 8 * c));
+    int bn = gemm_pick_tile_n(m, 8 * c, c);
+    while ((8 * c) % bn != 0 && bn > 64) bn = bn == 256 ? 160 : bn == 160 ? 128 : 64;
+    if ((8 * c) % bn != 0) return fail(L2D_ERR_INVALID, "GEGLU width " + std::to_string(8 * c) + " not tileable");
+    RC(pool.halfs(&out->w, (size_t)8 * c * c));
+    RC(pool.halfs(&out->b, (size_t)8 * c));
+    RC(l2d_geglu_interleave(w, b, out->w, out->b, 8 * c, c, bn, st));
+    out->n = 8 * c;
+    out->k = c;
+    *tile = bn;
+    return L2D_OK;
+  }
+
+  // ---- op wrappers -------------------------------------------------------------------------
+  int gemm(const __half* a, int64_t lda, const Lin& l, __half* out, int64_t ldo, int m, const __half* residual = nullptr,
+           int64_t ldr = 0, int act = L2D_ACT_NONE, int force_bn = 0) {
+    return gemm_launch(a, lda, l.w, l.k, out, ldo, m, l.n, l.k, l.b, nullptr, 0, 1, residual, ldr, act, force_bn, st);
+  }
+  int layernorm(const __half* x, const Norm& n, __half* y, int rows, int c) {
+    return l2d_layernorm(x, n.g, n.b, y, rows, c, 1e-5f, st);
+  }
+  int gn(const __half* x1, int c1, const __half* x2, int c2, const Norm& n, __half* y, int n_img, int h, int w, float eps,
+         int silu, int mode, int stride = 1) {
+    return groupnorm_launch(x1, c1, x2, c2, n.g, n.b, y, s.gn_ws, n_img, h, w, groups, eps, silu, mode, stride, st);
+  }
+
+  int temporal_load(const WeightTable& wt, const std::string& p, int c, int m_rows, TemporalP* t, const __half* pe_src_hint) {
+    (void)pe_src_hint;
+    t->c = c;
+    const std::string pp = p.empty() ? std::string() : p + ".";
+    RC(load_norm(wt, pp + "norm", c, &t->norm));
+    RC(load_lin(wt, pp + "proj_in", c, c, true, &t->proj_in));
+    const std::string b = pp + "transformer_blocks.0";
+    for (int i = 0; i < 2; ++i) {
+      const std::string a = b + ".attention_blocks." + std::to_string(i);
+      RC(load_cat(wt, {a + ".to_q", a + ".to_k", a + ".to_v"}, c, c, &t->qkv[i]));
+      RC(load_lin(wt, a + ".to_out.0", c, c, true, &t->out[i]));
+      RC(load_norm(wt, b + ".norms." + std::to_string(i), c, &t->ln[i]));
+      // prepare_pe_buffer (stream_motion_module.py:79-97): (q_pe|k_pe|v_pe) = pe[:L] @ [Wq;Wk;Wv]^T, an fp16 Linear
+      auto it = wt.by_name.find(a + ".pos_encoder.pe");
+      if (it == wt.by_name.end()) return fail(L2D_ERR_MISSING, "missing weight tensor '" + a + ".pos_encoder.pe'");
+      const l2d_tensor* pe = it->second;
+      if (pe->ndim != 3 || pe->shape[2] != c || pe->shape[1] < L)
+        return fail(L2D_ERR_INVALID, "'" + a + ".pos_encoder.pe' must be [1, max_len >= L, C]");
+      __half* pe_copy = nullptr;
+      RC(upload_copy(&pe_copy, static_cast<const __half*>(pe->data), (size_t)L * c));
+      RC(pool.halfs(&t->pe_tab[i], (size_t)L * 3 * c));
+      RC(gemm(pe_copy, c, t->qkv[i], t->pe_tab[i], 3 * c, L));
+    }
+    RC(load_geglu(wt, b + ".ff.net.0.proj", c, m_rows, &t->ff1, &t->ff1_tile));
+    RC(load_lin(wt, b + ".ff.net.2", c, 4 * c, true, &t->ff2));
+    RC(load_norm(wt, b + ".ff_norm", c, &t->ff_norm));
+    RC(load_lin(wt, pp + "proj_out", c, c, true, &t->proj_out));
+    return L2D_OK;
+  }
+
+  // x [M,C] channels-last -> out [M,C]  (motion_module.py:256-299, 401-435)
+  int temporal_forward(const TemporalP& t, const __half* x, __half* out, int h, int w, void* cache0, void* cache1,
+                       const __half* mask, const int64_t* pe_idx, const int64_t* update_idx) {
+    const int c = t.c, hw = h * w, m = n_rows * hw;
+    RC(gn(x, c, nullptr, 0, t.norm, s.t0, n_rows, h, w, 1e-6f, 0, 0));
+    RC(gemm(s.t0, c, t.proj_in, s.t, c, m));
+    void* caches[2] = {cache0, cache1};
+    for (int i = 0; i < 2; ++i) {
+      RC(layernorm(s.t, t.ln[i], s.ln, m, c));
+      RC(gemm(s.ln, c, t.qkv[i], s.qkv, 3 * c, m));
+      KvAttnParams p{};
+      p.q = s.qkv; p.k_new = s.qkv + c; p.v_new = s.qkv + 2 * c; p.ld = 3 * c;
+      p.cache = static_cast<__half*>(caches[i]);
+      p.q_pe = t.pe_tab[i]; p.k_pe = t.pe_tab[i] + c; p.v_pe = t.pe_tab[i] + 2 * c; p.pe_ld = 3 * c;
+      p.mask = mask; p.pe_idx = pe_idx; p.update_idx = update_idx; p.out = s.att;
+      p.n_rows = n_rows; p.hw = hw; p.L = L; p.C = c; p.heads = heads;
+      RC(kv_attn_launch(p, st));
+      RC(gemm(s.att, c, t.out[i], s.t, c, m, s.t, c));
+    }
+    RC(layernorm(s.t, t.ff_norm, s.ln, m, c));
+    RC(gemm(s.ln, c, t.ff1, s.ff, 4 * c, m, nullptr, 0, L2D_ACT_GEGLU, t.ff1_tile));
+    RC(gemm(s.ff, 4 * c, t.ff2, s.t, c, m, s.t, c));
+    RC(gemm(s.t, c, t.proj_out, out, c, m, x, c));
+    return L2D_OK;
+  }
+};
+
+}  // namespace l2d
+
+using namespace l2d;
+
+// =============================================================================================
+// B2: stand-alone TemporalTransformer3DModel
+// =============================================================================================
+struct l2d_tt {
+  Core core;
+  TemporalP p;
+  int c = 0, h = 0, w = 0;
+  __half *x_nhwc = nullptr, *y_nhwc = nullptr;
+};
+
+extern "C" int l2d_tt_create(l2d_tt** out, const l2d_tensor* weights, int n_weights, int channels, int heads, int groups,
+                             int window, int n_rows, int h, int w) {
+  L2D_CHECK_ARG(out && weights && n_weights > 0, "null arguments");
+  L2D_CHECK_ARG(channels % 8 == 0 && channels % heads == 0 && (channels / heads) % 8 == 0, "unsupported channel/head split");
+  L2D_CHECK_ARG(channels % groups == 0 && window > 0 && window <= 32 && n_rows > 0 && h > 0 && w > 0, "bad geometry");
+  std::unique_ptr<l2d_tt> t(new l2d_tt());
+  Core& k = t->core;
+  k.heads = heads; k.groups = groups; k.L = window; k.n_rows = n_rows;
+  t->c = channels; t->h = h; t->w = w;
+  const size_t m = (size_t)n_rows * h * w, c = channels;
+  RC(k.pool.halfs(&k.s.t, m * c));
+  RC(k.pool.halfs(&k.s.t0, m * c));
+  RC(k.pool.halfs(&k.s.ln, m * c));
+  RC(k.pool.halfs(&k.s.att, m * c));
+  RC(k.pool.halfs(&k.s.qkv, m * 3 * c));
+  RC(k.pool.halfs(&k.s.ff, m * 4 * c));
+  RC(k.pool.alloc(reinterpret_cast<void**>(&k.s.gn_ws), (size_t)l2d_groupnorm_workspace_bytes(n_rows, groups)));
+  RC(k.pool.halfs(&t->x_nhwc, m * c));
+  RC(k.pool.halfs(&t->y_nhwc, m * c));
+  WeightTable wt;
+  RC(wt.build(weights, n_weights));
+  RC(k.temporal_load(wt, "", channels, (int)m, &t->p, nullptr));
+  L2D_CUDA(cudaStreamSynchronize(k.st));
+  *out = t.release();
+  return L2D_OK;
+}
+
+extern "C" int l2d_tt_forward(l2d_tt* tt, const void* x_nchw, void* y_nchw, void* kv_cache0, void* kv_cache1,
+                              const void* mask, const int64_t* pe_idx, const int64_t* update_idx, void* stream) {
+  L2D_CHECK_ARG(tt && x_nchw && y_nchw && kv_cache0 && kv_cache1 && mask && pe_idx && update_idx, "null pointer");
+  Core& k = tt->core;
+  k.st = (cudaStream_t)stream;
+  const int hw = tt->h * tt->w;
+  RC(l2d_nchw_to_nhwc(x_nchw, tt->x_nhwc, k.n_rows, tt->c, hw, stream));
+  RC(k.temporal_forward(tt->p, tt->x_nhwc, tt->y_nhwc, tt->h, tt->w, kv_cache0, kv_cache1, (const __half*)mask, pe_idx,
+                        update_idx));
+  RC(l2d_nhwc_to_nchw(tt->y_nhwc, nullptr, y_nchw, k.n_rows, tt->c, hw, stream));
+  return L2D_OK;
+}
+
+extern "C" void l2d_tt_destroy(l2d_tt* tt) { delete tt; }
+
+// =============================================================================================
+// B1: the streaming UNet step
+// =============================================================================================
+struct Level {
+  int c, h, w, m;
+};
+
+struct l2d_unet {
+  Core core;
+  l2d_unet_config cfg{};
+  std::vector<Level> lv;
+  int temb_dim = 0, temb_total = 0;
+  // parameters
+  Conv3 conv_in, map_in, map_out, conv_out;
+  std::vector<Conv3> map_blocks;
+  Lin time1, time2, temb_all, kv2_all;
+  Norm norm_out;
+  std::vector<std::vector<ResnetP>> down_res, up_res;
+  std::vector<std::vector<SpatialP>> down_attn, up_attn;
+  std::vector<std::vector<TemporalP>> down_mm, up_mm;
+  std::vector<Conv3> down_samp, up_samp;
+  ResnetP mid_res[2];
+  SpatialP mid_attn;
+  // activations
+  std::vector<__half*> skips;
+  std::vector<int> skip_c;
+  __half *hA = nullptr, *hB = nullptr, *temb_sin = nullptr, *temb1 = nullptr, *emb = nullptr, *temb_proj = nullptr,
+         *kv2 = nullptr, *out8 = nullptr, *map_a = nullptr, *map_b = nullptr;
+  int n_kv = 0;
+  // CUDA graph
+  cudaGraphExec_t graph_exec = nullptr;
+  l2d_unet_step_args captured{};
+  std::vector<void*> captured_kv;
+  int steps_done = 0;
+  int64_t launches_per_step = 0;
+  ~l2d_unet() {
+    if (graph_exec) cudaGraphExecDestroy(graph_exec);
+  }
+};
+
+namespace {
+
+int load_resnet(l2d_unet* u, const WeightTable& wt, const std::string& p, int cin, int cout, ResnetP* r) {
+  Core& k = u->core;
+  r->cin = cin;
+  r->cout = cout;
+  RC(k.load_norm(wt, p + ".norm1", cin, &r->norm1));
+  RC(k.load_conv3(wt, p + ".conv1", cin, cout, &r->conv1));
+  RC(k.load_norm(wt, p + ".norm2", cout, &r->norm2));
+  RC(k.load_conv3(wt, p + ".conv2", cout, cout, &r->conv2));
+  if (cin != cout) RC(k.load_lin(wt, p + ".conv_shortcut", cout, cin, true, &r->shortcut));
+  return L2D_OK;
+}
+
+int load_spatial(l2d_unet* u, const WeightTable& wt, const std::string& p, int c, int m, SpatialP* s) {
+  Core& k = u->core;
+  const int cd = u->cfg.cross_attention_dim;
+  s->c = c;
+  RC(k.load_norm(wt, p + ".norm", c, &s->norm));
+  RC(k.load_lin(wt, p + ".proj_in", c, c, true, &s->proj_in));
+  const std::string b = p + ".transformer_blocks.0";
+  RC(k.load_cat(wt, {b + ".attn1.to_q", b + ".attn1.to_k", b + ".attn1.to_v"}, c, c, &s->qkv));
+  RC(k.load_lin(wt, b + ".attn1.to_out.0", c, c, true, &s->out1));
+  RC(k.load_norm(wt, b + ".norm1", c, &s->ln1));
+  RC(k.load_lin(wt, b + ".attn2.to_q", c, c, false, &s->q2));
+  RC(k.load_lin(wt, b + ".attn2.to_out.0", c, c, true, &s->out2));
+  RC(k.load_norm(wt, b + ".norm2", c, &s->ln2));
+  RC(k.load_geglu(wt, b + ".ff.net.0.proj", c, m, &s->ff1, &s->ff1_tile));
+  RC(k.load_lin(wt, b + ".ff.net.2", c, 4 * c, true, &s->ff2));
+  RC(k.load_norm(wt, b + ".norm3", c, &s->ln3));
+  RC(k.load_lin(wt, p + ".proj_out", c, c, true, &s->proj_out));
+  (void)cd;
+  return L2D_OK;
+}
+
+// conv3x3 as GEMM over an im2col matrix already in s.cols
+int conv_gemm(Core& k, const Conv3& cv, __half* out, int64_t ldo, int m, const __half* rg, int64_t rg_ld, int rpg,
+              const __half* residual, int64_t ldr, int act) {
+  return gemm_launch(k.s.cols, cv.kpad, cv.w, cv.kpad, out, ldo, m, cv.n_pad, cv.kpad, cv.b, rg, rg_ld, rpg, residual, ldr,
+                     act, 0, k.st);
+}
+
+// ResnetBlock3D.forward (resnet.py:229-259); input = concat(x1[M,c1], x2[M,c2]) channels-last
+int resnet_forward(l2d_unet* u, const ResnetP& r, const __half* x1, int c1, const __half* x2, int c2, __half* out,
+                   const Level& lv) {
+  Core& k = u->core;
+  const float eps = u->cfg.norm_eps;
+  const int n = k.n_rows, m = lv.m, hw = lv.h * lv.w;
+  RC(k.gn(x1, c1, x2, c2, r.norm1, k.s.cols, n, lv.h, lv.w, eps, 1, 1));
+  RC(conv_gemm(k, r.conv1, k.s.h1, r.cout, m, u->temb_proj + r.temb_off, u->temb_total, hw, nullptr, 0, L2D_ACT_NONE));
+  RC(k.gn(k.s.h1, r.cout, nullptr, 0, r.norm2, k.s.cols, n, lv.h, lv.w, eps, 1, 1));
+  const __half* res = x1;
+  int64_t ldr = c1;
+  if (r.shortcut.n) {
+    // 1x1 conv over the (virtual) channel concat: two K segments of the same weight matrix
+    RC(gemm_launch(x1, c1, r.shortcut.w, r.cin, k.s.sc, r.cout, m, r.cout, c1, r.shortcut.b, nullptr, 0, 1, nullptr, 0,
+                   L2D_ACT_NONE, 0, k.st));
+    if (c2 > 0)
+      RC(gemm_launch(x2, c2, r.shortcut.w + c1, r.cin, k.s.sc, r.cout, m, r.cout, c2, nullptr, nullptr, 0, 1, k.s.sc,
+                     r.cout, L2D_ACT_NONE, 0, k.st));
+    res = k.s.sc;
+    ldr = r.cout;
+  } else if (c2 > 0) {
+    return fail(L2D_ERR_INVALID, "resnet without shortcut cannot take a concatenated input");
+  }
+  RC(conv_gemm(k, r.conv2, out, r.cout, m, nullptr, 0, 1, res, ldr, L2D_ACT_NONE));
+  return L2D_OK;
+}
+
+// Transformer3DModel.forward + BasicTransformerBlock.forward (attention.py:91-135, 221-270)
+int spatial_forward(l2d_unet* u, const SpatialP& sp, const __half* x, __half* out, const Level& lv) {
+  Core& k = u->core;
+  Scratch& s = k.s;
+  const int c = sp.c, m = lv.m, hw = lv.h * lv.w, n = k.n_rows, heads = k.heads, hd = c / heads;
+  const int ctx = u->cfg.ctx_len;
+  RC(k.gn(x, c, nullptr, 0, sp.norm, s.t0, n, lv.h, lv.w, 1e-6f, 0, 0));
+  RC(k.gemm(s.t0, c, sp.proj_in, s.t, c, m));
+  // self-attention
+  RC(k.layernorm(s.t, sp.ln1, s.ln, m, c));
+  RC(k.gemm(s.ln, c, sp.qkv, s.qkv, 3 * c, m));
+  RC(attention_launch(s.qkv, 3 * c, s.qkv + c, 3 * c, s.qkv + 2 * c, 3 * c, s.att, c, n, heads, hw, hw, hd, k.st));
+  RC(k.gemm(s.att, c, sp.out1, s.t, c, m, s.t, c));
+  // cross-attention against the (pre-projected) text context
+  RC(k.layernorm(s.t, sp.ln2, s.ln, m, c));
+  RC(k.gemm(s.ln, c, sp.q2, s.q2, c, m));
+  const __half* kv = u->kv2 + sp.kv2_off;
+  RC(attention_launch(s.q2, c, kv, u->kv2_all.n, kv + c, u->kv2_all.n, s.att, c, n, heads, hw, ctx, hd, k.st));
+  RC(k.gemm(s.att, c, sp.out2, s.t, c, m, s.t, c));
+  // feed-forward
+  RC(k.layernorm(s.t, sp.ln3, s.ln, m, c));
+  RC(k.gemm(s.ln, c, sp.ff1, s.ff, 4 * c, m, nullptr, 0, L2D_ACT_GEGLU, sp.ff1_tile));
+  RC(k.gemm(s.ff, 4 * c, sp.ff2, s.t, c, m, s.t, c));
+  RC(k.gemm(s.t, c, sp.proj_out, out, c, m, x, c));
+  return L2D_OK;
+}
+
+int run_step(l2d_unet* u, const l2d_unet_step_args* a) {
+  Core& k = u->core;
+  Scratch& s = k.s;
+  const l2d_unet_config& cfg = u->cfg;
+  const int n = k.n_rows, nlev = cfg.n_levels;
+  const __half* mask = static_cast<const __half*>(a->temporal_attention_mask);
+  cudaStream_t st = k.st;
+
+  // time embedding (unet_depth_streaming.py:497-505) and every resnet's time_emb_proj(SiLU(emb)) (resnet.py:237-238)
+  RC(l2d_timestep_embedding(a->timestep, u->temb_sin, n, cfg.block_out_channels[0], st));
+  RC(l2d_small_linear(u->temb_sin, u->time1.w, u->time1.b, u->temb1, n, u->time1.n, u->time1.k, 0, 1, st));
+  RC(l2d_small_linear(u->temb1, u->time2.w, u->time2.b, u->emb, n, u->time2.n, u->time2.k, 0, 0, st));
+  RC(l2d_small_linear(u->emb, u->temb_all.w, u->temb_all.b, u->temb_proj, n, u->temb_all.n, u->temb_all.k, 1, 0, st));
+  // K|V projections of the text context for all 16 cross-attention blocks in one GEMM
+  RC(k.gemm(static_cast<const __half*>(a->encoder_hidden_states), cfg.cross_attention_dim, u->kv2_all, u->kv2,
+            u->kv2_all.n, n * cfg.ctx_len));
+
+  // conv_in + depth mapping network (:523-526; resnet.py:44-54)
+  const Level& l0 = u->lv[0];
+  __half* x = u->hA;
+  __half* y = u->hB;
+  RC(l2d_im2col3x3_nchw4(a->sample, s.cols, n, l0.h, l0.w, st));
+  RC(conv_gemm(k, u->conv_in, x, l0.c, l0.m, nullptr, 0, 1, nullptr, 0, L2D_ACT_NONE));
+  {
+    RC(l2d_im2col3x3_nchw4(a->depth_sample, s.cols, n, l0.h, l0.w, st));
+    __half* cur = u->map_a;
+    __half* nxt = u->map_b;
+    RC(conv_gemm(k, u->map_in, cur, u->map_in.n_pad, l0.m, nullptr, 0, 1, nullptr, 0, L2D_ACT_SILU));
+    int cc = u->map_in.n_pad;
+    for (const Conv3& cv : u->map_blocks) {
+      RC(l2d_im2col3x3(cur, s.cols, n, l0.h, l0.w, cc, 1, 0, 0, st));
+      RC(conv_gemm(k, cv, nxt, cv.n_pad, l0.m, nullptr, 0, 1, nullptr, 0, L2D_ACT_SILU));
+      std::swap(cur, nxt);
+      cc = cv.n_pad;
+    }
+    RC(l2d_im2col3x3(cur, s.cols, n, l0.h, l0.w, cc, 1, 0, 0, st));
+    RC(conv_gemm(k, u->map_out, x, l0.c, l0.m, nullptr, 0, 1, x, l0.c, L2D_ACT_NONE));   // sample += mapping(depth)
+  }
+
+  int kv_i = 0, skip_i = 0;
+  auto push_skip = [&](const __half* src, const Level& lvl) -> int {
+    L2D_CUDA(cudaMemcpyAsync(u->skips[skip_i], src, (size_t)lvl.m * lvl.c * sizeof(__half), cudaMemcpyDeviceToDevice, st));
+    count_launch();
+    ++skip_i;
+    return L2D_OK;
+  };
+  RC(push_skip(x, l0));
+
+  // ---- down (:529-553) ----
+  for (int bi = 0; bi < nlev; ++bi) {
+    const Level& lvl = u->lv[bi];
+    for (int li = 0; li < cfg.layers_per_block; ++li) {
+      const ResnetP& r = u->down_res[bi][li];
+      RC(resnet_forward(u, r, x, r.cin, nullptr, 0, y, lvl));
+      std::swap(x, y);
+      if (cfg.down_has_attn[bi]) {
+        RC(spatial_forward(u, u->down_attn[bi][li], x, y, lvl));
+        std::swap(x, y);
+      }
+      RC(k.temporal_forward(u->down_mm[bi][li], x, y, lvl.h, lvl.w, a->kv_cache[kv_i], a->kv_cache[kv_i + 1], mask,
+                            a->pe_idx, a->update_idx));
+      kv_i += 2;
+      std::swap(x, y);
+      RC(push_skip(x, lvl));
+    }
+    if (bi != nlev - 1) {
+      const Level& nl = u->lv[bi + 1];
+      RC(l2d_im2col3x3(x, s.cols, n, lvl.h, lvl.w, lvl.c, 2, 0, 0, st));
+      RC(conv_gemm(k, u->down_samp[bi], y, lvl.c, nl.m, nullptr, 0, 1, nullptr, 0, L2D_ACT_NONE));
+      std::swap(x, y);
+      Level ds{lvl.c, nl.h, nl.w, nl.m};
+      RC(push_skip(x, ds));
+    }
+  }
+
+  // ---- mid (:564-573) ----
+  {
+    const Level& lvl = u->lv[nlev - 1];
+    RC(resnet_forward(u, u->mid_res[0], x, lvl.c, nullptr, 0, y, lvl));
+    std::swap(x, y);
+    RC(spatial_forward(u, u->mid_attn, x, y, lvl));
+    std::swap(x, y);
+    RC(resnet_forward(u, u->mid_res[1], x, lvl.c, nullptr, 0, y, lvl));
+    std::swap(x, y);
+  }
+
+  // ---- up (:582-617) ----
+  int cur_c = u->lv[nlev - 1].c;
+  for (int bi = 0; bi < nlev; ++bi) {
+    const Level& lvl = u->lv[nlev - 1 - bi];
+    for (int li = 0; li < cfg.layers_per_block + 1; ++li) {
+      --skip_i;
+      const ResnetP& r = u->up_res[bi][li];
+      if (cur_c + u->skip_c[skip_i] != r.cin) return fail(L2D_ERR_INVALID, "internal: skip-connection channel mismatch");
+      RC(resnet_forward(u, r, x, cur_c, u->skips[skip_i], u->skip_c[skip_i], y, lvl));
+      std::swap(x, y);
+      cur_c = r.cout;
+      if (cfg.up_has_attn[bi]) {
+        RC(spatial_forward(u, u->up_attn[bi][li], x, y, lvl));
+        std::swap(x, y);
+      }
+      RC(k.temporal_forward(u->up_mm[bi][li], x, y, lvl.h, lvl.w, a->kv_cache[kv_i], a->kv_cache[kv_i + 1], mask,
+                            a->pe_idx, a->update_idx));
+      kv_i += 2;
+      std::swap(x, y);
+    }
+    if (bi != nlev - 1) {
+      const Level& nl = u->lv[nlev - 2 - bi];
+      RC(l2d_im2col3x3(x, s.cols, n, lvl.h, lvl.w, lvl.c, 1, 1, 0, st));
+      RC(conv_gemm(k, u->up_samp[bi], y, lvl.c, nl.m, nullptr, 0, 1, nullptr, 0, L2D_ACT_NONE));
+      std::swap(x, y);
+    }
+  }
+  if (skip_i != 0 || kv_i != u->n_kv) return fail(L2D_ERR_INVALID, "internal: topology bookkeeping mismatch");
+
+  // ---- post-process (:620-622) ----
+  RC(k.gn(x, l0.c, nullptr, 0, u->norm_out, s.cols, n, l0.h, l0.w, cfg.norm_eps, 1, 1));
+  RC(conv_gemm(k, u->conv_out, u->out8, u->conv_out.n_pad, l0.m, nullptr, 0, 1, nullptr, 0, L2D_ACT_NONE));
+  const int total = n * l0.h * l0.w * u->conv_out.cout;
+  nhwc_to_nchw4_kernel<<<ceil_div(total, 256), 256, 0, st>>>(u->out8, static_cast<__half*>(a->out_sample), n, l0.h * l0.w,
+                                                            u->conv_out.n_pad, u->conv_out.cout);
+  L2D_LAUNCH_CHECK();
+  return L2D_OK;
+}
+
+}  // namespace
+
+extern "C" int l2d_unet_create(l2d_unet** out, const l2d_unet_config* cfg, const l2d_tensor* weights, int n_weights) {
+  L2D_CHECK_ARG(out && cfg && weights && n_weights > 0, "null arguments");
+  L2D_CHECK_ARG(cfg->n_levels >= 1 && cfg->n_levels <= 8 && cfg->layers_per_block >= 1, "bad topology");
+  L2D_CHECK_ARG(cfg->n_rows >= 1 && cfg->n_rows <= 8, "n_rows must be in 1..8");
+  L2D_CHECK_ARG(cfg->window >= 1 && cfg->window <= 32, "window must be in 1..32");
+  L2D_CHECK_ARG(cfg->latent_h % (1 << (cfg->n_levels - 1)) == 0 && cfg->latent_w % (1 << (cfg->n_levels - 1)) == 0,
+                "latent size must be divisible by 2^(levels-1)");
+  L2D_CHECK_ARG(cfg->n_mapping >= 1 && cfg->n_mapping <= 8, "bad mapping network");
+  for (int i = 0; i < cfg->n_levels; ++i) {
+    const int c = cfg->block_out_channels[i];
+    L2D_CHECK_ARG(c % 8 == 0 && c % cfg->groups == 0 && c % cfg->heads == 0 && (c / cfg->heads) % 8 == 0 &&
+                      (c / cfg->groups) % 2 == 0,
+                  "unsupported channel count at a level");
+  }
+  L2D_CHECK_ARG(cfg->cross_attention_dim % 8 == 0, "cross_attention_dim % 8 != 0");
+  std::unique_ptr<l2d_unet> u(new l2d_unet());
+  u->cfg = *cfg;
+  Core& k = u->core;
+  k.heads = cfg->heads; k.groups = cfg->groups; k.L = cfg->window; k.n_rows = cfg->n_rows;
+  const int nlev = cfg->n_levels, n = cfg->n_rows, lpb = cfg->layers_per_block;
+  for (int i = 0; i < nlev; ++i) {
+    Level l{cfg->block_out_channels[i], cfg->latent_h >> i, cfg->latent_w >> i, 0};
+    l.m = n * l.h * l.w;
+    u->lv.push_back(l);
+  }
+  u->temb_dim = 4 * cfg->block_out_channels[0];
+
+  // ---- workspace sizing ----
+  size_t max_mc = 0, max_cols = (size_t)u->lv[0].m * 64, max_map = 0;
+  for (int i = 0; i < nlev; ++i) {
+    const Level& l = u->lv[i];
+    max_mc = std::max(max_mc, (size_t)l.m * l.c);
+    // widest conv input at this level: the up-block concat (<= 2x the widest neighbour), conservatively 2*max(c_i, c_{i+1}) + c
+    const int cn = cfg->block_out_channels[std::min(i + 1, nlev - 1)];
+    const int cp = cfg->block_out_channels[std::max(i - 1, 0)];
+    const int cmax = std::max(std::max(l.c + cn, l.c + l.c), l.c + cp);
+    max_cols = std::max(max_cols, (size_t)l.m * 9 * cmax);
+  }
+  for (int i = 0; i < cfg->n_mapping; ++i) {
+    const int c8 = (cfg->mapping_channels[i] + 7) / 8 * 8;
+    max_map = std::max(max_map, (size_t)u->lv[0].m * c8);
+    max_cols = std::max(max_cols, (size_t)u->lv[0].m * 9 * c8);
+  }
+  Scratch& s = k.s;
+  RC(k.pool.halfs(&s.cols, max_cols));
+  RC(k.pool.halfs(&s.t, max_mc));
+  RC(k.pool.halfs(&s.t0, max_mc));
+  RC(k.pool.halfs(&s.ln, max_mc));
+  RC(k.pool.halfs(&s.att, max_mc));
+  RC(k.pool.halfs(&s.q2, max_mc));
+  RC(k.pool.halfs(&s.h1, max_mc));
+  RC(k.pool.halfs(&s.sc, max_mc));
+  RC(k.pool.halfs(&s.qkv, max_mc * 3));
+  RC(k.pool.halfs(&s.ff, max_mc * 4));
+  RC(k.pool.alloc(reinterpret_cast<void**>(&s.gn_ws), (size_t)l2d_groupnorm_workspace_bytes(n, cfg->groups)));
+  RC(k.pool.halfs(&u->hA, max_mc));
+  RC(k.pool.halfs(&u->hB, max_mc));
+  RC(k.pool.halfs(&u->map_a, max_map));
+  RC(k.pool.halfs(&u->map_b, max_map));
+  RC(k.pool.halfs(&u->temb_sin, (size_t)n * cfg->block_out_channels[0]));
+  RC(k.pool.halfs(&u->temb1, (size_t)n * u->temb_dim));
+  RC(k.pool.halfs(&u->emb, (size_t)n * u->temb_dim));
+
+  WeightTable wt;
+  RC(wt.build(weights, n_weights));
+  const int* c = cfg->block_out_channels;
+
+  // ---- parameters ----
+  RC(k.load_conv3(wt, "conv_in", 4, c[0], &u->conv_in));
+  RC(k.load_conv3(wt, "flow_conv_in.conv_in", 4, cfg->mapping_channels[0], &u->map_in));
+  for (int i = 0; i + 1 < cfg->n_mapping; ++i) {
+    Conv3 a, b;
+    const int ci = (cfg->mapping_channels[i] + 7) / 8 * 8, co = cfg->mapping_channels[i + 1];
+    if (ci != cfg->mapping_channels[i]) return fail(L2D_ERR_INVALID, "mapping channels must be multiples of 8");
+    RC(k.load_conv3(wt, "flow_conv_in.blocks." + std::to_string(2 * i), ci, ci, &a));
+    RC(k.load_conv3(wt, "flow_conv_in.blocks." + std::to_string(2 * i + 1), ci, co, &b));
+    u->map_blocks.push_back(a);
+    u->map_blocks.push_back(b);
+  }
+  RC(k.load_conv3(wt, "flow_conv_in.conv_out", cfg->mapping_channels[cfg->n_mapping - 1], c[0], &u->map_out));
+  RC(k.load_lin(wt, "time_embedding.linear_1", u->temb_dim, c[0], true, &u->time1));
+  RC(k.load_lin(wt, "time_embedding.linear_2", u->temb_dim, u->temb_dim, true, &u->time2));
+
+  std::vector<std::pair<std::string, ResnetP*>> all_res;       // for the stacked time_emb_proj
+  std::vector<std::pair<std::string, SpatialP*>> all_spatial;  // for the stacked cross-attention K|V projection
+  u->down_res.resize(nlev); u->down_attn.resize(nlev); u->down_mm.resize(nlev);
+  u->up_res.resize(nlev); u->up_attn.resize(nlev); u->up_mm.resize(nlev);
+  u->down_samp.resize(nlev); u->up_samp.resize(nlev);
+  // reserve so the pointers collected below stay valid
+  for (int bi = 0; bi < nlev; ++bi) {
+    u->down_res[bi].resize(lpb); u->down_mm[bi].resize(lpb);
+    if (cfg->down_has_attn[bi]) u->down_attn[bi].resize(lpb);
+    u->up_res[bi].resize(lpb + 1); u->up_mm[bi].resize(lpb + 1);
+    if (cfg->up_has_attn[bi]) u->up_attn[bi].resize(lpb + 1);
+  }
+  // skip-connection channel bookkeeping mirrors down_block_res_samples (:529-553)
+  u->skip_c.push_back(c[0]);
+  int out_ch = c[0];
+  for (int bi = 0; bi < nlev; ++bi) {
+    const int in_ch = out_ch;
+    out_ch = c[bi];
+    const Level& lvl = u->lv[bi];
+    const std::string bp = "down_blocks." + std::to_string(bi);
+    for (int li = 0; li < lpb; ++li) {
+      const std::string rp = bp + ".resnets." + std::to_string(li);
+      RC(load_resnet(u.get(), wt, rp, li == 0 ? in_ch : out_ch, out_ch, &u->down_res[bi][li]));
+      all_res.push_back({rp, &u->down_res[bi][li]});
+      if (cfg->down_has_attn[bi]) {
+        const std::string ap = bp + ".attentions." + std::to_string(li);
+        RC(load_spatial(u.get(), wt, ap, out_ch, lvl.m, &u->down_attn[bi][li]));
+        all_spatial.push_back({ap, &u->down_attn[bi][li]});
+      }
+      RC(k.temporal_load(wt, bp + ".motion_modules." + std::to_string(li) + ".temporal_transformer", out_ch, lvl.m,
+                         &u->down_mm[bi][li], nullptr));
+      u->skip_c.push_back(out_ch);
+    }
+    if (bi != nlev - 1) {
+      RC(k.load_conv3(wt, bp + ".downsamplers.0.conv", out_ch, out_ch, &u->down_samp[bi]));
+      u->skip_c.push_back(out_ch);
+    }
+  }
+  {
+    const Level& lvl = u->lv[nlev - 1];
+    RC(load_resnet(u.get(), wt, "mid_block.resnets.0", lvl.c, lvl.c, &u->mid_res[0]));
+    RC(load_resnet(u.get(), wt, "mid_block.resnets.1", lvl.c, lvl.c, &u->mid_res[1]));
+    all_res.push_back({"mid_block.resnets.0", &u->mid_res[0]});
+    all_res.push_back({"mid_block.resnets.1", &u->mid_res[1]});
+    RC(load_spatial(u.get(), wt, "mid_block.attentions.0", lvl.c, lvl.m, &u->mid_attn));
+    all_spatial.push_back({"mid_block.attentions.0", &u->mid_attn});
+  }
+  {
+    out_ch = c[nlev - 1];
+    for (int bi = 0; bi < nlev; ++bi) {
+      const int prev_out = out_ch;
+      out_ch = c[nlev - 1 - bi];
+      const int in_ch = c[std::max(nlev - 2 - bi, 0)];
+      const Level& lvl = u->lv[nlev - 1 - bi];
+      const std::string bp = "up_blocks." + std::to_string(bi);
+      for (int li = 0; li < lpb + 1; ++li) {
+        const int skip = li == lpb ? in_ch : out_ch;
+        const int rin = li == 0 ? prev_out : out_ch;
+        const std::string rp = bp + ".resnets." + std::to_string(li);
+        RC(load_resnet(u.get(), wt, rp, rin + skip, out_ch, &u->up_res[bi][li]));
+        all_res.push_back({rp, &u->up_res[bi][li]});
+        if (cfg->up_has_attn[bi]) {
+          const std::string ap = bp + ".attentions." + std::to_string(li);
+          RC(load_spatial(u.get(), wt, ap, out_ch, lvl.m, &u->up_attn[bi][li]));
+          all_spatial.push_back({ap, &u->up_attn[bi][li]});
+        }
+        RC(k.temporal_load(wt, bp + ".motion_modules." + std::to_string(li) + ".temporal_transformer", out_ch, lvl.m,
+                           &u->up_mm[bi][li], nullptr));
+      }
+      if (bi != nlev - 1) RC(k.load_conv3(wt, bp + ".upsamplers.0.conv", out_ch, out_ch, &u->up_samp[bi]));
+    }
+  }
+  RC(k.load_norm(wt, "conv_norm_out", c[0], &u->norm_out));
+  RC(k.load_conv3(wt, "conv_out", c[0], 4, &u->conv_out));
+  RC(k.pool.halfs(&u->out8, (size_t)u->lv[0].m * u->conv_out.n_pad));
+
+  // stacked time_emb_proj: [sum Cout, temb_dim]
+  {
+    int total = 0;
+    for (auto& pr : all_res) {
+      pr.second->temb_off = total;
+      total += pr.second->cout;
+    }
+    u->temb_total = total;
+    RC(k.pool.halfs(&u->temb_all.w, (size_t)total * u->temb_dim));
+    RC(k.pool.halfs(&u->temb_all.b, total));
+    u->temb_all.n = total;
+    u->temb_all.k = u->temb_dim;
+    for (auto& pr : all_res) {
+      const __half *w = nullptr, *b = nullptr;
+      RC(wt.get(pr.first + ".time_emb_proj.weight", &w, (int64_t)pr.second->cout * u->temb_dim));
+      RC(wt.get(pr.first + ".time_emb_proj.bias", &b, pr.second->cout));
+      L2D_CUDA(cudaMemcpyAsync(u->temb_all.w + (size_t)pr.second->temb_off * u->temb_dim, w,
+                               (size_t)pr.second->cout * u->temb_dim * sizeof(__half), cudaMemcpyDeviceToDevice, k.st));
+      L2D_CUDA(cudaMemcpyAsync(u->temb_all.b + pr.second->temb_off, b, pr.second->cout * sizeof(__half),
+                               cudaMemcpyDeviceToDevice, k.st));
+    }
+    RC(k.pool.halfs(&u->temb_proj, (size_t)n * total));
+  }
+  // stacked cross-attention [to_k; to_v] of every spatial block: [sum 2C, cross_dim]
+  {
+    const int cd = cfg->cross_attention_dim;
+    int total = 0;
+    for (auto& pr : all_spatial) {
+      pr.second->kv2_off = total;
+      total += 2 * pr.second->c;
+    }
+    RC(k.pool.halfs(&u->kv2_all.w, (size_t)std::max(total, 8) * cd));
+    u->kv2_all.n = total;
+    u->kv2_all.k = cd;
+    for (auto& pr : all_spatial) {
+      const __half *wk = nullptr, *wv = nullptr;
+      const std::string b = pr.first + ".transformer_blocks.0.attn2";
+      const int cc = pr.second->c;
+      RC(wt.get(b + ".to_k.weight", &wk, (int64_t)cc * cd));
+      RC(wt.get(b + ".to_v.weight", &wv, (int64_t)cc * cd));
+      L2D_CUDA(cudaMemcpyAsync(u->kv2_all.w + (size_t)pr.second->kv2_off * cd, wk, (size_t)cc * cd * sizeof(__half),
+                               cudaMemcpyDeviceToDevice, k.st));
+      L2D_CUDA(cudaMemcpyAsync(u->kv2_all.w + (size_t)(pr.second->kv2_off + cc) * cd, wv, (size_t)cc * cd * sizeof(__half),
+                               cudaMemcpyDeviceToDevice, k.st));
+    }
+    RC(k.pool.halfs(&u->kv2, (size_t)n * cfg->ctx_len * std::max(total, 8)));
+  }
+  // skip buffers
+  {
+    int lvl_i = 0, cnt = 0;
+    std::vector<size_t> sizes;
+    sizes.push_back((size_t)u->lv[0].m * c[0]);
+    for (int bi = 0; bi < nlev; ++bi) {
+      for (int li = 0; li < lpb; ++li) sizes.push_back((size_t)u->lv[bi].m * c[bi]);
+      if (bi != nlev - 1) sizes.push_back((size_t)u->lv[bi + 1].m * c[bi]);
+    }
+    (void)lvl_i; (void)cnt;
+    if (sizes.size() != u->skip_c.size()) return fail(L2D_ERR_INVALID, "internal: skip bookkeeping");
+    for (size_t sz : sizes) {
+      __half* p = nullptr;
+      RC(k.pool.halfs(&p, sz));
+      u->skips.push_back(p);
+    }
+  }
+  u->n_kv = 2 * (nlev * lpb + nlev * (lpb + 1));
+  L2D_CUDA(cudaStreamSynchronize(k.st));
+  L2D_CUDA(cudaGetLastError());
+  *out = u.release();
+  return L2D_OK;
+}
+
+extern "C" int l2d_unet_step(l2d_unet* u, const l2d_unet_step_args* a, void* stream) {
+  L2D_CHECK_ARG(u && a, "null arguments");
+  L2D_CHECK_ARG(a->sample && a->timestep && a->encoder_hidden_states && a->temporal_attention_mask && a->depth_sample &&
+                    a->kv_cache && a->pe_idx && a->update_idx && a->out_sample,
+                "null tensor pointer in step args");
+  L2D_CHECK_ARG(a->n_kv == u->n_kv, "expected " + std::to_string(u->n_kv) + " kv-cache tensors");
+  for (int i = 0; i < a->n_kv; ++i) L2D_CHECK_ARG(a->kv_cache[i] != nullptr, "null kv-cache pointer");
+  Core& k = u->core;
+  k.st = (cudaStream_t)stream;
+  const int64_t l0 = l2d_launch_count();
+  if (!u->cfg.use_cuda_graph || u->steps_done == 0) {
+    // eager (the first step always is: it sizes smem attributes and fills the tensor-map cache)
+    RC(run_step(u, a));
+    u->launches_per_step = l2d_launch_count() - l0;
+    ++u->steps_done;
+    return L2D_OK;
+  }
+  bool same = u->graph_exec != nullptr && u->captured.sample == a->sample && u->captured.timestep == a->timestep &&
+              u->captured.encoder_hidden_states == a->encoder_hidden_states &&
+              u->captured.temporal_attention_mask == a->temporal_attention_mask &&
+              u->captured.depth_sample == a->depth_sample && u->captured.pe_idx == a->pe_idx &&
+              u->captured.update_idx == a->update_idx && u->captured.out_sample == a->out_sample &&
+              (int)u->captured_kv.size() == a->n_kv;
+  for (int i = 0; same && i < a->n_kv; ++i) same = u->captured_kv[i] == a->kv_cache[i];
+  if (!same) {
+    if (u->graph_exec) {
+      cudaGraphExecDestroy(u->graph_exec);
+      u->graph_exec = nullptr;
+    }
+    cudaGraph_t graph = nullptr;
+    L2D_CUDA(cudaStreamBeginCapture(k.st, cudaStreamCaptureModeThreadLocal));
+    const int rc = run_step(u, a);
+    cudaError_t e = cudaStreamEndCapture(k.st, &graph);
+    if (rc != L2D_OK) {
+      if (graph) cudaGraphDestroy(graph);
+      return rc;
+    }
+    if (e != cudaSuccess) return fail(L2D_ERR_CUDA, std::string("cudaStreamEndCapture: ") + cudaGetErrorString(e));
+    e = cudaGraphInstantiate(&u->graph_exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (e != cudaSuccess) return fail(L2D_ERR_CUDA, std::string("cudaGraphInstantiate: ") + cudaGetErrorString(e));
+    u->captured = *a;
+    u->captured_kv.assign(a->kv_cache, a->kv_cache + a->n_kv);
+    u->launches_per_step = l2d_launch_count() - l0;
+    count_launch(-(int)u->launches_per_step);   // capture enqueued nothing; the replay below is what runs
+  }
+  L2D_CUDA(cudaGraphLaunch(u->graph_exec, k.st));
+  count_launch((int)u->launches_per_step);
+  ++u->steps_done;
+  return L2D_OK;
+}
+
+extern "C" int64_t l2d_unet_device_bytes(const l2d_unet* u) { return u ? u->core.pool.bytes : 0; }
+extern "C" int64_t l2d_unet_launches_per_step(const l2d_unet* u) { return u ? u->launches_per_step : 0; }
+extern "C" void l2d_unet_destroy(l2d_unet* u) { delete u; }

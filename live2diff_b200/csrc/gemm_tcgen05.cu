@@ -1,0 +1,468 @@
+// K7 (and, through im2col, K4) -- fp16 GEMM on the 5th-gen tensor cores:
+//     out[M,N] = epilogue( A[M,K] . W[N,K]^T ),  fp32 accumulation in TMEM.
+//
+// Covers every dense contraction of the UNet step: nn.Linear (to_q/k/v, to_out, proj_in/out, GEGLU
+// FF -- attention.py:173-205, motion_module.py:182-199,360; stream_motion_module.py:105-107,206),
+// 1x1 convs (attention.py:62,87; resnet.py:227) and, fed by the im2col kernels, the 3x3 convs of
+// resnet.py:57-65,92,141,194,214.
+//
+// Structure (one 128 x BN output tile per CTA, 192 threads):
+//   warp 0   : TMA producer  -- cp.async.bulk.tensor 2D loads of A[128x64] and W[BNx64] tiles
+//              (128B swizzle) into a STAGES-deep shared-memory ring, mbarrier complete_tx
+//   warp 1   : TMEM allocator + MMA issuer -- one elected lane issues tcgen05.mma.cta_group::1
+//              .kind::f16 (M=128, N=BN, K=16) from shared-memory descriptors; tcgen05.commit
+//              releases ring slots and finally signals the accumulator-ready barrier
+//   warps 2-5: epilogue -- tcgen05.ld 32x32b TMEM -> registers, fused bias / per-image bias (temb) /
+//              SiLU / GEGLU / residual, 128-bit global stores
+// Partial tiles rely on TMA out-of-bounds zero fill (loads) and predicated stores.
+#include <cuda.h>
+
+#include <mutex>
+#include <unordered_map>
+
+#include "ops.cuh"
+
+namespace l2d {
+
+constexpr int BM = 128;
+constexpr int BK = 64;  // 64 fp16 = 128 B = one swizzle-128B row
+
+// ---------------------------------------------------------------------------------------------
+// PTX wrappers
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done = 0;
+  uint32_t spins = 0;
+  long long t0 = 0;
+  while (true) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (done) break;
+    // never hang the GPU: a protocol bug becomes a launch failure after ~2 s
+    if ((++spins & 1023u) == 0) {
+      const long long now = clock64();
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > 4000000000ll) __trap();
+    }
+  }
+}
+__device__ __forceinline__ void fence_barrier_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+
+__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t cols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(cols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t addr, uint32_t cols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(cols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                         uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t addr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(addr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major, 128B-swizzled operand tile descriptor (cute::UMMA::SmemDescriptor bit layout):
+//   [0,14) start address >> 4 | [16,30) LBO >> 4 (unused for swizzled K-major) | [32,46) SBO >> 4 = 1024 B
+//   (8 rows x 128 B) | [46,48) version = 1 | [61,64) layout = SWIZZLE_128B (2)
+__device__ __forceinline__ uint64_t make_sw128_desc(uint32_t smem_addr) {
+  uint64_t d = (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= 1ull << 46;
+  d |= 2ull << 61;
+  return d;
+}
+// cute::UMMA::InstrDescriptor: c_format F32 (1) @4, a/b format F16 (0) @7/@10, a/b K-major (0) @15/@16,
+// N >> 3 @17, M >> 4 @24
+__host__ __device__ constexpr uint32_t make_idesc(int n) {
+  return (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+}
+
+// ---------------------------------------------------------------------------------------------
+struct GemmEpilogue {
+  __half* out;
+  int64_t ldo;
+  const __half* bias;           // [N] or null
+  const __half* rowgroup_bias;  // [M / rows_per_group, >=N] or null
+  int64_t rg_ld;
+  int rows_per_group;
+  const __half* residual;       // [M, ldr] or null
+  int64_t ldr;
+  int act;
+};
+
+template <int BN>
+struct GemmSmem {
+  static constexpr int A_BYTES = BM * BK * 2;
+  static constexpr int B_BYTES = BN * BK * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+};
+
+__device__ __forceinline__ void epi_store16(const GemmEpilogue& e, float (&v)[16], int row, int col0, int M, int n_out,
+                                            bool row_ok) {
+  // v: activated accumulator values for output columns col0 .. col0+15 of `row`
+  if (!row_ok) return;
+#pragma unroll
+  for (int hlf = 0; hlf < 2; ++hlf) {
+    const int col = col0 + hlf * 8;
+    if (col < n_out) {
+      float o[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) o[i] = v[hlf * 8 + i];
+      if (e.residual) {
+        float r[8];
+        // plain (coherent) load: the residual may alias `out` (in-place  h += f(h))
+        unpack8(*reinterpret_cast<const uint4*>(e.residual + (size_t)row * e.ldr + col), r);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) o[i] += r[i];
+      }
+      *reinterpret_cast<uint4*>(e.out + (size_t)row * e.ldo + col) = pack8(o);
+    }
+  }
+}
+
+template <int BN, int STAGES>
+__global__ void __launch_bounds__(192, 1)
+gemm_f16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                        const GemmEpilogue epi, int M, int N, int K) {
+  using S = GemmSmem<BN>;
+  constexpr uint32_t TMEM_COLS = BN <= 32 ? 32 : BN <= 64 ? 64 : BN <= 128 ? 128 : 256;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  // 1024 B alignment is required by the 128B swizzle atom (8 rows x 128 B)
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem + STAGES * S::A_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * S::STAGE_BYTES);
+  uint64_t* full_bar = bars;
+  uint64_t* empty_bar = bars + STAGES;
+  uint64_t* tmem_full_bar = bars + 2 * STAGES;
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int n0 = blockIdx.x * BN;
+  const int m0 = blockIdx.y * BM;
+  const int num_kb = (K + BK - 1) / BK;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmap_a);
+    prefetch_tmap(&tmap_b);
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(smem_u32(&full_bar[s]), 1);
+      mbar_init(smem_u32(&empty_bar[s]), 1);
+    }
+    mbar_init(smem_u32(tmem_full_bar), 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(smem_u32(tmem_ptr_smem), TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      for (int kb = 0; kb < num_kb; ++kb) {
+        const int s = kb % STAGES;
+        const uint32_t ph = (uint32_t)(kb / STAGES) & 1u;
+        mbar_wait(smem_u32(&empty_bar[s]), ph ^ 1u);
+        const uint32_t fb = smem_u32(&full_bar[s]);
+        mbar_expect_tx(fb, S::STAGE_BYTES);
+        tma_load_2d(smem_u32(smem_a + s * S::A_BYTES), &tmap_a, fb, kb * BK, m0);
+        tma_load_2d(smem_u32(smem_b + s * S::B_BYTES), &tmap_b, fb, kb * BK, n0);
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc(BN);
+      for (int kb = 0; kb < num_kb; ++kb) {
+        const int s = kb % STAGES;
+        const uint32_t ph = (uint32_t)(kb / STAGES) & 1u;
+        mbar_wait(smem_u32(&full_bar[s]), ph);
+        tc_fence_after();
+        const uint64_t da = make_sw128_desc(smem_u32(smem_a + s * S::A_BYTES));
+        const uint64_t db = make_sw128_desc(smem_u32(smem_b + s * S::B_BYTES));
+#pragma unroll
+        for (int k = 0; k < BK / 16; ++k) {
+          // advance 16 elements (32 B) along K inside the swizzle atom: +2 in the (>>4) address field
+          umma_f16(tmem_base, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (kb | k) != 0);
+        }
+        umma_commit(smem_u32(&empty_bar[s]));  // slot free once these MMAs have read it
+      }
+      umma_commit(smem_u32(tmem_full_bar));    // accumulator complete
+    }
+  } else {
+    // ===================== epilogue (warps 2..5) =====================
+    const int q = warp & 3;  // TMEM lane quarter this warp may access
+    const int row = m0 + q * 32 + lane;
+    const bool row_ok = row < M;
+    mbar_wait(smem_u32(tmem_full_bar), 0);
+    tc_fence_after();
+    const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
+    const __half* rg = (epi.rowgroup_bias && row_ok)
+                           ? epi.rowgroup_bias + (size_t)(row / epi.rows_per_group) * epi.rg_ld : nullptr;
+    if (epi.act != L2D_ACT_GEGLU) {
+#pragma unroll 1
+      for (int cc = 0; cc < BN / 16; ++cc) {
+        uint32_t r[16];
+        tmem_ld16(taddr + cc * 16, r);
+        tmem_ld_wait();
+        const int col0 = n0 + cc * 16;
+        float v[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+#pragma unroll
+        for (int hlf = 0; hlf < 2; ++hlf) {
+          const int col = col0 + hlf * 8;
+          if (col < N) {
+            if (epi.bias) {
+              float b[8];
+              unpack8(ldg_cached(epi.bias + col), b);
+#pragma unroll
+              for (int i = 0; i < 8; ++i) v[hlf * 8 + i] += b[i];
+            }
+            if (rg) {
+              float b[8];
+              unpack8(ldg_cached(rg + col), b);
+#pragma unroll
+              for (int i = 0; i < 8; ++i) v[hlf * 8 + i] += b[i];
+            }
+          }
+        }
+        if (epi.act == L2D_ACT_SILU) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) v[i] = silu_f(v[i]);
+        }
+        epi_store16(epi, v, row, col0, M, N, row_ok);
+      }
+    } else {
+      // GEGLU: tile columns [0,BN/2) = value half, [BN/2,BN) = matching gate half (weights interleaved
+      // by l2d_geglu_interleave); output columns blockIdx.x*BN/2 + ...
+      constexpr int HB = BN / 2;
+      const int n_out = N / 2;
+#pragma unroll 1
+      for (int cc = 0; cc < HB / 16; ++cc) {
+        uint32_t rh[16], rgt[16];
+        tmem_ld16(taddr + cc * 16, rh);
+        tmem_ld16(taddr + HB + cc * 16, rgt);
+        tmem_ld_wait();
+        const int colh = n0 + cc * 16;       // column in the interleaved weight (value half)
+        const int colg = n0 + HB + cc * 16;  // gate half
+        float v[16];
+#pragma unroll
+        for (int hlf = 0; hlf < 2; ++hlf) {
+          float bh[8], bg[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) bh[i] = bg[i] = 0.f;
+          if (epi.bias && colh + hlf * 8 < N) {
+            unpack8(ldg_cached(epi.bias + colh + hlf * 8), bh);
+            unpack8(ldg_cached(epi.bias + colg + hlf * 8), bg);
+          }
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            // the reference rounds the projection to fp16 before h * gelu(g) (GEGLU.forward on an fp16 Linear output)
+            const float hval = __half2float(__float2half_rn(__uint_as_float(rh[hlf * 8 + i]) + bh[i]));
+            const float gval = __half2float(__float2half_rn(__uint_as_float(rgt[hlf * 8 + i]) + bg[i]));
+            v[hlf * 8 + i] = hval * gelu_erf_f(gval);
+          }
+        }
+        epi_store16(epi, v, row, blockIdx.x * HB + cc * 16, M, n_out, row_ok && (colh < N));
+      }
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side: tensor-map cache + dispatch
+// ---------------------------------------------------------------------------------------------
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static PFN_encodeTiled get_encode() {
+  static PFN_encodeTiled fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_encodeTiled>(p);
+  });
+  return fn;
+}
+
+struct TmapKey {
+  const void* ptr;
+  int64_t rows, cols, ld;
+  int box_rows;
+  bool operator==(const TmapKey& o) const {
+    return ptr == o.ptr && rows == o.rows && cols == o.cols && ld == o.ld && box_rows == o.box_rows;
+  }
+};
+struct TmapKeyHash {
+  size_t operator()(const TmapKey& k) const {
+    size_t h = std::hash<const void*>()(k.ptr);
+    h ^= std::hash<int64_t>()(k.rows * 1315423911ll + k.cols) + 0x9e3779b97f4a7c15ull + (h << 6) + (h >> 2);
+    h ^= std::hash<int64_t>()(k.ld * 31 + k.box_rows) + 0x9e3779b97f4a7c15ull + (h << 6) + (h >> 2);
+    return h;
+  }
+};
+
+// 2D row-major fp16 [rows, cols] with row pitch ld elements; box = [box_rows, 64], 128B swizzle
+static int get_tmap(const void* ptr, int64_t rows, int64_t cols, int64_t ld, int box_rows, CUtensorMap* out) {
+  static std::unordered_map<TmapKey, CUtensorMap, TmapKeyHash> cache;
+  static std::mutex mu;
+  TmapKey key{ptr, rows, cols, ld, box_rows};
+  std::lock_guard<std::mutex> lk(mu);
+  auto it = cache.find(key);
+  if (it != cache.end()) {
+    *out = it->second;
+    return L2D_OK;
+  }
+  PFN_encodeTiled enc = get_encode();
+  if (!enc) return fail(L2D_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available (driver too old?)");
+  cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t gstr[1] = {(cuuint64_t)ld * 2};
+  cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUtensorMap m;
+  CUresult r = enc(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(ptr), gdim, gstr, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(L2D_ERR_CUDA, "cuTensorMapEncodeTiled failed, CUresult " + std::to_string((int)r));
+  if (cache.size() > 65536) cache.clear();
+  cache.emplace(key, m);
+  *out = m;
+  return L2D_OK;
+}
+
+int gemm_pick_tile_n(int m, int n, int k) {
+  (void)k;
+  const int cands[4] = {256, 160, 128, 64};
+  int best = 64;
+  double best_cost = 1e30;
+  const int tiles_m = ceil_div(m, BM);
+  for (int bn : cands) {
+    const int tiles = tiles_m * ceil_div(n, bn);
+    const int waves = ceil_div(tiles, 148);
+    const double cost = (double)waves * (bn + 128);
+    if (cost < best_cost - 1e-9) {
+      best_cost = cost;
+      best = bn;
+    }
+  }
+  return best;
+}
+
+template <int BN, int STAGES>
+static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmEpilogue& e, int M, int N, int K,
+                       cudaStream_t st) {
+  constexpr size_t smem = (size_t)STAGES * GemmSmem<BN>::STAGE_BYTES + (2 * STAGES + 2) * 8 + 1024;
+  static bool configured = false;
+  if (!configured) {
+    L2D_CUDA(cudaFuncSetAttribute(gemm_f16_tcgen05_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)smem));
+    configured = true;
+  }
+  dim3 grid(ceil_div(N, BN), ceil_div(M, BM));
+  gemm_f16_tcgen05_kernel<BN, STAGES><<<grid, 192, smem, st>>>(ta, tb, e, M, N, K);
+  L2D_LAUNCH_CHECK();
+  return L2D_OK;
+}
+
+int gemm_launch(const __half* a, int64_t lda, const __half* w, int64_t ldw, __half* out, int64_t ldo, int m, int n, int k,
+                const __half* bias, const __half* rowgroup_bias, int64_t rg_ld, int rows_per_group,
+                const __half* residual, int64_t ldr, int act, int force_bn, cudaStream_t st) {
+  const int bn = force_bn > 0 ? force_bn : gemm_pick_tile_n(m, n, k);
+  CUtensorMap ta, tb;
+  int rc = get_tmap(a, m, k, lda, BM, &ta);
+  if (rc != L2D_OK) return rc;
+  rc = get_tmap(w, n, k, ldw, bn, &tb);
+  if (rc != L2D_OK) return rc;
+  GemmEpilogue e{out, ldo, bias, rowgroup_bias, rg_ld, rows_per_group > 0 ? rows_per_group : 1, residual, ldr, act};
+  switch (bn) {
+    case 64: return launch_gemm<64, 6>(ta, tb, e, m, n, k, st);
+    case 128: return launch_gemm<128, 6>(ta, tb, e, m, n, k, st);
+    case 160: return launch_gemm<160, 5>(ta, tb, e, m, n, k, st);
+    case 256: return launch_gemm<256, 4>(ta, tb, e, m, n, k, st);
+    default: return fail(L2D_ERR_INVALID, "gemm: unsupported tile_n");
+  }
+}
+
+}  // namespace l2d
+
+using namespace l2d;
+
+extern "C" int l2d_gemm_tile_n(int m, int n, int k) { return gemm_pick_tile_n(m, n, k); }
+
+extern "C" int l2d_gemm(const void* a, int64_t lda, const void* w, void* out, int64_t ldo, int m, int n, int k,
+                        const void* bias, const void* rowgroup_bias, int rows_per_group, const void* residual,
+                        int64_t ldr, int act, void* stream) {
+  L2D_CHECK_ARG(a && w && out, "null pointer");
+  L2D_CHECK_ARG(m > 0 && n > 0 && k > 0, "empty problem");
+  L2D_CHECK_ARG(k % 8 == 0 && n % 8 == 0 && lda % 8 == 0 && ldo % 8 == 0, "K, N, lda, ldo must be multiples of 8");
+  L2D_CHECK_ARG(lda >= k, "lda < K");
+  L2D_CHECK_ARG(act >= 0 && act <= 2, "bad act");
+  L2D_CHECK_ARG(!residual || ldr % 8 == 0, "ldr must be a multiple of 8");
+  L2D_CHECK_ARG(!rowgroup_bias || rows_per_group > 0, "rows_per_group must be > 0");
+  L2D_CHECK_ARG(((uintptr_t)a % 16 == 0) && ((uintptr_t)w % 16 == 0) && ((uintptr_t)out % 16 == 0), "16-byte alignment");
+  if (act == L2D_ACT_GEGLU) {
+    const int bn = gemm_pick_tile_n(m, n, k);
+    L2D_CHECK_ARG(n % bn == 0, "GEGLU: N must be a multiple of the N tile (see l2d_gemm_tile_n)");
+  }
+  return gemm_launch((const __half*)a, lda, (const __half*)w, k, (__half*)out, ldo, m, n, k, (const __half*)bias,
+                     (const __half*)rowgroup_bias, n, rows_per_group, (const __half*)residual, ldr, act, 0,
+                     (cudaStream_t)stream);
+}

@@ -1,0 +1,426 @@
+// K5/K6 -- GroupNorm(+SiLU)(+3x3 im2col) and LayerNorm on channels-last fp16 activations, plus the
+// raw im2col / layout kernels.  All HBM/L2-bandwidth kernels: 128-bit accesses, fp32 statistics,
+// warp-shuffle reductions.
+//
+// Reference semantics: nn.GroupNorm / InflatedGroupNorm per frame (resnet.py:68-76; eps 1e-5 in
+// resnets/conv_norm_out, 1e-6 at transformer entries -- SURVEY A-9), nn.LayerNorm(eps 1e-5),
+// F.silu, 3x3 / stride-2 / nearest-x2 convolutions of resnet.py:57-153 (the im2col here feeds the
+// tcgen05 GEMM that performs the convolution's contraction).
+#include "ops.cuh"
+
+namespace l2d {
+
+// ---------------------------------------------------------------------------------------------
+// LayerNorm: one warp per row, values kept in registers (C <= 8*32*MAXCH)
+// ---------------------------------------------------------------------------------------------
+constexpr int LN_MAXCH = 10;  // 16B chunks per lane -> C <= 2560
+
+__global__ void __launch_bounds__(256) layernorm_kernel(const __half* __restrict__ x, const __half* __restrict__ gamma,
+                                                        const __half* __restrict__ beta, __half* __restrict__ y,
+                                                        int rows, int C, float eps) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp >= rows) return;
+  const int nch = C >> 3;
+  const __half* xr = x + (size_t)warp * C;
+  float v[LN_MAXCH][8];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < LN_MAXCH; ++i) {
+    const int ch = lane + i * 32;
+    if (ch < nch) {
+      unpack8(ldg_cached(xr + ch * 8), v[i]);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) s += v[i][e];
+    }
+  }
+  const float mean = warp_sum(s) / (float)C;
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < LN_MAXCH; ++i) {
+    const int ch = lane + i * 32;
+    if (ch < nch) {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const float d = v[i][e] - mean;
+        q = fmaf(d, d, q);
+      }
+    }
+  }
+  const float rstd = rsqrtf(warp_sum(q) / (float)C + eps);
+  __half* yr = y + (size_t)warp * C;
+#pragma unroll
+  for (int i = 0; i < LN_MAXCH; ++i) {
+    const int ch = lane + i * 32;
+    if (ch < nch) {
+      float g[8], b[8], o[8];
+      unpack8(ldg_cached(gamma + ch * 8), g);
+      unpack8(ldg_cached(beta + ch * 8), b);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) o[e] = (v[i][e] - mean) * rstd * g[e] + b[e];
+      *reinterpret_cast<uint4*>(yr + ch * 8) = pack8(o);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// GroupNorm statistics: grid (chunks, N).  Each block reduces a slab of pixels x all channels to
+// per-group (mean, M2) partials; the apply kernel merges the partials (Chan's formula).
+// ---------------------------------------------------------------------------------------------
+constexpr int GN_MAX_SPLIT = 32;
+
+struct GnSrc {
+  const __half* x1;
+  const __half* x2;
+  int c1, c2;  // channels of each source (c2 may be 0)
+};
+
+__device__ __forceinline__ uint4 gn_load_chunk(const GnSrc& s, size_t pix, int ch8) {
+  const int c = ch8 * 8;
+  if (c < s.c1) return ldg_cached(s.x1 + pix * s.c1 + c);
+  return ldg_cached(s.x2 + pix * s.c2 + (c - s.c1));
+}
+
+// partial layout: [N][split][G][2] floats (mean, M2); counts are implied (equal slabs except the last)
+__global__ void __launch_bounds__(512) groupnorm_stats_kernel(GnSrc src, float* __restrict__ partial, int hw, int G,
+                                                               int split) {
+  extern __shared__ float sm[];  // [2][C] per-channel sum, sumsq
+  const int C = src.c1 + src.c2;
+  const int nch = C >> 3;
+  const int n = blockIdx.y, sp = blockIdx.x;
+  const int per = (hw + split - 1) / split;
+  const int p0 = sp * per, p1 = min(hw, p0 + per);
+  float* s_sum = sm;
+  float* s_sq = sm + C;
+  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) sm[i] = 0.f;
+  __syncthreads();
+  const int R = blockDim.x / nch;  // pixel lanes
+  const int r = threadIdx.x / nch, ch = threadIdx.x - r * nch;
+  if (r < R) {
+    float a[8] = {0, 0, 0, 0, 0, 0, 0, 0}, b[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (int p = p0 + r; p < p1; p += R) {
+      float v[8];
+      unpack8(gn_load_chunk(src, (size_t)n * hw + p, ch), v);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        a[e] += v[e];
+        b[e] = fmaf(v[e], v[e], b[e]);
+      }
+    }
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      atomicAdd(&s_sum[ch * 8 + e], a[e]);
+      atomicAdd(&s_sq[ch * 8 + e], b[e]);
+    }
+  }
+  __syncthreads();
+  const int cpg = C / G;
+  const float cnt = (float)(p1 - p0) * (float)cpg;
+  for (int g = threadIdx.x; g < G; g += blockDim.x) {
+    float s = 0.f, q = 0.f;
+    for (int i = 0; i < cpg; ++i) {
+      s += s_sum[g * cpg + i];
+      q += s_sq[g * cpg + i];
+    }
+    const float mean = cnt > 0.f ? s / cnt : 0.f;
+    const float m2 = fmaxf(q - s * mean, 0.f);
+    float* o = partial + (((size_t)n * split + sp) * G + g) * 2;
+    o[0] = mean;
+    o[1] = m2;
+  }
+}
+
+// Apply: y = act((x - mean_g) * rstd_g * gamma_c + beta_c); mode 0 writes NHWC, mode 1 writes the
+// 3x3 im2col matrix (pad 1, given stride) of the normalised tensor.
+struct GnApplyParams {
+  GnSrc src;
+  const __half* gamma;
+  const __half* beta;
+  const float* partial;
+  __half* y;
+  int h, w, G, split;
+  float eps;
+  int silu, mode, stride;
+};
+
+__global__ void __launch_bounds__(256) groupnorm_apply_kernel(const GnApplyParams p) {
+  extern __shared__ float sm[];  // A[C], B[C]
+  const int C = p.src.c1 + p.src.c2;
+  const int hw = p.h * p.w;
+  const int n = blockIdx.y;
+  const int cpg = C / p.G;
+  float* sA = sm;
+  float* sB = sm + C;
+  // merge the split partials of every group of image n
+  for (int g = threadIdx.x; g < p.G; g += blockDim.x) {
+    const int per = (hw + p.split - 1) / p.split;
+    float mean = 0.f, m2 = 0.f, cnt = 0.f;
+    for (int s = 0; s < p.split; ++s) {
+      const int p0 = s * per, p1 = min(hw, p0 + per);
+      const float c = (float)max(p1 - p0, 0) * (float)cpg;
+      if (c <= 0.f) continue;
+      const float* src = p.partial + (((size_t)n * p.split + s) * p.G + g) * 2;
+      const float d = src[0] - mean;
+      const float tot = cnt + c;
+      m2 += src[1] + d * d * cnt * c / tot;
+      mean += d * c / tot;
+      cnt = tot;
+    }
+    const float rstd = rsqrtf(m2 / cnt + p.eps);
+    for (int i = 0; i < cpg; ++i) {
+      const int c = g * cpg + i;
+      const float ga = __half2float(p.gamma[c]) * rstd;
+      sA[c] = ga;
+      sB[c] = __half2float(p.beta[c]) - mean * ga;
+    }
+  }
+  __syncthreads();
+  const int nch = C >> 3;
+  if (p.mode == 0) {
+    const size_t total = (size_t)hw * nch;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+      const int ch = (int)(i % nch);
+      const size_t pix = (size_t)n * hw + i / nch;
+      float v[8];
+      unpack8(gn_load_chunk(p.src, pix, ch), v);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        float t = fmaf(v[e], sA[ch * 8 + e], sB[ch * 8 + e]);
+        v[e] = p.silu ? silu_f(t) : t;
+      }
+      *reinterpret_cast<uint4*>(p.y + pix * C + ch * 8) = pack8(v);
+    }
+  } else {
+    const int ho = p.h / p.stride, wo = p.w / p.stride;
+    const size_t total = (size_t)ho * wo * 9 * nch;
+    const size_t K = (size_t)9 * C;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+      const int ch = (int)(i % nch);
+      const int tap = (int)((i / nch) % 9);
+      const size_t opix = i / ((size_t)nch * 9);
+      const int oy = (int)(opix / wo), ox = (int)(opix % wo);
+      const int iy = oy * p.stride + tap / 3 - 1, ix = ox * p.stride + tap % 3 - 1;
+      uint4 o = make_uint4(0, 0, 0, 0);
+      if (iy >= 0 && iy < p.h && ix >= 0 && ix < p.w) {
+        float v[8];
+        unpack8(gn_load_chunk(p.src, (size_t)n * hw + (size_t)iy * p.w + ix, ch), v);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          float t = fmaf(v[e], sA[ch * 8 + e], sB[ch * 8 + e]);
+          v[e] = p.silu ? silu_f(t) : t;
+        }
+        o = pack8(v);
+      }
+      *reinterpret_cast<uint4*>(p.y + ((size_t)n * ho * wo + opix) * K + (size_t)tap * C + ch * 8) = o;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// raw im2col (no normalisation): stride 1/2, optional nearest x2 upsample, optional SiLU
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) im2col3x3_kernel(const __half* __restrict__ x, __half* __restrict__ y, int n_img,
+                                                        int h, int w, int C, int stride, int up, int silu) {
+  const int hs = up ? 2 * h : h, ws = up ? 2 * w : w;  // size of the (virtual) conv input
+  const int ho = hs / stride, wo = ws / stride;
+  const int nch = C >> 3;
+  const size_t total = (size_t)n_img * ho * wo * 9 * nch;
+  const size_t K = (size_t)9 * C;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int ch = (int)(i % nch);
+    const int tap = (int)((i / nch) % 9);
+    const size_t opix = i / ((size_t)nch * 9);
+    const int n = (int)(opix / ((size_t)ho * wo));
+    const int rem = (int)(opix % ((size_t)ho * wo));
+    const int oy = rem / wo, ox = rem % wo;
+    int iy = oy * stride + tap / 3 - 1, ix = ox * stride + tap % 3 - 1;
+    uint4 o = make_uint4(0, 0, 0, 0);
+    if (iy >= 0 && iy < hs && ix >= 0 && ix < ws) {
+      if (up) {
+        iy >>= 1;
+        ix >>= 1;
+      }
+      o = ldg_cached(x + (((size_t)n * h + iy) * w + ix) * C + ch * 8);
+      if (silu) {
+        float v[8];
+        unpack8(o, v);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) v[e] = silu_f(v[e]);
+        o = pack8(v);
+      }
+    }
+    *reinterpret_cast<uint4*>(y + opix * K + (size_t)tap * C + ch * 8) = o;
+  }
+}
+
+// 4-channel NCHW latent -> [N*h*w, 64]; cols 0..35 = (tap, channel), 36..63 = 0
+__global__ void __launch_bounds__(256) im2col3x3_nchw4_kernel(const __half* __restrict__ x, __half* __restrict__ y,
+                                                              int n_img, int h, int w) {
+  const size_t total = (size_t)n_img * h * w * 8;  // 8 chunks of 8 columns per row
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int chunk = (int)(i & 7);
+    const size_t pix = i >> 3;
+    const int n = (int)(pix / ((size_t)h * w));
+    const int rem = (int)(pix % ((size_t)h * w));
+    const int oy = rem / w, ox = rem % w;
+    float v[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const int col = chunk * 8 + e;
+      float t = 0.f;
+      if (col < 36) {
+        const int tap = col >> 2, c = col & 3;
+        const int iy = oy + tap / 3 - 1, ix = ox + tap % 3 - 1;
+        if (iy >= 0 && iy < h && ix >= 0 && ix < w) t = __half2float(x[(((size_t)n * 4 + c) * h + iy) * w + ix]);
+      }
+      v[e] = t;
+    }
+    *reinterpret_cast<uint4*>(y + pix * 64 + chunk * 8) = pack8(v);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// NCHW <-> NHWC (32x32 smem tile transpose)
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) transpose_kernel(const __half* __restrict__ x, const __half* __restrict__ res,
+                                                        __half* __restrict__ y, int rows, int cols) {
+  // x: [batch][rows][cols] -> y: [batch][cols][rows]; res (optional) has y's layout
+  __shared__ __half tile[32][33];
+  const size_t base = (size_t)blockIdx.z * rows * cols;
+  const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  for (int i = ty; i < 32; i += 8) {
+    const int r = r0 + i, c = c0 + tx;
+    if (r < rows && c < cols) tile[i][tx] = x[base + (size_t)r * cols + c];
+  }
+  __syncthreads();
+  for (int i = ty; i < 32; i += 8) {
+    const int c = c0 + i, r = r0 + tx;
+    if (r < rows && c < cols) {
+      const size_t o = base + (size_t)c * rows + r;
+      __half v = tile[tx][i];
+      if (res) v = __hadd(v, res[o]);
+      y[o] = v;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// launchers
+// ---------------------------------------------------------------------------------------------
+static int pick_split(int hw) {
+  int s = hw / 128;
+  if (s < 1) s = 1;
+  if (s > GN_MAX_SPLIT) s = GN_MAX_SPLIT;
+  return s;
+}
+
+int groupnorm_launch(const __half* x1, int c1, const __half* x2, int c2, const __half* gamma, const __half* beta,
+                     __half* y, float* ws, int n_img, int h, int w, int G, float eps, int silu, int mode, int stride,
+                     cudaStream_t st) {
+  const int C = c1 + c2, hw = h * w, nch = C / 8;
+  const int split = pick_split(hw);
+  GnSrc src{x1, x2, c1, c2};
+  int threads = 512;
+  if (nch > threads) return fail(L2D_ERR_INVALID, "groupnorm: C > 4096");
+  static size_t cfg_stats = 0, cfg_apply = 0;
+  const size_t smem = (size_t)2 * C * sizeof(float);
+  if (smem > 48 * 1024) {
+    if (smem > cfg_stats) {
+      L2D_CUDA(cudaFuncSetAttribute(groupnorm_stats_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      cfg_stats = smem;
+    }
+    if (smem > cfg_apply) {
+      L2D_CUDA(cudaFuncSetAttribute(groupnorm_apply_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      cfg_apply = smem;
+    }
+  }
+  groupnorm_stats_kernel<<<dim3(split, n_img), threads, smem, st>>>(src, ws, hw, G, split);
+  L2D_LAUNCH_CHECK();
+  GnApplyParams p{src, gamma, beta, ws, y, h, w, G, split, eps, silu, mode, stride};
+  size_t work = mode == 0 ? (size_t)hw * nch : (size_t)(h / stride) * (w / stride) * 9 * nch;
+  int blocks = (int)std::min<size_t>((work + 255) / 256, 148 * 8);
+  if (blocks < 1) blocks = 1;
+  groupnorm_apply_kernel<<<dim3(blocks, n_img), 256, smem, st>>>(p);
+  L2D_LAUNCH_CHECK();
+  return L2D_OK;
+}
+
+}  // namespace l2d
+
+using namespace l2d;
+
+extern "C" int l2d_layernorm(const void* x, const void* gamma, const void* beta, void* y, int rows, int channels,
+                             float eps, void* stream) {
+  L2D_CHECK_ARG(x && gamma && beta && y, "null pointer");
+  L2D_CHECK_ARG(channels % 8 == 0 && channels <= 8 * 32 * LN_MAXCH, "need C % 8 == 0 and C <= 2560");
+  if (rows <= 0) return L2D_OK;
+  const int blocks = ceil_div(rows, 8);
+  layernorm_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>((const __half*)x, (const __half*)gamma,
+                                                             (const __half*)beta, (__half*)y, rows, channels, eps);
+  L2D_LAUNCH_CHECK();
+  return L2D_OK;
+}
+
+extern "C" int64_t l2d_groupnorm_workspace_bytes(int n_img, int groups) {
+  return (int64_t)n_img * GN_MAX_SPLIT * groups * 2 * sizeof(float);
+}
+
+extern "C" int l2d_groupnorm(const void* x1, int c1, const void* x2, int c2, const void* gamma, const void* beta,
+                             void* y, void* workspace, int n_img, int h, int w, int groups, float eps, int silu,
+                             int mode, int stride, void* stream) {
+  L2D_CHECK_ARG(x1 && gamma && beta && y && workspace, "null pointer");
+  L2D_CHECK_ARG(c2 == 0 || x2, "x2 is null but c2 > 0");
+  L2D_CHECK_ARG(c1 % 8 == 0 && c2 % 8 == 0, "channel counts must be multiples of 8");
+  L2D_CHECK_ARG(groups > 0 && (c1 + c2) % groups == 0, "channels % groups != 0");
+  L2D_CHECK_ARG(mode == 0 || mode == 1, "mode must be 0 or 1");
+  L2D_CHECK_ARG(stride == 1 || (mode == 1 && stride == 2 && h % 2 == 0 && w % 2 == 0), "bad stride");
+  return groupnorm_launch((const __half*)x1, c1, (const __half*)x2, c2, (const __half*)gamma, (const __half*)beta,
+                          (__half*)y, (float*)workspace, n_img, h, w, groups, eps, silu, mode, stride,
+                          (cudaStream_t)stream);
+}
+
+extern "C" int l2d_im2col3x3(const void* x, void* y, int n_img, int h, int w, int channels, int stride, int upsample2x,
+                             int silu, void* stream) {
+  L2D_CHECK_ARG(x && y, "null pointer");
+  L2D_CHECK_ARG(channels % 8 == 0, "C % 8 != 0");
+  L2D_CHECK_ARG(stride == 1 || stride == 2, "stride must be 1 or 2");
+  L2D_CHECK_ARG(!(upsample2x && stride != 1), "upsample with stride 2 is not a reference op");
+  const int hs = upsample2x ? 2 * h : h, ws = upsample2x ? 2 * w : w;
+  L2D_CHECK_ARG(hs % stride == 0 && ws % stride == 0, "odd size with stride 2");
+  const size_t total = (size_t)n_img * (hs / stride) * (ws / stride) * 9 * (channels / 8);
+  int blocks = (int)std::min<size_t>((total + 255) / 256, 148 * 16);
+  if (blocks < 1) blocks = 1;
+  im2col3x3_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>((const __half*)x, (__half*)y, n_img, h, w, channels,
+                                                             stride, upsample2x, silu);
+  L2D_LAUNCH_CHECK();
+  return L2D_OK;
+}
+
+extern "C" int l2d_im2col3x3_nchw4(const void* x, void* y, int n_img, int h, int w, void* stream) {
+  L2D_CHECK_ARG(x && y, "null pointer");
+  const size_t total = (size_t)n_img * h * w * 8;
+  int blocks = (int)std::min<size_t>((total + 255) / 256, 148 * 16);
+  if (blocks < 1) blocks = 1;
+  im2col3x3_nchw4_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>((const __half*)x, (__half*)y, n_img, h, w);
+  L2D_LAUNCH_CHECK();
+  return L2D_OK;
+}
+
+extern "C" int l2d_nchw_to_nhwc(const void* x, void* y, int n_img, int channels, int hw, void* stream) {
+  L2D_CHECK_ARG(x && y, "null pointer");
+  dim3 grid(ceil_div(hw, 32), ceil_div(channels, 32), n_img);
+  transpose_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const __half*)x, nullptr, (__half*)y, channels, hw);
+  L2D_LAUNCH_CHECK();
+  return L2D_OK;
+}
+
+extern "C" int l2d_nhwc_to_nchw(const void* x, const void* residual_nchw, void* y, int n_img, int channels, int hw,
+                                void* stream) {
+  L2D_CHECK_ARG(x && y, "null pointer");
+  dim3 grid(ceil_div(channels, 32), ceil_div(hw, 32), n_img);
+  transpose_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const __half*)x, (const __half*)residual_nchw, (__half*)y,
+                                                           hw, channels);
+  L2D_LAUNCH_CHECK();
+  return L2D_OK;
+}

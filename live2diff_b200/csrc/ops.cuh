@@ -1,0 +1,41 @@
+// Internal launcher interfaces shared between the kernel files and the engine.
+#pragma once
+#include "common.cuh"
+
+namespace l2d {
+
+struct KvAttnParams {
+  const __half* q;
+  const __half* k_new;
+  const __half* v_new;
+  int64_t ld;
+  __half* cache;
+  const __half* q_pe;
+  const __half* k_pe;
+  const __half* v_pe;
+  const __half* mask;
+  const int64_t* pe_idx;
+  const int64_t* update_idx;
+  __half* out;
+  int n_rows, hw, L, C, heads;
+  int64_t pe_ld;  // row pitch of the q_pe/k_pe/v_pe tables (elements)
+  int T;    // C / 8 chunk-threads per pixel
+  int P;    // pixels per block
+  int hd8;  // chunks per head
+  float scale;
+};
+int kv_attn_launch(const KvAttnParams& p, cudaStream_t stream);
+
+int groupnorm_launch(const __half* x1, int c1, const __half* x2, int c2, const __half* gamma, const __half* beta,
+                     __half* y, float* ws, int n_img, int h, int w, int G, float eps, int silu, int mode, int stride,
+                     cudaStream_t st);
+
+int gemm_pick_tile_n(int m, int n, int k);
+int gemm_launch(const __half* a, int64_t lda, const __half* w, int64_t ldw, __half* out, int64_t ldo, int m, int n, int k,
+                const __half* bias, const __half* rowgroup_bias, int64_t rg_ld, int rows_per_group,
+                const __half* residual, int64_t ldr, int act, int force_bn, cudaStream_t st);
+
+int attention_launch(const __half* q, int64_t ldq, const __half* k, int64_t ldk, const __half* v, int64_t ldv, __half* o,
+                     int64_t ldo, int batch, int heads, int sq, int skv, int hd, cudaStream_t st);
+
+}  // namespace l2d

@@ -1,0 +1,154 @@
+"""`B200UNetStep`: the object installed at `stream.unet` (boundary B1).
+
+Call contract = the one `StreamAnimateDiffusionDepth.unet_step` uses
+(live2diff/pipeline_stream_animation_depth.py:456-469) and the reference's TensorRT engine object
+implements (live2diff/acceleration/tensorrt/engine.py:142-185; swap point live2diff/utils/wrapper.py:613):
+
+    out = unet(sample[N,4,1,h,w], timestep[N], depth_sample=..., encoder_hidden_states=[N,77,768],
+               temporal_attention_mask=[N,L], kv_cache=[40 x [N,2,hw,L,C]], pe_idx=[N,L], update_idx=[N],
+               return_dict=True)
+    out["sample"]   -> [N,4,1,h,w]      out["kv_cache"] -> the same 40 tensors, mutated in place
+
+plus no-op `.to()` / `.forward()` like engine.py:187-191.  The whole step runs inside libl2d_b200.so
+(csrc/engine.cu); with `use_cuda_graph=True` inputs are staged into fixed device buffers and the step is
+replayed from a CUDA graph.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, List, Optional
+
+import torch
+
+from ._lib import L2DUnetConfig, L2DUnetStepArgs, check, current_stream, lib, make_tensor_table
+from .weights import UNetDims, unet_param_spec
+
+
+class UNetStepOutput(dict):
+    """Mapping with attribute access (`out.sample`, `out["sample"]`) like diffusers' BaseOutput."""
+
+    def __getattr__(self, k):
+        try:
+            return self[k]
+        except KeyError as e:
+            raise AttributeError(k) from e
+
+
+class B200UNetStep:
+    def __init__(self, state_dict: Dict[str, torch.Tensor], dims: UNetDims, n_rows: int, latent_h: int, latent_w: int,
+                 ctx_len: int = 77, use_cuda_graph: bool = True, device: Optional[torch.device] = None):
+        if not torch.cuda.is_available():
+            raise RuntimeError("B200UNetStep needs a CUDA device; live2diff_b200 has no CPU fallback")
+        self.dims, self.n_rows, self.h, self.w, self.ctx_len = dims, n_rows, latent_h, latent_w, ctx_len
+        self.device = torch.device(device or "cuda")
+        spec = unet_param_spec(dims)
+        missing = [k for k in spec if k not in state_dict]
+        if missing:
+            raise KeyError(f"state_dict is missing {len(missing)} tensors, e.g. {missing[:3]}")
+        named = {}
+        for k, shape in spec.items():
+            t = state_dict[k]
+            if tuple(t.shape) != tuple(shape):
+                raise ValueError(f"{k}: shape {tuple(t.shape)} != expected {tuple(shape)}")
+            named[k] = t.detach().to(device=self.device, dtype=torch.float16).contiguous()
+        cfg = L2DUnetConfig()
+        nlev = len(dims.block_out_channels)
+        cfg.n_levels = nlev
+        for i, c in enumerate(dims.block_out_channels):
+            cfg.block_out_channels[i] = c
+            cfg.down_has_attn[i] = int(dims.down_has_attn[i])
+            cfg.up_has_attn[i] = int(dims.up_has_attn[i])
+        cfg.layers_per_block, cfg.heads = dims.layers_per_block, dims.heads
+        cfg.cross_attention_dim, cfg.ctx_len, cfg.groups = dims.cross_attention_dim, ctx_len, dims.norm_groups
+        cfg.window, cfg.n_rows, cfg.latent_h, cfg.latent_w = dims.window_size, n_rows, latent_h, latent_w
+        for i, c in enumerate(dims.mapping_channels):
+            cfg.mapping_channels[i] = c
+        cfg.n_mapping = len(dims.mapping_channels)
+        cfg.norm_eps = dims.norm_eps
+        cfg.use_cuda_graph = int(use_cuda_graph)
+        arr, keep = make_tensor_table(named)
+        handle = C.c_void_p()
+        with torch.cuda.device(self.device):
+            check(lib().l2d_unet_create(C.byref(handle), C.byref(cfg), arr, len(named)))
+        self._handle = handle
+        del named, arr, keep                      # the engine owns repacked copies
+        self.dtype = torch.float16
+        self.use_cuda_graph = use_cuda_graph
+        dev = self.device
+        # fixed staging buffers (stable addresses for the CUDA graph)
+        self._sample = torch.empty(n_rows, 4, 1, latent_h, latent_w, dtype=torch.float16, device=dev)
+        self._depth = torch.empty_like(self._sample)
+        self._out = torch.empty_like(self._sample)
+        self._t = torch.empty(n_rows, dtype=torch.int64, device=dev)
+        self._ctx = torch.empty(n_rows, ctx_len, dims.cross_attention_dim, dtype=torch.float16, device=dev)
+        self._mask = torch.empty(n_rows, dims.window_size, dtype=torch.float16, device=dev)
+        self._pe_idx = torch.empty(n_rows, dims.window_size, dtype=torch.int64, device=dev)
+        self._upd = torch.empty(n_rows, dtype=torch.int64, device=dev)
+        self._kv_ids = None
+        self._kv_arr = None
+        self._kv_shapes = dims.kv_cache_shapes(n_rows, latent_h, latent_w)
+
+    # -- reference-compatible helpers --------------------------------------------------------
+    def to(self, *args, **kwargs):
+        return self
+
+    def forward(self, *args, **kwargs):
+        pass
+
+    def prepare_cache(self, denoising_steps_num: Optional[int] = None) -> List[torch.Tensor]:
+        """`unet.prepare_cache` (unet_depth_streaming.py:283-302): zero caches in motion_module_idx order."""
+        n = self.n_rows if denoising_steps_num is None else denoising_steps_num
+        assert n == self.n_rows
+        return [torch.zeros(s, dtype=torch.float16, device=self.device) for s in self._kv_shapes]
+
+    @property
+    def device_bytes(self) -> int:
+        return lib().l2d_unet_device_bytes(self._handle)
+
+    @property
+    def launches_per_step(self) -> int:
+        return lib().l2d_unet_launches_per_step(self._handle)
+
+    def __del__(self):
+        if getattr(self, "_handle", None):
+            lib().l2d_unet_destroy(self._handle)
+            self._handle = None
+
+    def _kv_table(self, kv_cache):
+        ids = tuple(t.data_ptr() for t in kv_cache)
+        if ids != self._kv_ids:
+            if len(kv_cache) != len(self._kv_shapes):
+                raise ValueError(f"expected {len(self._kv_shapes)} kv-cache tensors, got {len(kv_cache)}")
+            for t, s in zip(kv_cache, self._kv_shapes):
+                if tuple(t.shape) != tuple(s) or t.dtype != torch.float16 or not t.is_cuda or not t.is_contiguous():
+                    raise ValueError(f"kv-cache tensor {tuple(t.shape)} {t.dtype}: expected contiguous CUDA fp16 {s}")
+            self._kv_arr = (C.c_void_p * len(ids))(*ids)
+            self._kv_ids = ids
+        return self._kv_arr
+
+    @torch.no_grad()
+    def __call__(self, sample, timestep, encoder_hidden_states=None, temporal_attention_mask=None, depth_sample=None,
+                 kv_cache=None, pe_idx=None, update_idx=None, return_dict: bool = True, **kwargs):
+        if any(v is None for v in (encoder_hidden_states, temporal_attention_mask, depth_sample, kv_cache, pe_idx,
+                                   update_idx)):
+            raise ValueError("stream.unet(...) needs encoder_hidden_states, temporal_attention_mask, depth_sample, "
+                             "kv_cache, pe_idx and update_idx")
+        self._sample.copy_(sample.reshape(self._sample.shape), non_blocking=True)
+        self._depth.copy_(depth_sample.reshape(self._depth.shape), non_blocking=True)
+        self._t.copy_(timestep.reshape(-1).expand(self.n_rows), non_blocking=True)   # int64 like the pipeline (:246)
+        self._ctx.copy_(encoder_hidden_states, non_blocking=True)
+        self._mask.copy_(temporal_attention_mask, non_blocking=True)
+        self._pe_idx.copy_(pe_idx, non_blocking=True)
+        self._upd.copy_(update_idx, non_blocking=True)
+        args = L2DUnetStepArgs()
+        args.sample, args.timestep = self._sample.data_ptr(), self._t.data_ptr()
+        args.encoder_hidden_states, args.temporal_attention_mask = self._ctx.data_ptr(), self._mask.data_ptr()
+        args.depth_sample = self._depth.data_ptr()
+        args.kv_cache = C.cast(self._kv_table(kv_cache), C.POINTER(C.c_void_p))
+        args.n_kv = len(kv_cache)
+        args.pe_idx, args.update_idx, args.out_sample = self._pe_idx.data_ptr(), self._upd.data_ptr(), self._out.data_ptr()
+        check(lib().l2d_unet_step(self._handle, C.byref(args), current_stream()))
+        out = self._out.clone()
+        if not return_dict:
+            return (out, kv_cache)
+        return UNetStepOutput(sample=out, kv_cache=kv_cache)
