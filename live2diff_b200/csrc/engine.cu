@@ -151,13 +151,80 @@ struct Scratch {
   float* gn_ws = nullptr;
 };
 
+enum Family { FAM_KV = 0, FAM_GEMM = 1, FAM_ATTN = 2, FAM_NORM = 3, FAM_IM2COL = 4, FAM_OTHER = 5, FAM_COUNT = 6 };
+
+// Per-kernel-family CUDA-event timing of one eager step (bench.py's roofline numbers come from here)
+struct Profiler {
+  bool on = false;
+  std::vector<cudaEvent_t> pool;
+  size_t used = 0;
+  std::vector<std::pair<size_t, size_t>> spans[FAM_COUNT];   // indices into pool (start, stop)
+  ~Profiler() {
+    for (cudaEvent_t e : pool) cudaEventDestroy(e);
+  }
+  size_t next() {
+    if (used == pool.size()) {
+      cudaEvent_t e;
+      cudaEventCreate(&e);
+      pool.push_back(e);
+    }
+    return used++;
+  }
+  void reset() {
+    used = 0;
+    for (auto& v : spans) v.clear();
+  }
+};
+
 // Shared by the UNet engine and the stand-alone temporal module (B2)
 struct Core {
   DevPool pool;
   cudaStream_t st = nullptr;
   int heads = 8, groups = 32, L = 16, n_rows = 2;
   Scratch s;
-  int64_t launches_mark = 0;
+  Profiler prof;
+
+  struct Scope {
+    Core& c;
+    size_t i0 = 0;
+    int fam;
+    Scope(Core& core, int f) : c(core), fam(f) {
+      if (c.prof.on) {
+        i0 = c.prof.next();
+        cudaEventRecord(c.prof.pool[i0], c.st);
+      }
+    }
+    ~Scope() {
+      if (c.prof.on) {
+        const size_t i1 = c.prof.next();
+        cudaEventRecord(c.prof.pool[i1], c.st);
+        c.prof.spans[fam].push_back({i0, i1});
+      }
+    }
+  };
+  int gemm_raw(const __half* a, int64_t lda, const __half* w, int64_t ldw, __half* out, int64_t ldo, int m, int n, int k,
+               const __half* bias, const __half* rg, int64_t rg_ld, int rpg, const __half* residual, int64_t ldr, int act,
+               int force_bn) {
+    Scope sc(*this, FAM_GEMM);
+    return gemm_launch(a, lda, w, ldw, out, ldo, m, n, k, bias, rg, rg_ld, rpg, residual, ldr, act, force_bn, st);
+  }
+  int kv(const KvAttnParams& p) {
+    Scope sc(*this, FAM_KV);
+    return kv_attn_launch(p, st);
+  }
+  int attn(const __half* q, int64_t ldq, const __half* k, int64_t ldk, const __half* v, int64_t ldv, __half* o, int64_t ldo,
+           int batch, int sq, int skv, int hd) {
+    Scope sc(*this, FAM_ATTN);
+    return attention_launch(q, ldq, k, ldk, v, ldv, o, ldo, batch, heads, sq, skv, hd, st);
+  }
+  int im2col(const __half* x, __half* y, int n_img, int h, int w, int c, int stride, int up) {
+    Scope sc(*this, FAM_IM2COL);
+    return l2d_im2col3x3(x, y, n_img, h, w, c, stride, up, 0, st);
+  }
+  int im2col4(const void* x, __half* y, int n_img, int h, int w) {
+    Scope sc(*this, FAM_IM2COL);
+    return l2d_im2col3x3_nchw4(x, y, n_img, h, w, st);
+  }
 
   int upload_copy(__half** dst, const __half* src, size_t n) {
     RC(pool.halfs(dst, n));
@@ -234,13 +301,15 @@ struct Core {
   // ---- op wrappers -------------------------------------------------------------------------
   int gemm(const __half* a, int64_t lda, const Lin& l, __half* out, int64_t ldo, int m, const __half* residual = nullptr,
            int64_t ldr = 0, int act = L2D_ACT_NONE, int force_bn = 0) {
-    return gemm_launch(a, lda, l.w, l.k, out, ldo, m, l.n, l.k, l.b, nullptr, 0, 1, residual, ldr, act, force_bn, st);
+    return gemm_raw(a, lda, l.w, l.k, out, ldo, m, l.n, l.k, l.b, nullptr, 0, 1, residual, ldr, act, force_bn);
   }
   int layernorm(const __half* x, const Norm& n, __half* y, int rows, int c) {
+    Scope sc(*this, FAM_NORM);
     return l2d_layernorm(x, n.g, n.b, y, rows, c, 1e-5f, st);
   }
   int gn(const __half* x1, int c1, const __half* x2, int c2, const Norm& n, __half* y, int n_img, int h, int w, float eps,
          int silu, int mode, int stride = 1) {
+    Scope sc(*this, mode == 1 ? FAM_IM2COL : FAM_NORM);   // the im2col variant is dominated by its 9x write
     return groupnorm_launch(x1, c1, x2, c2, n.g, n.b, y, s.gn_ws, n_img, h, w, groups, eps, silu, mode, stride, st);
   }
 
@@ -290,7 +359,7 @@ struct Core {
       p.q_pe = t.pe_tab[i]; p.k_pe = t.pe_tab[i] + c; p.v_pe = t.pe_tab[i] + 2 * c; p.pe_ld = 3 * c;
       p.mask = mask; p.pe_idx = pe_idx; p.update_idx = update_idx; p.out = s.att;
       p.n_rows = n_rows; p.hw = hw; p.L = L; p.C = c; p.heads = heads;
-      RC(kv_attn_launch(p, st));
+      RC(kv(p));
       RC(gemm(s.att, c, t.out[i], s.t, c, m, s.t, c));
     }
     RC(layernorm(s.t, t.ff_norm, s.ln, m, c));
@@ -386,7 +455,10 @@ struct l2d_unet {
   __half *hA = nullptr, *hB = nullptr, *temb_sin = nullptr, *temb1 = nullptr, *emb = nullptr, *temb_proj = nullptr,
          *kv2 = nullptr, *out8 = nullptr, *map_a = nullptr, *map_b = nullptr;
   int n_kv = 0;
-  // CUDA graph
+  // CUDA graph (captured and replayed on an engine-owned stream: the caller's stream may be the legacy
+  // default stream, which cannot be captured; events order the two streams)
+  cudaStream_t own_st = nullptr;
+  cudaEvent_t ev_in = nullptr, ev_out = nullptr;
   cudaGraphExec_t graph_exec = nullptr;
   l2d_unet_step_args captured{};
   std::vector<void*> captured_kv;
@@ -394,6 +466,9 @@ struct l2d_unet {
   int64_t launches_per_step = 0;
   ~l2d_unet() {
     if (graph_exec) cudaGraphExecDestroy(graph_exec);
+    if (ev_in) cudaEventDestroy(ev_in);
+    if (ev_out) cudaEventDestroy(ev_out);
+    if (own_st) cudaStreamDestroy(own_st);
   }
 };
 
@@ -435,8 +510,8 @@ int load_spatial(l2d_unet* u, const WeightTable& wt, const std::string& p, int c
 // conv3x3 as GEMM over an im2col matrix already in s.cols
 int conv_gemm(Core& k, const Conv3& cv, __half* out, int64_t ldo, int m, const __half* rg, int64_t rg_ld, int rpg,
               const __half* residual, int64_t ldr, int act) {
-  return gemm_launch(k.s.cols, cv.kpad, cv.w, cv.kpad, out, ldo, m, cv.n_pad, cv.kpad, cv.b, rg, rg_ld, rpg, residual, ldr,
-                     act, 0, k.st);
+  return k.gemm_raw(k.s.cols, cv.kpad, cv.w, cv.kpad, out, ldo, m, cv.n_pad, cv.kpad, cv.b, rg, rg_ld, rpg, residual, ldr,
+                    act, 0);
 }
 
 // ResnetBlock3D.forward (resnet.py:229-259); input = concat(x1[M,c1], x2[M,c2]) channels-last
@@ -452,11 +527,11 @@ int resnet_forward(l2d_unet* u, const ResnetP& r, const __half* x1, int c1, cons
   int64_t ldr = c1;
   if (r.shortcut.n) {
     // 1x1 conv over the (virtual) channel concat: two K segments of the same weight matrix
-    RC(gemm_launch(x1, c1, r.shortcut.w, r.cin, k.s.sc, r.cout, m, r.cout, c1, r.shortcut.b, nullptr, 0, 1, nullptr, 0,
-                   L2D_ACT_NONE, 0, k.st));
+    RC(k.gemm_raw(x1, c1, r.shortcut.w, r.cin, k.s.sc, r.cout, m, r.cout, c1, r.shortcut.b, nullptr, 0, 1, nullptr, 0,
+                  L2D_ACT_NONE, 0));
     if (c2 > 0)
-      RC(gemm_launch(x2, c2, r.shortcut.w + c1, r.cin, k.s.sc, r.cout, m, r.cout, c2, nullptr, nullptr, 0, 1, k.s.sc,
-                     r.cout, L2D_ACT_NONE, 0, k.st));
+      RC(k.gemm_raw(x2, c2, r.shortcut.w + c1, r.cin, k.s.sc, r.cout, m, r.cout, c2, nullptr, nullptr, 0, 1, k.s.sc,
+                    r.cout, L2D_ACT_NONE, 0));
     res = k.s.sc;
     ldr = r.cout;
   } else if (c2 > 0) {
@@ -470,20 +545,20 @@ int resnet_forward(l2d_unet* u, const ResnetP& r, const __half* x1, int c1, cons
 int spatial_forward(l2d_unet* u, const SpatialP& sp, const __half* x, __half* out, const Level& lv) {
   Core& k = u->core;
   Scratch& s = k.s;
-  const int c = sp.c, m = lv.m, hw = lv.h * lv.w, n = k.n_rows, heads = k.heads, hd = c / heads;
+  const int c = sp.c, m = lv.m, hw = lv.h * lv.w, n = k.n_rows, hd = c / k.heads;
   const int ctx = u->cfg.ctx_len;
   RC(k.gn(x, c, nullptr, 0, sp.norm, s.t0, n, lv.h, lv.w, 1e-6f, 0, 0));
   RC(k.gemm(s.t0, c, sp.proj_in, s.t, c, m));
   // self-attention
   RC(k.layernorm(s.t, sp.ln1, s.ln, m, c));
   RC(k.gemm(s.ln, c, sp.qkv, s.qkv, 3 * c, m));
-  RC(attention_launch(s.qkv, 3 * c, s.qkv + c, 3 * c, s.qkv + 2 * c, 3 * c, s.att, c, n, heads, hw, hw, hd, k.st));
+  RC(k.attn(s.qkv, 3 * c, s.qkv + c, 3 * c, s.qkv + 2 * c, 3 * c, s.att, c, n, hw, hw, hd));
   RC(k.gemm(s.att, c, sp.out1, s.t, c, m, s.t, c));
   // cross-attention against the (pre-projected) text context
   RC(k.layernorm(s.t, sp.ln2, s.ln, m, c));
   RC(k.gemm(s.ln, c, sp.q2, s.q2, c, m));
   const __half* kv = u->kv2 + sp.kv2_off;
-  RC(attention_launch(s.q2, c, kv, u->kv2_all.n, kv + c, u->kv2_all.n, s.att, c, n, heads, hw, ctx, hd, k.st));
+  RC(k.attn(s.q2, c, kv, u->kv2_all.n, kv + c, u->kv2_all.n, s.att, c, n, hw, ctx, hd));
   RC(k.gemm(s.att, c, sp.out2, s.t, c, m, s.t, c));
   // feed-forward
   RC(k.layernorm(s.t, sp.ln3, s.ln, m, c));
@@ -502,10 +577,13 @@ int run_step(l2d_unet* u, const l2d_unet_step_args* a) {
   cudaStream_t st = k.st;
 
   // time embedding (unet_depth_streaming.py:497-505) and every resnet's time_emb_proj(SiLU(emb)) (resnet.py:237-238)
-  RC(l2d_timestep_embedding(a->timestep, u->temb_sin, n, cfg.block_out_channels[0], st));
+  {
+    Core::Scope sc(k, FAM_OTHER);
+    RC(l2d_timestep_embedding(a->timestep, u->temb_sin, n, cfg.block_out_channels[0], st));
   RC(l2d_small_linear(u->temb_sin, u->time1.w, u->time1.b, u->temb1, n, u->time1.n, u->time1.k, 0, 1, st));
   RC(l2d_small_linear(u->temb1, u->time2.w, u->time2.b, u->emb, n, u->time2.n, u->time2.k, 0, 0, st));
-  RC(l2d_small_linear(u->emb, u->temb_all.w, u->temb_all.b, u->temb_proj, n, u->temb_all.n, u->temb_all.k, 1, 0, st));
+    RC(l2d_small_linear(u->emb, u->temb_all.w, u->temb_all.b, u->temb_proj, n, u->temb_all.n, u->temb_all.k, 1, 0, st));
+  }
   // K|V projections of the text context for all 16 cross-attention blocks in one GEMM
   RC(k.gemm(static_cast<const __half*>(a->encoder_hidden_states), cfg.cross_attention_dim, u->kv2_all, u->kv2,
             u->kv2_all.n, n * cfg.ctx_len));
@@ -514,26 +592,27 @@ int run_step(l2d_unet* u, const l2d_unet_step_args* a) {
   const Level& l0 = u->lv[0];
   __half* x = u->hA;
   __half* y = u->hB;
-  RC(l2d_im2col3x3_nchw4(a->sample, s.cols, n, l0.h, l0.w, st));
+  RC(k.im2col4(a->sample, s.cols, n, l0.h, l0.w));
   RC(conv_gemm(k, u->conv_in, x, l0.c, l0.m, nullptr, 0, 1, nullptr, 0, L2D_ACT_NONE));
   {
-    RC(l2d_im2col3x3_nchw4(a->depth_sample, s.cols, n, l0.h, l0.w, st));
+    RC(k.im2col4(a->depth_sample, s.cols, n, l0.h, l0.w));
     __half* cur = u->map_a;
     __half* nxt = u->map_b;
     RC(conv_gemm(k, u->map_in, cur, u->map_in.n_pad, l0.m, nullptr, 0, 1, nullptr, 0, L2D_ACT_SILU));
     int cc = u->map_in.n_pad;
     for (const Conv3& cv : u->map_blocks) {
-      RC(l2d_im2col3x3(cur, s.cols, n, l0.h, l0.w, cc, 1, 0, 0, st));
+      RC(k.im2col(cur, s.cols, n, l0.h, l0.w, cc, 1, 0));
       RC(conv_gemm(k, cv, nxt, cv.n_pad, l0.m, nullptr, 0, 1, nullptr, 0, L2D_ACT_SILU));
       std::swap(cur, nxt);
       cc = cv.n_pad;
     }
-    RC(l2d_im2col3x3(cur, s.cols, n, l0.h, l0.w, cc, 1, 0, 0, st));
+    RC(k.im2col(cur, s.cols, n, l0.h, l0.w, cc, 1, 0));
     RC(conv_gemm(k, u->map_out, x, l0.c, l0.m, nullptr, 0, 1, x, l0.c, L2D_ACT_NONE));   // sample += mapping(depth)
   }
 
   int kv_i = 0, skip_i = 0;
   auto push_skip = [&](const __half* src, const Level& lvl) -> int {
+    Core::Scope sc(k, FAM_OTHER);
     L2D_CUDA(cudaMemcpyAsync(u->skips[skip_i], src, (size_t)lvl.m * lvl.c * sizeof(__half), cudaMemcpyDeviceToDevice, st));
     count_launch();
     ++skip_i;
@@ -560,7 +639,7 @@ int run_step(l2d_unet* u, const l2d_unet_step_args* a) {
     }
     if (bi != nlev - 1) {
       const Level& nl = u->lv[bi + 1];
-      RC(l2d_im2col3x3(x, s.cols, n, lvl.h, lvl.w, lvl.c, 2, 0, 0, st));
+      RC(k.im2col(x, s.cols, n, lvl.h, lvl.w, lvl.c, 2, 0));
       RC(conv_gemm(k, u->down_samp[bi], y, lvl.c, nl.m, nullptr, 0, 1, nullptr, 0, L2D_ACT_NONE));
       std::swap(x, y);
       Level ds{lvl.c, nl.h, nl.w, nl.m};
@@ -601,7 +680,7 @@ int run_step(l2d_unet* u, const l2d_unet_step_args* a) {
     }
     if (bi != nlev - 1) {
       const Level& nl = u->lv[nlev - 2 - bi];
-      RC(l2d_im2col3x3(x, s.cols, n, lvl.h, lvl.w, lvl.c, 1, 1, 0, st));
+      RC(k.im2col(x, s.cols, n, lvl.h, lvl.w, lvl.c, 1, 1));
       RC(conv_gemm(k, u->up_samp[bi], y, lvl.c, nl.m, nullptr, 0, 1, nullptr, 0, L2D_ACT_NONE));
       std::swap(x, y);
     }
@@ -858,46 +937,89 @@ extern "C" int l2d_unet_step(l2d_unet* u, const l2d_unet_step_args* a, void* str
   L2D_CHECK_ARG(a->n_kv == u->n_kv, "expected " + std::to_string(u->n_kv) + " kv-cache tensors");
   for (int i = 0; i < a->n_kv; ++i) L2D_CHECK_ARG(a->kv_cache[i] != nullptr, "null kv-cache pointer");
   Core& k = u->core;
-  k.st = (cudaStream_t)stream;
+  cudaStream_t caller = (cudaStream_t)stream;
   const int64_t l0 = l2d_launch_count();
-  if (!u->cfg.use_cuda_graph || u->steps_done == 0) {
-    // eager (the first step always is: it sizes smem attributes and fills the tensor-map cache)
+  if (!u->cfg.use_cuda_graph) {
+    k.st = caller;
     RC(run_step(u, a));
     u->launches_per_step = l2d_launch_count() - l0;
     ++u->steps_done;
     return L2D_OK;
   }
-  bool same = u->graph_exec != nullptr && u->captured.sample == a->sample && u->captured.timestep == a->timestep &&
-              u->captured.encoder_hidden_states == a->encoder_hidden_states &&
-              u->captured.temporal_attention_mask == a->temporal_attention_mask &&
-              u->captured.depth_sample == a->depth_sample && u->captured.pe_idx == a->pe_idx &&
-              u->captured.update_idx == a->update_idx && u->captured.out_sample == a->out_sample &&
-              (int)u->captured_kv.size() == a->n_kv;
-  for (int i = 0; same && i < a->n_kv; ++i) same = u->captured_kv[i] == a->kv_cache[i];
-  if (!same) {
-    if (u->graph_exec) {
-      cudaGraphExecDestroy(u->graph_exec);
-      u->graph_exec = nullptr;
-    }
-    cudaGraph_t graph = nullptr;
-    L2D_CUDA(cudaStreamBeginCapture(k.st, cudaStreamCaptureModeThreadLocal));
-    const int rc = run_step(u, a);
-    cudaError_t e = cudaStreamEndCapture(k.st, &graph);
-    if (rc != L2D_OK) {
-      if (graph) cudaGraphDestroy(graph);
-      return rc;
-    }
-    if (e != cudaSuccess) return fail(L2D_ERR_CUDA, std::string("cudaStreamEndCapture: ") + cudaGetErrorString(e));
-    e = cudaGraphInstantiate(&u->graph_exec, graph, 0);
-    cudaGraphDestroy(graph);
-    if (e != cudaSuccess) return fail(L2D_ERR_CUDA, std::string("cudaGraphInstantiate: ") + cudaGetErrorString(e));
-    u->captured = *a;
-    u->captured_kv.assign(a->kv_cache, a->kv_cache + a->n_kv);
-    u->launches_per_step = l2d_launch_count() - l0;
-    count_launch(-(int)u->launches_per_step);   // capture enqueued nothing; the replay below is what runs
+  if (!u->own_st) {
+    L2D_CUDA(cudaStreamCreateWithFlags(&u->own_st, cudaStreamNonBlocking));
+    L2D_CUDA(cudaEventCreateWithFlags(&u->ev_in, cudaEventDisableTiming));
+    L2D_CUDA(cudaEventCreateWithFlags(&u->ev_out, cudaEventDisableTiming));
   }
-  L2D_CUDA(cudaGraphLaunch(u->graph_exec, k.st));
-  count_launch((int)u->launches_per_step);
+  // everything the caller enqueued so far (input staging) happens-before the step
+  L2D_CUDA(cudaEventRecord(u->ev_in, caller));
+  L2D_CUDA(cudaStreamWaitEvent(u->own_st, u->ev_in, 0));
+  k.st = u->own_st;
+  if (u->steps_done == 0) {
+    // the first step is always eager: it sizes smem attributes and fills the tensor-map cache
+    RC(run_step(u, a));
+    u->launches_per_step = l2d_launch_count() - l0;
+  } else {
+    bool same = u->graph_exec != nullptr && u->captured.sample == a->sample && u->captured.timestep == a->timestep &&
+                u->captured.encoder_hidden_states == a->encoder_hidden_states &&
+                u->captured.temporal_attention_mask == a->temporal_attention_mask &&
+                u->captured.depth_sample == a->depth_sample && u->captured.pe_idx == a->pe_idx &&
+                u->captured.update_idx == a->update_idx && u->captured.out_sample == a->out_sample &&
+                (int)u->captured_kv.size() == a->n_kv;
+    for (int i = 0; same && i < a->n_kv; ++i) same = u->captured_kv[i] == a->kv_cache[i];
+    if (!same) {
+      if (u->graph_exec) {
+        cudaGraphExecDestroy(u->graph_exec);
+        u->graph_exec = nullptr;
+      }
+      cudaGraph_t graph = nullptr;
+      L2D_CUDA(cudaStreamBeginCapture(k.st, cudaStreamCaptureModeThreadLocal));
+      const int rc = run_step(u, a);
+      cudaError_t e = cudaStreamEndCapture(k.st, &graph);
+      if (rc != L2D_OK) {
+        if (graph) cudaGraphDestroy(graph);
+        return rc;
+      }
+      if (e != cudaSuccess) return fail(L2D_ERR_CUDA, std::string("cudaStreamEndCapture: ") + cudaGetErrorString(e));
+      e = cudaGraphInstantiate(&u->graph_exec, graph, 0);
+      cudaGraphDestroy(graph);
+      if (e != cudaSuccess) return fail(L2D_ERR_CUDA, std::string("cudaGraphInstantiate: ") + cudaGetErrorString(e));
+      u->captured = *a;
+      u->captured_kv.assign(a->kv_cache, a->kv_cache + a->n_kv);
+      u->launches_per_step = l2d_launch_count() - l0;
+      count_launch(-(int)u->launches_per_step);   // capture enqueued nothing; the replay below is what runs
+    }
+    L2D_CUDA(cudaGraphLaunch(u->graph_exec, k.st));
+    count_launch((int)u->launches_per_step);
+  }
+  L2D_CUDA(cudaEventRecord(u->ev_out, u->own_st));
+  L2D_CUDA(cudaStreamWaitEvent(caller, u->ev_out, 0));
+  ++u->steps_done;
+  return L2D_OK;
+}
+
+extern "C" int l2d_unet_profile_step(l2d_unet* u, const l2d_unet_step_args* a, void* stream, float* ms_by_family,
+                                     int32_t* launches_by_family) {
+  L2D_CHECK_ARG(u && a && ms_by_family && launches_by_family, "null arguments");
+  L2D_CHECK_ARG(a->n_kv == u->n_kv && a->kv_cache, "bad kv-cache table");
+  Core& k = u->core;
+  k.st = (cudaStream_t)stream;
+  k.prof.reset();
+  k.prof.on = true;
+  const int rc = run_step(u, a);
+  k.prof.on = false;
+  if (rc != L2D_OK) return rc;
+  L2D_CUDA(cudaStreamSynchronize(k.st));
+  for (int f = 0; f < FAM_COUNT; ++f) {
+    float tot = 0.f;
+    for (auto& sp : k.prof.spans[f]) {
+      float ms = 0.f;
+      L2D_CUDA(cudaEventElapsedTime(&ms, k.prof.pool[sp.first], k.prof.pool[sp.second]));
+      tot += ms;
+    }
+    ms_by_family[f] = tot;
+    launches_by_family[f] = (int32_t)k.prof.spans[f].size();
+  }
   ++u->steps_done;
   return L2D_OK;
 }

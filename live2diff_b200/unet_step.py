@@ -126,13 +126,11 @@ class B200UNetStep:
             self._kv_ids = ids
         return self._kv_arr
 
-    @torch.no_grad()
-    def __call__(self, sample, timestep, encoder_hidden_states=None, temporal_attention_mask=None, depth_sample=None,
-                 kv_cache=None, pe_idx=None, update_idx=None, return_dict: bool = True, **kwargs):
-        if any(v is None for v in (encoder_hidden_states, temporal_attention_mask, depth_sample, kv_cache, pe_idx,
-                                   update_idx)):
-            raise ValueError("stream.unet(...) needs encoder_hidden_states, temporal_attention_mask, depth_sample, "
-                             "kv_cache, pe_idx and update_idx")
+    FAMILIES = ("kv_attn", "gemm", "spatial_attn", "norm", "im2col", "other")
+
+    def _stage(self, sample, timestep, encoder_hidden_states, temporal_attention_mask, depth_sample, kv_cache, pe_idx,
+               update_idx):
+        """Copy the call's inputs into the fixed staging buffers (stable addresses for the CUDA graph)."""
         self._sample.copy_(sample.reshape(self._sample.shape), non_blocking=True)
         self._depth.copy_(depth_sample.reshape(self._depth.shape), non_blocking=True)
         self._t.copy_(timestep.reshape(-1).expand(self.n_rows), non_blocking=True)   # int64 like the pipeline (:246)
@@ -147,6 +145,28 @@ class B200UNetStep:
         args.kv_cache = C.cast(self._kv_table(kv_cache), C.POINTER(C.c_void_p))
         args.n_kv = len(kv_cache)
         args.pe_idx, args.update_idx, args.out_sample = self._pe_idx.data_ptr(), self._upd.data_ptr(), self._out.data_ptr()
+        return args
+
+    @torch.no_grad()
+    def profile_step(self, sample, timestep, *, encoder_hidden_states, temporal_attention_mask, depth_sample, kv_cache,
+                     pe_idx, update_idx):
+        """One real, eager step with CUDA events around every launch; returns {family: (ms, launches)}."""
+        args = self._stage(sample, timestep, encoder_hidden_states, temporal_attention_mask, depth_sample, kv_cache,
+                           pe_idx, update_idx)
+        ms = (C.c_float * 6)()
+        cnt = (C.c_int32 * 6)()
+        check(lib().l2d_unet_profile_step(self._handle, C.byref(args), current_stream(), ms, cnt))
+        return {f: (float(ms[i]), int(cnt[i])) for i, f in enumerate(self.FAMILIES)}
+
+    @torch.no_grad()
+    def __call__(self, sample, timestep, encoder_hidden_states=None, temporal_attention_mask=None, depth_sample=None,
+                 kv_cache=None, pe_idx=None, update_idx=None, return_dict: bool = True, **kwargs):
+        if any(v is None for v in (encoder_hidden_states, temporal_attention_mask, depth_sample, kv_cache, pe_idx,
+                                   update_idx)):
+            raise ValueError("stream.unet(...) needs encoder_hidden_states, temporal_attention_mask, depth_sample, "
+                             "kv_cache, pe_idx and update_idx")
+        args = self._stage(sample, timestep, encoder_hidden_states, temporal_attention_mask, depth_sample, kv_cache,
+                           pe_idx, update_idx)
         check(lib().l2d_unet_step(self._handle, C.byref(args), current_stream()))
         out = self._out.clone()
         if not return_dict:

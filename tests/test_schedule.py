@@ -69,3 +69,39 @@ def test_lcm_constants():
     assert sub.tolist() == [399, 199]
     torch.testing.assert_close(a * a + b * b, torch.ones(2))
     assert 0 < float(c_skip[0]) < 1e-6 and 0.999 < float(c_out[0]) <= 1.0
+
+
+# ---- the product's host-side state machine (live2diff_b200.schedule) against the same reference traces ----
+@pytest.mark.parametrize("i", range(4))
+def test_product_ring_schedule_matches_reference_trace(i):
+    from live2diff_b200.schedule import RingSchedule
+
+    tr = traces()[i]
+    rs = RingSchedule(tr["n_rows"], tr["window"], tr["warmup"])
+    for f in tr["frames"]:
+        assert [[1] * v + [0] * (tr["window"] - v) for v in rs.valid] == f["valid"]
+        assert rs.pe_idx == f["pe_idx"]
+        assert rs.update_idx == f["update_idx"]
+        rs.advance()
+
+
+def test_product_ring_schedule_n1():
+    from live2diff_b200.schedule import RingSchedule
+
+    rs = RingSchedule(1, 4, 2)
+    ab, pe, up = S.init_schedule(1, 4, 2)
+    for _ in range(12):
+        assert rs.mask_rows() == ab.tolist() and rs.pe_idx == pe.tolist() and rs.update_idx == up.tolist()
+        rs.advance()
+        S.update_schedule(ab, pe, up, 4, 2)
+
+
+def test_product_lcm_constants_match_oracle():
+    from live2diff_b200.schedule import stream_constants
+
+    for tl in ([30, 40], [25, 31, 37, 43], [0]):
+        c = stream_constants(tl)
+        sub, c_skip, c_out, a, b = S.stream_constants(tl)
+        assert c.timesteps == sub.tolist()
+        torch.testing.assert_close(torch.tensor(c.table(), dtype=torch.float32), torch.stack([a, b, c_skip, c_out]),
+                                   rtol=1e-6, atol=1e-7)
