@@ -17,6 +17,7 @@
 // Partial tiles rely on TMA out-of-bounds zero fill (loads) and predicated stores.
 #include <cuda.h>
 
+#include <algorithm>
 #include <mutex>
 #include <unordered_map>
 
@@ -132,6 +133,10 @@ struct GemmEpilogue {
   const __half* residual;       // [M, ldr] or null
   int64_t ldr;
   int act;
+  // split-K (gridDim.z > 1): fp32 partial sums + per-tile arrival counters, both all-zero between launches
+  float* ws;
+  int64_t ws_ld;
+  int* counters;
 };
 
 template <int BN>
@@ -185,7 +190,11 @@ gemm_f16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid
   const int lane = threadIdx.x & 31;
   const int n0 = blockIdx.x * BN;
   const int m0 = blockIdx.y * BM;
-  const int num_kb = (K + BK - 1) / BK;
+  const int total_kb = (K + BK - 1) / BK;
+  const int kb_per = (total_kb + (int)gridDim.z - 1) / (int)gridDim.z;
+  const int kb_begin = (int)blockIdx.z * kb_per;
+  const int num_kb = max(0, min(total_kb, kb_begin + kb_per) - kb_begin);   // k-blocks of this split (may be 0)
+  __shared__ int s_is_last;
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmap_a);
@@ -212,8 +221,8 @@ gemm_f16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid
         mbar_wait(smem_u32(&empty_bar[s]), ph ^ 1u);
         const uint32_t fb = smem_u32(&full_bar[s]);
         mbar_expect_tx(fb, S::STAGE_BYTES);
-        tma_load_2d(smem_u32(smem_a + s * S::A_BYTES), &tmap_a, fb, kb * BK, m0);
-        tma_load_2d(smem_u32(smem_b + s * S::B_BYTES), &tmap_b, fb, kb * BK, n0);
+        tma_load_2d(smem_u32(smem_a + s * S::A_BYTES), &tmap_a, fb, (kb_begin + kb) * BK, m0);
+        tma_load_2d(smem_u32(smem_b + s * S::B_BYTES), &tmap_b, fb, (kb_begin + kb) * BK, n0);
       }
     }
   } else if (warp == 1) {
@@ -234,7 +243,7 @@ gemm_f16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid
         }
         umma_commit(smem_u32(&empty_bar[s]));  // slot free once these MMAs have read it
       }
-      umma_commit(smem_u32(tmem_full_bar));    // accumulator complete
+      umma_commit(smem_u32(tmem_full_bar));    // accumulator complete (fires immediately when num_kb == 0)
     }
   } else {
     // ===================== epilogue (warps 2..5) =====================
@@ -246,39 +255,90 @@ gemm_f16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid
     const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
     const __half* rg = (epi.rowgroup_bias && row_ok)
                            ? epi.rowgroup_bias + (size_t)(row / epi.rows_per_group) * epi.rg_ld : nullptr;
-    if (epi.act != L2D_ACT_GEGLU) {
+    // bias / per-image bias / activation / residual / fp16 store of 16 consecutive output columns
+    auto finish16 = [&](float (&v)[16], int cc) {
+      const int col0 = n0 + cc * 16;
+#pragma unroll
+      for (int hlf = 0; hlf < 2; ++hlf) {
+        const int col = col0 + hlf * 8;
+        if (col < N) {
+          if (epi.bias) {
+            float b[8];
+            unpack8(ldg_cached(epi.bias + col), b);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[hlf * 8 + i] += b[i];
+          }
+          if (rg) {
+            float b[8];
+            unpack8(ldg_cached(rg + col), b);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[hlf * 8 + i] += b[i];
+          }
+        }
+      }
+      if (epi.act == L2D_ACT_SILU) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] = silu_f(v[i]);
+      }
+      epi_store16(epi, v, row, col0, M, N, row_ok);
+    };
+    if (gridDim.z > 1) {
+      // ---- split-K: add this split's partial tile into the fp32 workspace; the last-arriving CTA of the
+      //      tile applies the epilogue and restores the workspace/counter to zero ----
+      float* wrow = epi.ws + (size_t)row * epi.ws_ld;
+      if (num_kb > 0) {
+#pragma unroll 1
+        for (int cc = 0; cc < BN / 16; ++cc) {
+          uint32_t r[16];
+          tmem_ld16(taddr + cc * 16, r);
+          tmem_ld_wait();
+          if (row_ok) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i)
+              if (n0 + cc * 16 + i < N) atomicAdd(wrow + n0 + cc * 16 + i, __uint_as_float(r[i]));
+          }
+        }
+      }
+      __threadfence();
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (threadIdx.x == 64) {
+        const int tile_id = blockIdx.y * gridDim.x + blockIdx.x;
+        s_is_last = (atomicAdd(epi.counters + tile_id, 1) == (int)gridDim.z - 1) ? 1 : 0;
+        if (s_is_last) epi.counters[tile_id] = 0;
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (s_is_last) {
+        __threadfence();
+#pragma unroll 1
+        for (int cc = 0; cc < BN / 16; ++cc) {
+          float v[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) v[i] = 0.f;
+          if (row_ok) {
+#pragma unroll
+            for (int q4 = 0; q4 < 4; ++q4) {
+              const int col = n0 + cc * 16 + q4 * 4;
+              if (col < N) {
+                float4* src = reinterpret_cast<float4*>(wrow + col);
+                const float4 t = __ldcg(src);
+                *src = make_float4(0.f, 0.f, 0.f, 0.f);
+                v[q4 * 4 + 0] = t.x; v[q4 * 4 + 1] = t.y; v[q4 * 4 + 2] = t.z; v[q4 * 4 + 3] = t.w;
+              }
+            }
+          }
+          finish16(v, cc);
+        }
+      }
+    } else if (epi.act != L2D_ACT_GEGLU) {
 #pragma unroll 1
       for (int cc = 0; cc < BN / 16; ++cc) {
         uint32_t r[16];
         tmem_ld16(taddr + cc * 16, r);
         tmem_ld_wait();
-        const int col0 = n0 + cc * 16;
         float v[16];
 #pragma unroll
         for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
-#pragma unroll
-        for (int hlf = 0; hlf < 2; ++hlf) {
-          const int col = col0 + hlf * 8;
-          if (col < N) {
-            if (epi.bias) {
-              float b[8];
-              unpack8(ldg_cached(epi.bias + col), b);
-#pragma unroll
-              for (int i = 0; i < 8; ++i) v[hlf * 8 + i] += b[i];
-            }
-            if (rg) {
-              float b[8];
-              unpack8(ldg_cached(rg + col), b);
-#pragma unroll
-              for (int i = 0; i < 8; ++i) v[hlf * 8 + i] += b[i];
-            }
-          }
-        }
-        if (epi.act == L2D_ACT_SILU) {
-#pragma unroll
-          for (int i = 0; i < 16; ++i) v[i] = silu_f(v[i]);
-        }
-        epi_store16(epi, v, row, col0, M, N, row_ok);
+        finish16(v, cc);
       }
     } else {
       // GEGLU: tile columns [0,BN/2) = value half, [BN/2,BN) = matching gate half (weights interleaved
@@ -388,26 +448,65 @@ static int get_tmap(const void* ptr, int64_t rows, int64_t cols, int64_t ld, int
   return L2D_OK;
 }
 
-int gemm_pick_tile_n(int m, int n, int k) {
-  (void)k;
+// Cost model (SM cycles).  Measured on B200 (profiles/launches_r1.csv): a CTA's main loop is bound by the
+// L2 -> shared-memory fill rate of its SM, ~42 B/clk, i.e. (128+BN)*128/42 cycles per 64-deep k-block, far above the
+// tcgen05 issue time (BN/2 cycles).  So bigger N tiles are cheaper per flop, and small-M problems must be spread
+// over the SMs by splitting K.
+constexpr int kNumSms = 148;
+constexpr int64_t kWsElems = 4 << 20;   // fp32 split-K workspace (16 MB)
+constexpr int kMaxTiles = 4096;
+
+struct GemmPlan {
+  int bn, splits;
+};
+
+static GemmPlan gemm_plan(int m, int n, int k, bool allow_split, int force_bn) {
   const int cands[4] = {256, 160, 128, 64};
-  int best = 64;
+  const int tiles_m = ceil_div(m, BM), num_kb = ceil_div(k, BK);
+  GemmPlan best{64, 1};
   double best_cost = 1e30;
-  const int tiles_m = ceil_div(m, BM);
   for (int bn : cands) {
-    const int tiles = tiles_m * ceil_div(n, bn);
-    const int waves = ceil_div(tiles, 148);
-    const double cost = (double)waves * (bn + 128);
-    if (cost < best_cost - 1e-9) {
-      best_cost = cost;
-      best = bn;
+    if (force_bn > 0 && bn != force_bn) continue;
+    const int tiles_n = ceil_div(n, bn), tiles = tiles_m * tiles_n;
+    const double kb_cyc = (128.0 + bn) * 128.0 / 42.0;
+    int max_s = 1;
+    if (allow_split && (int64_t)tiles_m * BM * tiles_n * bn <= kWsElems && tiles <= kMaxTiles)
+      max_s = std::max(1, std::min(32, num_kb / 4));
+    for (int sp = 1; sp <= max_s; ++sp) {
+      const int kb_per = ceil_div(num_kb, sp);
+      if (sp > 1 && kb_per * (sp - 1) >= num_kb) continue;        // an empty last split: pointless
+      const int waves = ceil_div(tiles * sp, kNumSms);
+      double cta = kb_per * kb_cyc + 3000.0;
+      if (sp > 1) cta += 16.0 * bn + 1500.0;                      // fp32 atomics of the partial tile + final pass
+      const double cost = waves * cta;
+      if (cost < best_cost * 0.97 || (cost < best_cost && sp < best.splits)) {
+        best_cost = cost;
+        best = {bn, sp};
+      }
     }
   }
   return best;
 }
 
+int gemm_pick_tile_n(int m, int n, int k) { return gemm_plan(m, n, k, false, 0).bn; }
+
+static float* g_ws = nullptr;
+static int* g_counters = nullptr;
+
+static int ensure_splitk_workspace() {
+  if (g_ws) return L2D_OK;
+  cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+  L2D_CUDA(cudaMalloc(&g_ws, kWsElems * sizeof(float)));
+  L2D_CUDA(cudaMalloc(&g_counters, kMaxTiles * sizeof(int)));
+  L2D_CUDA(cudaMemset(g_ws, 0, kWsElems * sizeof(float)));
+  L2D_CUDA(cudaMemset(g_counters, 0, kMaxTiles * sizeof(int)));
+  L2D_CUDA(cudaDeviceSynchronize());
+  (void)cs;
+  return L2D_OK;
+}
+
 template <int BN, int STAGES>
-static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmEpilogue& e, int M, int N, int K,
+static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmEpilogue& e, int M, int N, int K, int splits,
                        cudaStream_t st) {
   constexpr size_t smem = (size_t)STAGES * GemmSmem<BN>::STAGE_BYTES + (2 * STAGES + 2) * 8 + 1024;
   static bool configured = false;
@@ -416,7 +515,7 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmE
                                   (int)smem));
     configured = true;
   }
-  dim3 grid(ceil_div(N, BN), ceil_div(M, BM));
+  dim3 grid(ceil_div(N, BN), ceil_div(M, BM), splits);
   gemm_f16_tcgen05_kernel<BN, STAGES><<<grid, 192, smem, st>>>(ta, tb, e, M, N, K);
   L2D_LAUNCH_CHECK();
   return L2D_OK;
@@ -425,18 +524,27 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmE
 int gemm_launch(const __half* a, int64_t lda, const __half* w, int64_t ldw, __half* out, int64_t ldo, int m, int n, int k,
                 const __half* bias, const __half* rowgroup_bias, int64_t rg_ld, int rows_per_group,
                 const __half* residual, int64_t ldr, int act, int force_bn, cudaStream_t st) {
-  const int bn = force_bn > 0 ? force_bn : gemm_pick_tile_n(m, n, k);
+  const GemmPlan plan = gemm_plan(m, n, k, act != L2D_ACT_GEGLU, force_bn);
+  const int bn = plan.bn;
   CUtensorMap ta, tb;
   int rc = get_tmap(a, m, k, lda, BM, &ta);
   if (rc != L2D_OK) return rc;
   rc = get_tmap(w, n, k, ldw, bn, &tb);
   if (rc != L2D_OK) return rc;
-  GemmEpilogue e{out, ldo, bias, rowgroup_bias, rg_ld, rows_per_group > 0 ? rows_per_group : 1, residual, ldr, act};
+  GemmEpilogue e{out, ldo, bias, rowgroup_bias, rg_ld, rows_per_group > 0 ? rows_per_group : 1, residual, ldr, act,
+                 nullptr, 0, nullptr};
+  if (plan.splits > 1) {
+    rc = ensure_splitk_workspace();
+    if (rc != L2D_OK) return rc;
+    e.ws = g_ws;
+    e.ws_ld = (int64_t)ceil_div(n, bn) * bn;
+    e.counters = g_counters;
+  }
   switch (bn) {
-    case 64: return launch_gemm<64, 6>(ta, tb, e, m, n, k, st);
-    case 128: return launch_gemm<128, 6>(ta, tb, e, m, n, k, st);
-    case 160: return launch_gemm<160, 5>(ta, tb, e, m, n, k, st);
-    case 256: return launch_gemm<256, 4>(ta, tb, e, m, n, k, st);
+    case 64: return launch_gemm<64, 6>(ta, tb, e, m, n, k, plan.splits, st);
+    case 128: return launch_gemm<128, 6>(ta, tb, e, m, n, k, plan.splits, st);
+    case 160: return launch_gemm<160, 5>(ta, tb, e, m, n, k, plan.splits, st);
+    case 256: return launch_gemm<256, 4>(ta, tb, e, m, n, k, plan.splits, st);
     default: return fail(L2D_ERR_INVALID, "gemm: unsupported tile_n");
   }
 }

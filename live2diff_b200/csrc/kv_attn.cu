@@ -4,170 +4,240 @@
 // PE-by-index add, rounding of q+pe / K+pe / V+pe to fp16) and :172-194 (per-row additive mask,
 // q_len == 1 SDPA over the L-slot window).  Math spec: SURVEY.md Appendix D.
 //
-// This is an HBM-bandwidth kernel (~1 flop/byte, q_len = 1): per (row n, pixel p) it streams the
-// pixel's contiguous K window [L,C] and V window [L,C] exactly once with 128-bit loads that bypass
-// L1, writes the new k/v into slot u_n, and never materialises K+pe / V+pe / the repeated mask.
-// Thread <-> one 8-channel (16 B) column chunk of one pixel; hd % 8 == 0 so a chunk never straddles
-// heads.  Per-head reduction of the q.k partials goes through shared memory; softmax and the P.V
-// accumulation are per-thread in fp32.
+// This is an HBM-bandwidth kernel (~1 flop/byte, q_len = 1).  The cache layout [N,2,hw,L,C] makes the K
+// (or V) windows of P consecutive pixels ONE contiguous P*L*C*2-byte span, so the kernel is a
+// persistent streaming pipeline over the HBM ring buffer:
+//   * grid = #SMs; each CTA walks tiles of P pixels (tile -> CTA round-robin)
+//   * one elected thread streams each tile's K span and V span into a ring of shared-memory slots with
+//     cp.async.bulk (TMA bulk copy, SASS UBLKCP) completing on mbarriers; up to S-1 spans (40 KB each at
+//     L=16) are in flight per SM while the current one is consumed
+//   * thread <-> one 8-channel (16 B) chunk of one pixel: conflict-free 128-bit shared loads, K+pe / V+pe
+//     formed in registers with the reference's fp16 rounding, q.k partials reduced per head through shared
+//     memory, fp32 softmax and P.V per thread, 128-bit stores of the output and of the appended k/v
+// Nothing is materialised in HBM (no K+pe / V+pe / repeated mask tensors), masked slots never enter the
+// math, and slot update_idx[n] is taken from the freshly projected k/v rather than from the ring.
 #include "ops.cuh"
 
 namespace l2d {
 
-constexpr int KV_CH = 16;  // slots handled per register chunk
+__device__ __forceinline__ uint32_t kv_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void kv_mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void kv_mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void kv_mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done = 0, spins = 0;
+  long long t0 = 0;
+  while (true) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (done) break;
+    if ((++spins & 1023u) == 0) {  // never hang the GPU on a protocol bug
+      const long long now = clock64();
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > 4000000000ll) __trap();
+    }
+  }
+}
+// global -> shared bulk copy (non-tensor TMA), completion counted in bytes on an mbarrier
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(dst), "l"(src), "r"(bytes), "r"(bar)
+               : "memory");
+}
 
+constexpr int KV_MAX_L = 32;
+constexpr int KV_MAX_SLOTS = 4;
 
-__global__ void __launch_bounds__(320, 1) kv_attn_kernel(const KvAttnParams p) {
-  extern __shared__ float smem[];
-  const int L = p.L, T = p.T, P = p.P;
-  float* s_part = smem;                          // [P][L][T]
-  float* s_sc = s_part + (size_t)P * L * T;      // [P][heads][L]
-  float* s_mask = s_sc + (size_t)P * p.heads * L;  // [L]
-  int* s_pi = reinterpret_cast<int*>(s_mask + L);  // [L]
+// dynamic shared memory: [ring: S * slot_bytes][s_part: P*L*T f32][s_sc: P*heads*L f32][s_mask: 32 f32][s_pi: 32 i32]
+//                        [bars: S u64, 8-byte aligned]
+__global__ void __launch_bounds__(320, 1) kv_attn_kernel(const KvAttnParams p, const int n_slots, const int slot_bytes,
+                                                         const int tiles_per_row) {
+  extern __shared__ __align__(128) uint8_t kv_smem[];
+  const int L = p.L, T = p.T, P = p.P, C = p.C;
+  uint8_t* ring = kv_smem;
+  float* s_part = reinterpret_cast<float*>(ring + (size_t)n_slots * slot_bytes);
+  float* s_sc = s_part + (size_t)P * L * T;
+  float* s_mask = s_sc + (size_t)P * p.heads * L;
+  int* s_pi = reinterpret_cast<int*>(s_mask + KV_MAX_L);
+  uint64_t* bars = reinterpret_cast<uint64_t*>((reinterpret_cast<uintptr_t>(s_pi + KV_MAX_L) + 7) & ~uintptr_t(7));
   __shared__ int s_u;
 
-  const int n = blockIdx.y;
   const int tid = threadIdx.x;
-  if (tid < L) {
-    s_pi[tid] = static_cast<int>(p.pe_idx[(size_t)n * L + tid]);
-    s_mask[tid] = __half2float(p.mask[(size_t)n * L + tid]);
+  const int total_tiles = tiles_per_row * p.n_rows;
+  const int my_tiles = (total_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;  // tiles b, b+G, ...
+  if (my_tiles <= 0) return;
+  const size_t win = (size_t)L * C;            // elements per pixel window
+  const size_t kv_plane = (size_t)p.hw * win;  // elements between the K and V planes of one row
+
+  // item q = 2*i + {0: K span, 1: V span} of this CTA's i-th tile; slot = q % S, phase parity = (q / S) & 1
+  auto issue = [&](int q) {
+    const int i = q >> 1;
+    if (i >= my_tiles) return;
+    const int tile = (int)blockIdx.x + i * (int)gridDim.x;
+    const int n = tile / tiles_per_row, p0 = (tile - n * tiles_per_row) * P;
+    const int np = min(P, p.hw - p0);
+    const __half* src = p.cache + ((size_t)n * 2 + (q & 1)) * kv_plane + (size_t)p0 * win;
+    const uint32_t bytes = (uint32_t)((size_t)np * win * sizeof(__half));
+    const int slot = q % n_slots;
+    const uint32_t bar = kv_smem_u32(&bars[slot]);
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic reads of the slot precede the async refill
+    kv_mbar_expect_tx(bar, bytes);
+    bulk_g2s(kv_smem_u32(ring + (size_t)slot * slot_bytes), src, bytes, bar);
+  };
+
+  if (tid == 0) {
+    for (int s = 0; s < n_slots; ++s) kv_mbar_init(kv_smem_u32(&bars[s]), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    for (int q = 0; q < n_slots; ++q) issue(q);
   }
-  if (tid == 0) s_u = static_cast<int>(p.update_idx[n]);
-  __syncthreads();
-  const int u = s_u;
 
   const int pl = tid / T;
   const int c = tid - pl * T;
-  const int pixel = blockIdx.x * P + pl;
-  const bool active = (pl < P) && (pixel < p.hw);
+  const bool lane_ok = pl < P;
+  int cur_n = -1;
 
-  uint4 vreg[KV_CH];
-  uint4 vnew = make_uint4(0, 0, 0, 0);
-  const __half* vbase = nullptr;
-  if (active) {
-    const size_t row = (size_t)n * p.hw + pixel;
-    const size_t win = (size_t)L * p.C;
-    __half* kbase = p.cache + (((size_t)n * 2) * p.hw + pixel) * win + (size_t)c * 8;
-    __half* vb = kbase + (size_t)p.hw * win;
-    vbase = vb;
-
-    const uint4 knew = ldg_cached(p.k_new + row * p.ld + (size_t)c * 8);
-    vnew = ldg_cached(p.v_new + row * p.ld + (size_t)c * 8);
-    uint4 qv = ldg_cached(p.q + row * p.ld + (size_t)c * 8);
-    qv = hadd8(qv, ldg_cached(p.q_pe + (size_t)s_pi[u] * p.pe_ld + (size_t)c * 8));   // q + Q_pe[pi[u]] -> fp16
-    float qf[8];
-    unpack8(qv, qf);
-
-    // ---- K window: q.k partials for this 8-channel chunk --------------------------------------
-    for (int j0 = 0; j0 < L; j0 += KV_CH) {
-      uint4 kreg[KV_CH];
-#pragma unroll
-      for (int jj = 0; jj < KV_CH; ++jj) {
-        const int j = j0 + jj;
-        if (j < L && j != u && s_mask[j] > -INFINITY) kreg[jj] = ldg_stream(kbase + (size_t)j * p.C);
+  for (int i = 0; i < my_tiles; ++i) {
+    const int tile = (int)blockIdx.x + i * (int)gridDim.x;
+    const int n = tile / tiles_per_row, p0 = (tile - n * tiles_per_row) * P;
+    if (n != cur_n) {  // per-row schedule: pe_idx[n,:], mask[n,:], update_idx[n]   (block-uniform branch)
+      __syncthreads();
+      if (tid < L) {
+        s_pi[tid] = static_cast<int>(p.pe_idx[(size_t)n * L + tid]);
+        s_mask[tid] = __half2float(p.mask[(size_t)n * L + tid]);
       }
-      if (j0 == 0) {
-        // V loads of the first chunk are issued now so their latency overlaps the reductions below
+      if (tid == 0) s_u = static_cast<int>(p.update_idx[n]);
+      cur_n = n;
+    }
+    __syncthreads();   // schedule visible; every thread has finished tile i-1 (its V slot may now be refilled)
+    const int u = s_u;
+    const int pixel = p0 + pl;
+    const bool active = lane_ok && pixel < p.hw;
+    const int qk = 2 * i, qv = 2 * i + 1;
+    if (tid == 0 && i > 0) issue(2 * (i - 1) + 1 + n_slots);   // refill the slot V_{i-1} occupied
+
+    uint4 knew = make_uint4(0, 0, 0, 0), vnew = make_uint4(0, 0, 0, 0);
+    float qf[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    size_t row = 0;
+    if (active) {
+      row = (size_t)n * p.hw + pixel;
+      knew = ldg_cached(p.k_new + row * p.ld + (size_t)c * 8);
+      vnew = ldg_cached(p.v_new + row * p.ld + (size_t)c * 8);
+      uint4 qv4 = ldg_cached(p.q + row * p.ld + (size_t)c * 8);
+      qv4 = hadd8(qv4, ldg_cached(p.q_pe + (size_t)s_pi[u] * p.pe_ld + (size_t)c * 8));   // q + Q_pe[pi[u]] -> fp16
+      unpack8(qv4, qf);
+      // PE-free append (stream_motion_module.py:117-119); the ring copy of slot u is never used
+      __half* kdst = p.cache + ((size_t)n * 2) * kv_plane + (size_t)pixel * win + (size_t)u * C + (size_t)c * 8;
+      *reinterpret_cast<uint4*>(kdst) = knew;
+      *reinterpret_cast<uint4*>(kdst + kv_plane) = vnew;
+    }
+
+    // ---- K span: q.k partials of this thread's 8-channel chunk -----------------------------------
+    kv_mbar_wait(kv_smem_u32(&bars[qk % n_slots]), (uint32_t)(qk / n_slots) & 1u);
+    if (active) {
+      const uint8_t* kb = ring + (size_t)(qk % n_slots) * slot_bytes + ((size_t)pl * win + (size_t)c * 8) * sizeof(__half);
+#pragma unroll 4
+      for (int j = 0; j < L; ++j) {
+        float part = 0.f;
+        if (s_mask[j] > -INFINITY) {
+          uint4 kk = (j == u) ? knew : *reinterpret_cast<const uint4*>(kb + (size_t)j * C * sizeof(__half));
+          kk = hadd8(kk, ldg_cached(p.k_pe + (size_t)s_pi[j] * p.pe_ld + (size_t)c * 8));   // K + K_pe -> fp16
+          float kf[8];
+          unpack8(kk, kf);
 #pragma unroll
-        for (int jj = 0; jj < KV_CH; ++jj) {
-          const int j = jj;
-          if (j < L && j != u && s_mask[j] > -INFINITY) vreg[jj] = ldg_stream(vb + (size_t)j * p.C);
+          for (int e = 0; e < 8; ++e) part = fmaf(qf[e], kf[e], part);
+        }
+        s_part[((size_t)pl * L + j) * T + c] = part;
+      }
+    }
+    __syncthreads();   // K slot consumed by everyone -> refill it; partials visible
+    if (tid == 0) issue(qk + n_slots);
+
+    // ---- per-head scores: sum the hd/8 chunk partials, scale, add mask -----------------------------
+    {
+      const int total = P * p.heads * L;
+      for (int idx = tid; idx < total; idx += blockDim.x) {
+        const int j = idx % L;
+        const int h = (idx / L) % p.heads;
+        const int pl2 = idx / (L * p.heads);
+        const float* src = s_part + ((size_t)pl2 * L + j) * T + h * p.hd8;
+        float s = 0.f;
+        for (int t = 0; t < p.hd8; ++t) s += src[t];
+        s_sc[idx] = s * p.scale + s_mask[j];
+      }
+    }
+    __syncthreads();
+
+    // ---- softmax over the window (fp32) + P.V -----------------------------------------------------
+    kv_mbar_wait(kv_smem_u32(&bars[qv % n_slots]), (uint32_t)(qv / n_slots) & 1u);
+    if (active) {
+      const int h = c / p.hd8;
+      const float* sc = s_sc + ((size_t)pl * p.heads + h) * L;
+      float mx = -INFINITY;
+      for (int j = 0; j < L; ++j) mx = fmaxf(mx, sc[j]);
+      float denom = 0.f;
+      for (int j = 0; j < L; ++j) denom += __expf(sc[j] - mx);
+      const float inv = 1.f / denom;
+      const uint8_t* vb = ring + (size_t)(qv % n_slots) * slot_bytes + ((size_t)pl * win + (size_t)c * 8) * sizeof(__half);
+      float o[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll 4
+      for (int j = 0; j < L; ++j) {
+        if (s_mask[j] > -INFINITY) {
+          const float pj = __expf(sc[j] - mx) * inv;
+          uint4 vv = (j == u) ? vnew : *reinterpret_cast<const uint4*>(vb + (size_t)j * C * sizeof(__half));
+          vv = hadd8(vv, ldg_cached(p.v_pe + (size_t)s_pi[j] * p.pe_ld + (size_t)c * 8));   // V + V_pe -> fp16
+          float vf[8];
+          unpack8(vv, vf);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) o[e] = fmaf(pj, vf[e], o[e]);
         }
       }
-#pragma unroll
-      for (int jj = 0; jj < KV_CH; ++jj) {
-        const int j = j0 + jj;
-        if (j < L) {
-          float part = 0.f;
-          if (s_mask[j] > -INFINITY) {
-            uint4 kk = (j == u) ? knew : kreg[jj];
-            kk = hadd8(kk, ldg_cached(p.k_pe + (size_t)s_pi[j] * p.pe_ld + (size_t)c * 8));  // K + K_pe -> fp16
-            float kf[8];
-            unpack8(kk, kf);
-#pragma unroll
-            for (int e = 0; e < 8; ++e) part = fmaf(qf[e], kf[e], part);
-          }
-          s_part[((size_t)pl * L + j) * T + c] = part;
-        }
-      }
-    }
-    // PE-free append (stream_motion_module.py:117-119)
-    *reinterpret_cast<uint4*>(kbase + (size_t)u * p.C) = knew;
-    *reinterpret_cast<uint4*>(vb + (size_t)u * p.C) = vnew;
-  }
-  __syncthreads();
-
-  // ---- per-head scores: sum the hd/8 chunk partials, scale, add mask ---------------------------
-  {
-    const int total = P * p.heads * L;
-    for (int idx = tid; idx < total; idx += blockDim.x) {
-      const int j = idx % L;
-      const int h = (idx / L) % p.heads;
-      const int pl2 = idx / (L * p.heads);
-      const float* src = s_part + ((size_t)pl2 * L + j) * T + h * p.hd8;
-      float s = 0.f;
-      for (int i = 0; i < p.hd8; ++i) s += src[i];
-      s_sc[idx] = s * p.scale + s_mask[j];
+      *reinterpret_cast<uint4*>(p.out + row * C + (size_t)c * 8) = pack8(o);
     }
   }
-  __syncthreads();
-  if (!active) return;
-
-  // ---- softmax over the window (fp32) + P.V ----------------------------------------------------
-  const int h = c / p.hd8;
-  const float* sc = s_sc + ((size_t)pl * p.heads + h) * L;
-  float mx = -INFINITY;
-  for (int j = 0; j < L; ++j) mx = fmaxf(mx, sc[j]);
-  float denom = 0.f;
-  for (int j = 0; j < L; ++j) denom += __expf(sc[j] - mx);
-  const float inv = 1.f / denom;
-
-  float o[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-  for (int j0 = 0; j0 < L; j0 += KV_CH) {
-    if (j0 > 0) {
-#pragma unroll
-      for (int jj = 0; jj < KV_CH; ++jj) {
-        const int j = j0 + jj;
-        if (j < L && j != u && s_mask[j] > -INFINITY) vreg[jj] = ldg_stream(vbase + (size_t)j * p.C);
-      }
-    }
-#pragma unroll
-    for (int jj = 0; jj < KV_CH; ++jj) {
-      const int j = j0 + jj;
-      if (j < L && s_mask[j] > -INFINITY) {
-        const float pj = __expf(sc[j] - mx) * inv;
-        uint4 vv = (j == u) ? vnew : vreg[jj];
-        vv = hadd8(vv, ldg_cached(p.v_pe + (size_t)s_pi[j] * p.pe_ld + (size_t)c * 8));  // V + V_pe -> fp16
-        float vf[8];
-        unpack8(vv, vf);
-#pragma unroll
-        for (int e = 0; e < 8; ++e) o[e] = fmaf(pj, vf[e], o[e]);
-      }
-    }
-  }
-  const size_t row = (size_t)n * p.hw + pixel;
-  *reinterpret_cast<uint4*>(p.out + row * p.C + (size_t)c * 8) = pack8(o);
 }
+
+static int g_num_sms = 0;
 
 int kv_attn_launch(const KvAttnParams& p0, cudaStream_t stream) {
   KvAttnParams p = p0;
   p.T = p.C / 8;
   p.hd8 = (p.C / p.heads) / 8;
-  int P = 320 / p.T;
+  if (p.T > 320) return fail(L2D_ERR_INVALID, "kv_attn: channels too large for one block (C <= 2560)");
+  int P = 160 / p.T;                 // 160 chunk-threads per CTA: 4/2/1 pixels at C = 320/640/1280
   if (P < 1) P = 1;
   if (P > p.hw) P = p.hw;
   p.P = P;
-  int threads = ((P * p.T + 31) / 32) * 32;
-  if (threads > 320) return fail(L2D_ERR_INVALID, "kv_attn: channels too large for one block (C <= 2560)");
+  const int threads = ((P * p.T + 31) / 32) * 32;
   p.scale = 1.0f / sqrtf((float)(p.C / p.heads));
-  size_t smem = ((size_t)P * p.L * p.T + (size_t)P * p.heads * p.L + 2 * p.L) * sizeof(float);
+  const int slot_bytes = (int)((size_t)P * p.L * p.C * sizeof(__half));
+  const size_t fixed = ((size_t)P * p.L * p.T + (size_t)P * p.heads * p.L + KV_MAX_L) * sizeof(float) +
+                       KV_MAX_L * sizeof(int) + KV_MAX_SLOTS * sizeof(uint64_t) + 128;
+  int n_slots = (int)((200 * 1024 - fixed) / (size_t)slot_bytes);
+  if (n_slots > KV_MAX_SLOTS) n_slots = KV_MAX_SLOTS;
+  if (n_slots < 2) return fail(L2D_ERR_INVALID, "kv_attn: window L*C too large for the shared-memory ring");
+  const size_t smem = (size_t)n_slots * slot_bytes + fixed;
   static size_t configured = 0;
-  if (smem > 48 * 1024 && smem > configured) {
+  if (smem > configured) {
     L2D_CUDA(cudaFuncSetAttribute(kv_attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = smem;
   }
-  dim3 grid(ceil_div(p.hw, P), p.n_rows);
-  kv_attn_kernel<<<grid, threads, smem, stream>>>(p);
+  if (g_num_sms == 0) {
+    int dev = 0;
+    L2D_CUDA(cudaGetDevice(&dev));
+    L2D_CUDA(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
+  }
+  const int tiles_per_row = ceil_div(p.hw, P);
+  const int total = tiles_per_row * p.n_rows;
+  const int grid = total < g_num_sms ? total : g_num_sms;
+  kv_attn_kernel<<<grid, threads, smem, stream>>>(p, n_slots, slot_bytes, tiles_per_row);
   L2D_LAUNCH_CHECK();
   return L2D_OK;
 }
@@ -181,10 +251,11 @@ extern "C" int l2d_kv_attn(const void* q, const void* k_new, const void* v_new, 
   using namespace l2d;
   L2D_CHECK_ARG(q && k_new && v_new && kv_cache && q_pe && k_pe && v_pe && mask && pe_idx && update_idx && out,
                 "null pointer");
-  L2D_CHECK_ARG(n_rows > 0 && hw > 0 && window > 0 && window <= 32, "need 0 < L <= 32");
+  L2D_CHECK_ARG(n_rows > 0 && hw > 0 && window > 0 && window <= KV_MAX_L, "need 0 < L <= 32");
   L2D_CHECK_ARG(heads > 0 && channels % heads == 0, "channels % heads != 0");
   L2D_CHECK_ARG(channels % 8 == 0 && (channels / heads) % 8 == 0, "need C % 8 == 0 and head_dim % 8 == 0");
   L2D_CHECK_ARG(qkv_ld % 8 == 0 && qkv_ld >= channels, "qkv_ld must be >= C and a multiple of 8");
+  L2D_CHECK_ARG((uintptr_t)kv_cache % 16 == 0, "kv_cache must be 16-byte aligned");
   KvAttnParams p{};
   p.q = (const __half*)q; p.k_new = (const __half*)k_new; p.v_new = (const __half*)v_new; p.ld = qkv_ld;
   p.cache = (__half*)kv_cache; p.q_pe = (const __half*)q_pe; p.k_pe = (const __half*)k_pe;

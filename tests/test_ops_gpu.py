@@ -248,3 +248,16 @@ def test_attention(b, heads, sq, skv, hd):
     ref16 = F.scaled_dot_product_attention(split(q, sq), split(k, skv), split(v, skv))
     merge = lambda t: t.transpose(1, 2).reshape(b * sq, c)
     referee(out, merge(ref32), merge(ref16), f"attention b{b} s{sq}x{skv} hd{hd}")
+
+
+def test_gemm_splitk_workspace_is_restored():
+    """Small-M / long-K problems run split-K (fp32 atomics into a workspace that the last CTA of each tile
+    zeroes again): back-to-back launches of different shapes must not see each other's partial sums."""
+    from live2diff_b200 import ops
+
+    for rep in range(3):
+        for (m, n, k) in [(128, 1280, 11520), (512, 1280, 5760), (300, 96, 2304), (128, 1280, 11520)]:
+            a, w = rnd(m, k, seed=30 + rep), rnd(n, k, seed=31, scale=1 / math.sqrt(k))
+            bias, res = rnd(n, seed=32), rnd(m, n, seed=33)
+            out = ops.gemm(a, w, bias=bias, residual=res)
+            strict(out, a.float() @ w.float().t() + bias.float() + res.float(), f"split-K {m}x{n}x{k} rep {rep}")
