@@ -730,7 +730,9 @@ extern "C" int l2d_unet_create(l2d_unet** out, const l2d_unet_config* cfg, const
   size_t max_mc = 0, max_cols = (size_t)u->lv[0].m * 64, max_map = 0;
   for (int i = 0; i < nlev; ++i) {
     const Level& l = u->lv[i];
-    max_mc = std::max(max_mc, (size_t)l.m * l.c);
+    // the widest channels-last tensor at this resolution: the block output [m, c] or the Upsample3D output arriving
+    // from the level below, which still carries that level's channel count
+    max_mc = std::max(max_mc, (size_t)l.m * std::max(l.c, cfg->block_out_channels[std::min(i + 1, nlev - 1)]));
     // widest conv input at this level: the up-block concat (<= 2x the widest neighbour), conservatively 2*max(c_i, c_{i+1}) + c
     const int cn = cfg->block_out_channels[std::min(i + 1, nlev - 1)];
     const int cp = cfg->block_out_channels[std::max(i - 1, 0)];

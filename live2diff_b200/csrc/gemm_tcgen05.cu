@@ -133,10 +133,11 @@ struct GemmEpilogue {
   const __half* residual;       // [M, ldr] or null
   int64_t ldr;
   int act;
-  // split-K (gridDim.z > 1): fp32 partial sums + per-tile arrival counters, both all-zero between launches
+  // split-K (gridDim.z > 1): every split stores its fp32 partial tile to ws[z][M_pad][ws_ld]; a second
+  // kernel (splitk_finish_kernel) sums the slices and applies the epilogue
   float* ws;
   int64_t ws_ld;
-  int* counters;
+  int64_t ws_slice;   // elements per split slice = M_pad * ws_ld
 };
 
 template <int BN>
@@ -194,7 +195,6 @@ gemm_f16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid
   const int kb_per = (total_kb + (int)gridDim.z - 1) / (int)gridDim.z;
   const int kb_begin = (int)blockIdx.z * kb_per;
   const int num_kb = max(0, min(total_kb, kb_begin + kb_per) - kb_begin);   // k-blocks of this split (may be 0)
-  __shared__ int s_is_last;
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmap_a);
@@ -283,50 +283,22 @@ gemm_f16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid
       epi_store16(epi, v, row, col0, M, N, row_ok);
     };
     if (gridDim.z > 1) {
-      // ---- split-K: add this split's partial tile into the fp32 workspace; the last-arriving CTA of the
-      //      tile applies the epilogue and restores the workspace/counter to zero ----
-      float* wrow = epi.ws + (size_t)row * epi.ws_ld;
-      if (num_kb > 0) {
+      // ---- split-K: store this split's fp32 partial tile (zeros when the split owns no k-blocks) ----
+      float* wrow = epi.ws + (size_t)blockIdx.z * epi.ws_slice + (size_t)row * epi.ws_ld + n0;
 #pragma unroll 1
-        for (int cc = 0; cc < BN / 16; ++cc) {
-          uint32_t r[16];
+      for (int cc = 0; cc < BN / 16; ++cc) {
+        uint32_t r[16];
+        if (num_kb > 0) {
           tmem_ld16(taddr + cc * 16, r);
           tmem_ld_wait();
-          if (row_ok) {
+        } else {
 #pragma unroll
-            for (int i = 0; i < 16; ++i)
-              if (n0 + cc * 16 + i < N) atomicAdd(wrow + n0 + cc * 16 + i, __uint_as_float(r[i]));
-          }
+          for (int i = 0; i < 16; ++i) r[i] = 0u;
         }
-      }
-      __threadfence();
-      asm volatile("bar.sync 1, 128;" ::: "memory");
-      if (threadIdx.x == 64) {
-        const int tile_id = blockIdx.y * gridDim.x + blockIdx.x;
-        s_is_last = (atomicAdd(epi.counters + tile_id, 1) == (int)gridDim.z - 1) ? 1 : 0;
-        if (s_is_last) epi.counters[tile_id] = 0;
-      }
-      asm volatile("bar.sync 1, 128;" ::: "memory");
-      if (s_is_last) {
-        __threadfence();
-#pragma unroll 1
-        for (int cc = 0; cc < BN / 16; ++cc) {
-          float v[16];
+        if (row_ok) {
 #pragma unroll
-          for (int i = 0; i < 16; ++i) v[i] = 0.f;
-          if (row_ok) {
-#pragma unroll
-            for (int q4 = 0; q4 < 4; ++q4) {
-              const int col = n0 + cc * 16 + q4 * 4;
-              if (col < N) {
-                float4* src = reinterpret_cast<float4*>(wrow + col);
-                const float4 t = __ldcg(src);
-                *src = make_float4(0.f, 0.f, 0.f, 0.f);
-                v[q4 * 4 + 0] = t.x; v[q4 * 4 + 1] = t.y; v[q4 * 4 + 2] = t.z; v[q4 * 4 + 3] = t.w;
-              }
-            }
-          }
-          finish16(v, cc);
+          for (int q4 = 0; q4 < 4; ++q4)
+            *reinterpret_cast<uint4*>(wrow + cc * 16 + q4 * 4) = make_uint4(r[q4 * 4], r[q4 * 4 + 1], r[q4 * 4 + 2], r[q4 * 4 + 3]);
         }
       }
     } else if (epi.act != L2D_ACT_GEGLU) {
@@ -380,6 +352,45 @@ gemm_f16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
+// Second pass of a split-K GEMM: out[m, n0..n0+7] = epilogue(sum_z ws[z][m][n0..]) -- one thread per 8 columns
+__global__ void __launch_bounds__(256) splitk_finish_kernel(const GemmEpilogue epi, int M, int N, int splits) {
+  const int n8 = N >> 3;
+  const size_t total = (size_t)M * n8;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int row = (int)(i / n8), col = (int)(i % n8) * 8;
+    float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    const float* src = epi.ws + (size_t)row * epi.ws_ld + col;
+    for (int z = 0; z < splits; ++z) {
+      const float4 a = __ldcg(reinterpret_cast<const float4*>(src + (size_t)z * epi.ws_slice));
+      const float4 b = __ldcg(reinterpret_cast<const float4*>(src + (size_t)z * epi.ws_slice + 4));
+      v[0] += a.x; v[1] += a.y; v[2] += a.z; v[3] += a.w; v[4] += b.x; v[5] += b.y; v[6] += b.z; v[7] += b.w;
+    }
+    if (epi.bias) {
+      float b[8];
+      unpack8(ldg_cached(epi.bias + col), b);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) v[e] += b[e];
+    }
+    if (epi.rowgroup_bias) {
+      float b[8];
+      unpack8(ldg_cached(epi.rowgroup_bias + (size_t)(row / epi.rows_per_group) * epi.rg_ld + col), b);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) v[e] += b[e];
+    }
+    if (epi.act == L2D_ACT_SILU) {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) v[e] = silu_f(v[e]);
+    }
+    if (epi.residual) {
+      float r[8];
+      unpack8(*reinterpret_cast<const uint4*>(epi.residual + (size_t)row * epi.ldr + col), r);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) v[e] += r[e];
+    }
+    *reinterpret_cast<uint4*>(epi.out + (size_t)row * epi.ldo + col) = pack8(v);
   }
 }
 
@@ -453,8 +464,7 @@ static int get_tmap(const void* ptr, int64_t rows, int64_t cols, int64_t ld, int
 // tcgen05 issue time (BN/2 cycles).  So bigger N tiles are cheaper per flop, and small-M problems must be spread
 // over the SMs by splitting K.
 constexpr int kNumSms = 148;
-constexpr int64_t kWsElems = 4 << 20;   // fp32 split-K workspace (16 MB)
-constexpr int kMaxTiles = 4096;
+constexpr int64_t kWsElems = 12 << 20;  // fp32 split-K workspace (48 MB)
 
 struct GemmPlan {
   int bn, splits;
@@ -470,15 +480,16 @@ static GemmPlan gemm_plan(int m, int n, int k, bool allow_split, int force_bn) {
     const int tiles_n = ceil_div(n, bn), tiles = tiles_m * tiles_n;
     const double kb_cyc = (128.0 + bn) * 128.0 / 42.0;
     int max_s = 1;
-    if (allow_split && (int64_t)tiles_m * BM * tiles_n * bn <= kWsElems && tiles <= kMaxTiles)
-      max_s = std::max(1, std::min(32, num_kb / 4));
+    if (allow_split) max_s = std::max(1, std::min(32, num_kb / 4));
     for (int sp = 1; sp <= max_s; ++sp) {
       const int kb_per = ceil_div(num_kb, sp);
       if (sp > 1 && kb_per * (sp - 1) >= num_kb) continue;        // an empty last split: pointless
+      if (sp > 1 && (int64_t)sp * tiles_m * BM * tiles_n * bn > kWsElems) continue;
       const int waves = ceil_div(tiles * sp, kNumSms);
       double cta = kb_per * kb_cyc + 3000.0;
-      if (sp > 1) cta += 16.0 * bn + 1500.0;                      // fp32 atomics of the partial tile + final pass
-      const double cost = waves * cta;
+      if (sp > 1) cta += 13.0 * bn;                               // fp32 store of the partial tile
+      double cost = waves * cta;
+      if (sp > 1) cost += 6000.0 + (double)sp * m * n * 4.0 / (kNumSms * 40.0);   // finish kernel: launch + slice reads
       if (cost < best_cost * 0.97 || (cost < best_cost && sp < best.splits)) {
         best_cost = cost;
         best = {bn, sp};
@@ -491,17 +502,10 @@ static GemmPlan gemm_plan(int m, int n, int k, bool allow_split, int force_bn) {
 int gemm_pick_tile_n(int m, int n, int k) { return gemm_plan(m, n, k, false, 0).bn; }
 
 static float* g_ws = nullptr;
-static int* g_counters = nullptr;
 
 static int ensure_splitk_workspace() {
   if (g_ws) return L2D_OK;
-  cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
   L2D_CUDA(cudaMalloc(&g_ws, kWsElems * sizeof(float)));
-  L2D_CUDA(cudaMalloc(&g_counters, kMaxTiles * sizeof(int)));
-  L2D_CUDA(cudaMemset(g_ws, 0, kWsElems * sizeof(float)));
-  L2D_CUDA(cudaMemset(g_counters, 0, kMaxTiles * sizeof(int)));
-  L2D_CUDA(cudaDeviceSynchronize());
-  (void)cs;
   return L2D_OK;
 }
 
@@ -532,21 +536,27 @@ int gemm_launch(const __half* a, int64_t lda, const __half* w, int64_t ldw, __ha
   rc = get_tmap(w, n, k, ldw, bn, &tb);
   if (rc != L2D_OK) return rc;
   GemmEpilogue e{out, ldo, bias, rowgroup_bias, rg_ld, rows_per_group > 0 ? rows_per_group : 1, residual, ldr, act,
-                 nullptr, 0, nullptr};
+                 nullptr, 0, 0};
   if (plan.splits > 1) {
     rc = ensure_splitk_workspace();
     if (rc != L2D_OK) return rc;
     e.ws = g_ws;
     e.ws_ld = (int64_t)ceil_div(n, bn) * bn;
-    e.counters = g_counters;
+    e.ws_slice = (int64_t)ceil_div(m, BM) * BM * e.ws_ld;
   }
   switch (bn) {
-    case 64: return launch_gemm<64, 6>(ta, tb, e, m, n, k, plan.splits, st);
-    case 128: return launch_gemm<128, 6>(ta, tb, e, m, n, k, plan.splits, st);
-    case 160: return launch_gemm<160, 5>(ta, tb, e, m, n, k, plan.splits, st);
-    case 256: return launch_gemm<256, 4>(ta, tb, e, m, n, k, plan.splits, st);
+    case 64: rc = launch_gemm<64, 6>(ta, tb, e, m, n, k, plan.splits, st); break;
+    case 128: rc = launch_gemm<128, 6>(ta, tb, e, m, n, k, plan.splits, st); break;
+    case 160: rc = launch_gemm<160, 5>(ta, tb, e, m, n, k, plan.splits, st); break;
+    case 256: rc = launch_gemm<256, 4>(ta, tb, e, m, n, k, plan.splits, st); break;
     default: return fail(L2D_ERR_INVALID, "gemm: unsupported tile_n");
   }
+  if (rc != L2D_OK || plan.splits == 1) return rc;
+  const size_t work = (size_t)m * (n / 8);
+  const int blocks = (int)std::min<size_t>((work + 255) / 256, (size_t)kNumSms * 8);
+  splitk_finish_kernel<<<blocks, 256, 0, st>>>(e, m, n, plan.splits);
+  L2D_LAUNCH_CHECK();
+  return L2D_OK;
 }
 
 }  // namespace l2d

@@ -58,8 +58,13 @@ constexpr int KV_MAX_SLOTS = 4;
 
 // dynamic shared memory: [ring: S * slot_bytes][s_part: P*L*T f32][s_sc: P*heads*L f32][s_mask: 32 f32][s_pi: 32 i32]
 //                        [bars: S u64, 8-byte aligned]
-__global__ void __launch_bounds__(320, 1) kv_attn_kernel(const KvAttnParams p, const int n_slots, const int slot_bytes,
-                                                         const int tiles_per_row) {
+// PE_REGS (L <= 16, <= 192 threads): the thread's K_pe / V_pe chunks of all L slots stay in registers for the whole
+// row n (every pixel of a row shares pe_idx[n]), so the slot loops are LDS.128 + 4 HADD2 + 8 cvt + 8 FFMA per slot
+// with no global loads and no index arithmetic.
+template <bool PE_REGS>
+__global__ void __launch_bounds__(PE_REGS ? 192 : 320, 1)
+kv_attn_kernel(const KvAttnParams p, const int n_slots, const int slot_bytes, const int tiles_per_row) {
+  constexpr int LR = 16;   // slots covered by the unrolled register path
   extern __shared__ __align__(128) uint8_t kv_smem[];
   const int L = p.L, T = p.T, P = p.P, C = p.C;
   uint8_t* ring = kv_smem;
@@ -88,7 +93,7 @@ __global__ void __launch_bounds__(320, 1) kv_attn_kernel(const KvAttnParams p, c
     const uint32_t bytes = (uint32_t)((size_t)np * win * sizeof(__half));
     const int slot = q % n_slots;
     const uint32_t bar = kv_smem_u32(&bars[slot]);
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic reads of the slot precede the async refill
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic accesses to the slot precede the async refill
     kv_mbar_expect_tx(bar, bytes);
     bulk_g2s(kv_smem_u32(ring + (size_t)slot * slot_bytes), src, bytes, bar);
   };
@@ -102,12 +107,16 @@ __global__ void __launch_bounds__(320, 1) kv_attn_kernel(const KvAttnParams p, c
   const int pl = tid / T;
   const int c = tid - pl * T;
   const bool lane_ok = pl < P;
+  const size_t row_bytes = (size_t)C * sizeof(__half);
   int cur_n = -1;
+  uint32_t vbits = 0;               // bit j set <=> slot j is visible to row n (mask[n,j] > -inf)
+  uint4 kpe[LR], vpe[LR];           // PE_REGS only
 
   for (int i = 0; i < my_tiles; ++i) {
     const int tile = (int)blockIdx.x + i * (int)gridDim.x;
     const int n = tile / tiles_per_row, p0 = (tile - n * tiles_per_row) * P;
-    if (n != cur_n) {  // per-row schedule: pe_idx[n,:], mask[n,:], update_idx[n]   (block-uniform branch)
+    const bool new_row = n != cur_n;   // block-uniform
+    if (new_row) {  // per-row schedule: pe_idx[n,:], mask[n,:], update_idx[n]
       __syncthreads();
       if (tid < L) {
         s_pi[tid] = static_cast<int>(p.pe_idx[(size_t)n * L + tid]);
@@ -118,6 +127,19 @@ __global__ void __launch_bounds__(320, 1) kv_attn_kernel(const KvAttnParams p, c
     }
     __syncthreads();   // schedule visible; every thread has finished tile i-1 (its V slot may now be refilled)
     const int u = s_u;
+    if (new_row) {
+      vbits = 0;
+      for (int j = 0; j < L; ++j) vbits |= (s_mask[j] > -INFINITY ? 1u : 0u) << j;
+      if (PE_REGS && lane_ok) {
+#pragma unroll
+        for (int j = 0; j < LR; ++j) {
+          if (j < L) {
+            kpe[j] = ldg_cached(p.k_pe + (size_t)s_pi[j] * p.pe_ld + (size_t)c * 8);
+            vpe[j] = ldg_cached(p.v_pe + (size_t)s_pi[j] * p.pe_ld + (size_t)c * 8);
+          }
+        }
+      }
+    }
     const int pixel = p0 + pl;
     const bool active = lane_ok && pixel < p.hw;
     const int qk = 2 * i, qv = 2 * i + 1;
@@ -133,7 +155,7 @@ __global__ void __launch_bounds__(320, 1) kv_attn_kernel(const KvAttnParams p, c
       uint4 qv4 = ldg_cached(p.q + row * p.ld + (size_t)c * 8);
       qv4 = hadd8(qv4, ldg_cached(p.q_pe + (size_t)s_pi[u] * p.pe_ld + (size_t)c * 8));   // q + Q_pe[pi[u]] -> fp16
       unpack8(qv4, qf);
-      // PE-free append (stream_motion_module.py:117-119); the ring copy of slot u is never used
+      // PE-free append to HBM (stream_motion_module.py:117-119)
       __half* kdst = p.cache + ((size_t)n * 2) * kv_plane + (size_t)pixel * win + (size_t)u * C + (size_t)c * 8;
       *reinterpret_cast<uint4*>(kdst) = knew;
       *reinterpret_cast<uint4*>(kdst + kv_plane) = vnew;
@@ -142,21 +164,42 @@ __global__ void __launch_bounds__(320, 1) kv_attn_kernel(const KvAttnParams p, c
     // ---- K span: q.k partials of this thread's 8-channel chunk -----------------------------------
     kv_mbar_wait(kv_smem_u32(&bars[qk % n_slots]), (uint32_t)(qk / n_slots) & 1u);
     if (active) {
-      const uint8_t* kb = ring + (size_t)(qk % n_slots) * slot_bytes + ((size_t)pl * win + (size_t)c * 8) * sizeof(__half);
-#pragma unroll 4
-      for (int j = 0; j < L; ++j) {
-        float part = 0.f;
-        if (s_mask[j] > -INFINITY) {
-          uint4 kk = (j == u) ? knew : *reinterpret_cast<const uint4*>(kb + (size_t)j * C * sizeof(__half));
-          kk = hadd8(kk, ldg_cached(p.k_pe + (size_t)s_pi[j] * p.pe_ld + (size_t)c * 8));   // K + K_pe -> fp16
-          float kf[8];
-          unpack8(kk, kf);
+      uint8_t* kb = ring + (size_t)(qk % n_slots) * slot_bytes + ((size_t)pl * win + (size_t)c * 8) * sizeof(__half);
+      // slot u of the window is the freshly projected k: patch this thread's own chunk of the landed span
+      *reinterpret_cast<uint4*>(kb + (size_t)u * row_bytes) = knew;
+      float* part_dst = s_part + (size_t)pl * L * T + c;
+      if (PE_REGS) {
 #pragma unroll
-          for (int e = 0; e < 8; ++e) part = fmaf(qf[e], kf[e], part);
+        for (int j = 0; j < LR; ++j) {
+          if (j < L) {
+            float part = 0.f;
+            if ((vbits >> j) & 1u) {
+              const uint4 kk = hadd8(*reinterpret_cast<const uint4*>(kb + (size_t)j * row_bytes), kpe[j]);   // K + K_pe -> fp16
+              float kf[8];
+              unpack8(kk, kf);
+#pragma unroll
+              for (int e = 0; e < 8; ++e) part = fmaf(qf[e], kf[e], part);
+            }
+            part_dst[(size_t)j * T] = part;
+          }
         }
-        s_part[((size_t)pl * L + j) * T + c] = part;
+      } else {
+#pragma unroll 4
+        for (int j = 0; j < L; ++j) {
+          float part = 0.f;
+          if ((vbits >> j) & 1u) {
+            const uint4 kk = hadd8(*reinterpret_cast<const uint4*>(kb + (size_t)j * row_bytes),
+                                   ldg_cached(p.k_pe + (size_t)s_pi[j] * p.pe_ld + (size_t)c * 8));
+            float kf[8];
+            unpack8(kk, kf);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) part = fmaf(qf[e], kf[e], part);
+          }
+          part_dst[(size_t)j * T] = part;
+        }
       }
     }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // my patch of slot u precedes the async refill
     __syncthreads();   // K slot consumed by everyone -> refill it; partials visible
     if (tid == 0) issue(qk + n_slots);
 
@@ -180,27 +223,51 @@ __global__ void __launch_bounds__(320, 1) kv_attn_kernel(const KvAttnParams p, c
     if (active) {
       const int h = c / p.hd8;
       const float* sc = s_sc + ((size_t)pl * p.heads + h) * L;
+      uint8_t* vb = ring + (size_t)(qv % n_slots) * slot_bytes + ((size_t)pl * win + (size_t)c * 8) * sizeof(__half);
+      *reinterpret_cast<uint4*>(vb + (size_t)u * row_bytes) = vnew;
+      float o[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
       float mx = -INFINITY;
       for (int j = 0; j < L; ++j) mx = fmaxf(mx, sc[j]);
-      float denom = 0.f;
-      for (int j = 0; j < L; ++j) denom += __expf(sc[j] - mx);
-      const float inv = 1.f / denom;
-      const uint8_t* vb = ring + (size_t)(qv % n_slots) * slot_bytes + ((size_t)pl * win + (size_t)c * 8) * sizeof(__half);
-      float o[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-#pragma unroll 4
-      for (int j = 0; j < L; ++j) {
-        if (s_mask[j] > -INFINITY) {
-          const float pj = __expf(sc[j] - mx) * inv;
-          uint4 vv = (j == u) ? vnew : *reinterpret_cast<const uint4*>(vb + (size_t)j * C * sizeof(__half));
-          vv = hadd8(vv, ldg_cached(p.v_pe + (size_t)s_pi[j] * p.pe_ld + (size_t)c * 8));   // V + V_pe -> fp16
-          float vf[8];
-          unpack8(vv, vf);
+      if (PE_REGS) {
+        float ex[LR];
+        float denom = 0.f;
 #pragma unroll
-          for (int e = 0; e < 8; ++e) o[e] = fmaf(pj, vf[e], o[e]);
+        for (int j = 0; j < LR; ++j) {
+          ex[j] = (j < L && ((vbits >> j) & 1u)) ? __expf(sc[j] - mx) : 0.f;
+          denom += ex[j];
+        }
+        const float inv = 1.f / denom;
+#pragma unroll
+        for (int j = 0; j < LR; ++j) {
+          if (j < L && ((vbits >> j) & 1u)) {
+            const float pj = ex[j] * inv;
+            const uint4 vv = hadd8(*reinterpret_cast<const uint4*>(vb + (size_t)j * row_bytes), vpe[j]);   // V + V_pe -> fp16
+            float vf[8];
+            unpack8(vv, vf);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) o[e] = fmaf(pj, vf[e], o[e]);
+          }
+        }
+      } else {
+        float denom = 0.f;
+        for (int j = 0; j < L; ++j) denom += __expf(sc[j] - mx);
+        const float inv = 1.f / denom;
+#pragma unroll 4
+        for (int j = 0; j < L; ++j) {
+          if ((vbits >> j) & 1u) {
+            const float pj = __expf(sc[j] - mx) * inv;
+            const uint4 vv = hadd8(*reinterpret_cast<const uint4*>(vb + (size_t)j * row_bytes),
+                                   ldg_cached(p.v_pe + (size_t)s_pi[j] * p.pe_ld + (size_t)c * 8));
+            float vf[8];
+            unpack8(vv, vf);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) o[e] = fmaf(pj, vf[e], o[e]);
+          }
         }
       }
       *reinterpret_cast<uint4*>(p.out + row * C + (size_t)c * 8) = pack8(o);
     }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // (V slot is refilled after the next tile's barrier)
   }
 }
 
@@ -224,10 +291,14 @@ int kv_attn_launch(const KvAttnParams& p0, cudaStream_t stream) {
   if (n_slots > KV_MAX_SLOTS) n_slots = KV_MAX_SLOTS;
   if (n_slots < 2) return fail(L2D_ERR_INVALID, "kv_attn: window L*C too large for the shared-memory ring");
   const size_t smem = (size_t)n_slots * slot_bytes + fixed;
-  static size_t configured = 0;
-  if (smem > configured) {
-    L2D_CUDA(cudaFuncSetAttribute(kv_attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = smem;
+  const bool pe_regs = p.L <= 16 && threads <= 192;
+  static size_t configured[2] = {0, 0};
+  if (smem > configured[pe_regs]) {
+    if (pe_regs)
+      L2D_CUDA(cudaFuncSetAttribute(kv_attn_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    else
+      L2D_CUDA(cudaFuncSetAttribute(kv_attn_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured[pe_regs] = smem;
   }
   if (g_num_sms == 0) {
     int dev = 0;
@@ -237,7 +308,10 @@ int kv_attn_launch(const KvAttnParams& p0, cudaStream_t stream) {
   const int tiles_per_row = ceil_div(p.hw, P);
   const int total = tiles_per_row * p.n_rows;
   const int grid = total < g_num_sms ? total : g_num_sms;
-  kv_attn_kernel<<<grid, threads, smem, stream>>>(p, n_slots, slot_bytes, tiles_per_row);
+  if (pe_regs)
+    kv_attn_kernel<true><<<grid, threads, smem, stream>>>(p, n_slots, slot_bytes, tiles_per_row);
+  else
+    kv_attn_kernel<false><<<grid, threads, smem, stream>>>(p, n_slots, slot_bytes, tiles_per_row);
   L2D_LAUNCH_CHECK();
   return L2D_OK;
 }
