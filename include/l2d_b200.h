@@ -97,6 +97,12 @@ int l2d_nhwc_to_nchw(const void* x, const void* residual_nchw, void* y, int n_im
 int l2d_gemm(const void* a, int64_t lda, const void* w, void* out, int64_t ldo, int m, int n, int k,
              const void* bias, const void* rowgroup_bias, int rows_per_group, const void* residual,
              int64_t ldr, int act, void* stream);
+/* Implicit-GEMM 3x3 convolution, pad 1, stride 1 (no im2col matrix): x [N,h,w,Cin] channels-last contiguous,
+ * weight [Cout, 9*Cin] with columns ordered (tap = ky*3+kx, cin), out rows = pixels (n*h*w + y*w + x), `ldo` elements
+ * per row.  Epilogue as l2d_gemm (rowgroup_bias [N, Cout] is per image).  Needs Cin % 64 == 0 and h, w whose
+ * power-of-two divisors tile 128 pixels (true for every stride-1 conv of the UNet at 512x512 / 768x512). */
+int l2d_conv3x3(const void* x, int n_img, int h, int w, int cin, const void* weight, void* out, int64_t ldo, int cout,
+                const void* bias, const void* rowgroup_bias, const void* residual, int64_t ldr, int act, void* stream);
 /* Row permutation applied to a GEGLU projection weight [2F,K] (+ bias [2F]) so that every GEMM N-tile
  * holds matching value/gate columns.  `tile_n` = the N tile l2d_gemm will use for n=2F (l2d_gemm_tile_n). */
 int l2d_gemm_tile_n(int m, int n, int k);

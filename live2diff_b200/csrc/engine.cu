@@ -208,6 +208,12 @@ struct Core {
     Scope sc(*this, FAM_GEMM);
     return gemm_launch(a, lda, w, ldw, out, ldo, m, n, k, bias, rg, rg_ld, rpg, residual, ldr, act, force_bn, st);
   }
+  // conv3x3 (pad 1, stride 1) over a channels-last tensor as an implicit GEMM (no im2col matrix)
+  int conv3x3(const __half* x, int n_img, int h, int w, int cin, const __half* wt, __half* out, int64_t ldo, int cout,
+              const __half* bias, const __half* rg, int64_t rg_ld, int rpg, const __half* residual, int64_t ldr, int act) {
+    Scope sc(*this, FAM_GEMM);
+    return conv3x3_launch(x, n_img, h, w, cin, wt, out, ldo, cout, bias, rg, rg_ld, rpg, residual, ldr, act, st);
+  }
   int kv(const KvAttnParams& p) {
     Scope sc(*this, FAM_KV);
     return kv_attn_launch(p, st);
@@ -520,9 +526,18 @@ int resnet_forward(l2d_unet* u, const ResnetP& r, const __half* x1, int c1, cons
   Core& k = u->core;
   const float eps = u->cfg.norm_eps;
   const int n = k.n_rows, m = lv.m, hw = lv.h * lv.w;
-  RC(k.gn(x1, c1, x2, c2, r.norm1, k.s.cols, n, lv.h, lv.w, eps, 1, 1));
-  RC(conv_gemm(k, r.conv1, k.s.h1, r.cout, m, u->temb_proj + r.temb_off, u->temb_total, hw, nullptr, 0, L2D_ACT_NONE));
-  RC(k.gn(k.s.h1, r.cout, nullptr, 0, r.norm2, k.s.cols, n, lv.h, lv.w, eps, 1, 1));
+  // GroupNorm+SiLU (channel concat fused) -> conv3x3.  When the level tiles (always at 512x512 / 768x512) the
+  // normalised tensor is written once, channels-last, and the conv is an implicit GEMM reading it through 4-D TMA
+  // boxes; otherwise the norm kernel writes the im2col matrix and a plain GEMM follows.
+  const bool implicit1 = conv3x3_implicit_supported(n, lv.h, lv.w, c1 + c2);
+  const bool implicit2 = conv3x3_implicit_supported(n, lv.h, lv.w, r.cout);
+  RC(k.gn(x1, c1, x2, c2, r.norm1, k.s.cols, n, lv.h, lv.w, eps, 1, implicit1 ? 0 : 1));
+  if (implicit1)
+    RC(k.conv3x3(k.s.cols, n, lv.h, lv.w, c1 + c2, r.conv1.w, k.s.h1, r.cout, r.conv1.n_pad, r.conv1.b,
+                 u->temb_proj + r.temb_off, u->temb_total, hw, nullptr, 0, L2D_ACT_NONE));
+  else
+    RC(conv_gemm(k, r.conv1, k.s.h1, r.cout, m, u->temb_proj + r.temb_off, u->temb_total, hw, nullptr, 0, L2D_ACT_NONE));
+  RC(k.gn(k.s.h1, r.cout, nullptr, 0, r.norm2, k.s.cols, n, lv.h, lv.w, eps, 1, implicit2 ? 0 : 1));
   const __half* res = x1;
   int64_t ldr = c1;
   if (r.shortcut.n) {
@@ -537,7 +552,11 @@ int resnet_forward(l2d_unet* u, const ResnetP& r, const __half* x1, int c1, cons
   } else if (c2 > 0) {
     return fail(L2D_ERR_INVALID, "resnet without shortcut cannot take a concatenated input");
   }
-  RC(conv_gemm(k, r.conv2, out, r.cout, m, nullptr, 0, 1, res, ldr, L2D_ACT_NONE));
+  if (implicit2)
+    RC(k.conv3x3(k.s.cols, n, lv.h, lv.w, r.cout, r.conv2.w, out, r.cout, r.conv2.n_pad, r.conv2.b, nullptr, 0, 1, res, ldr,
+                 L2D_ACT_NONE));
+  else
+    RC(conv_gemm(k, r.conv2, out, r.cout, m, nullptr, 0, 1, res, ldr, L2D_ACT_NONE));
   return L2D_OK;
 }
 
@@ -688,8 +707,14 @@ int run_step(l2d_unet* u, const l2d_unet_step_args* a) {
   if (skip_i != 0 || kv_i != u->n_kv) return fail(L2D_ERR_INVALID, "internal: topology bookkeeping mismatch");
 
   // ---- post-process (:620-622) ----
-  RC(k.gn(x, l0.c, nullptr, 0, u->norm_out, s.cols, n, l0.h, l0.w, cfg.norm_eps, 1, 1));
-  RC(conv_gemm(k, u->conv_out, u->out8, u->conv_out.n_pad, l0.m, nullptr, 0, 1, nullptr, 0, L2D_ACT_NONE));
+  if (conv3x3_implicit_supported(n, l0.h, l0.w, l0.c)) {
+    RC(k.gn(x, l0.c, nullptr, 0, u->norm_out, s.cols, n, l0.h, l0.w, cfg.norm_eps, 1, 0));
+    RC(k.conv3x3(s.cols, n, l0.h, l0.w, l0.c, u->conv_out.w, u->out8, u->conv_out.n_pad, u->conv_out.n_pad,
+                 u->conv_out.b, nullptr, 0, 1, nullptr, 0, L2D_ACT_NONE));
+  } else {
+    RC(k.gn(x, l0.c, nullptr, 0, u->norm_out, s.cols, n, l0.h, l0.w, cfg.norm_eps, 1, 1));
+    RC(conv_gemm(k, u->conv_out, u->out8, u->conv_out.n_pad, l0.m, nullptr, 0, 1, nullptr, 0, L2D_ACT_NONE));
+  }
   const int total = n * l0.h * l0.w * u->conv_out.cout;
   nhwc_to_nchw4_kernel<<<ceil_div(total, 256), 256, 0, st>>>(u->out8, static_cast<__half*>(a->out_sample), n, l0.h * l0.w,
                                                             u->conv_out.n_pad, u->conv_out.cout);

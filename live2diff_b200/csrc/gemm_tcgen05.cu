@@ -71,6 +71,13 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
       ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1)
       : "memory");
 }
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2,
+                                            int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
 }
@@ -123,6 +130,19 @@ __host__ __device__ constexpr uint32_t make_idesc(int n) {
 }
 
 // ---------------------------------------------------------------------------------------------
+// Implicit-GEMM 3x3 convolution (pad 1, stride 1) over a channels-last activation [N,H,W,Cin]: the A tile of
+// output pixels (bn images x bh rows x bw columns = 128) for tap (dy,dx) and channel block c0 is ONE 4-D TMA box
+// at (c0, w0+dx-1, h0+dy-1, n0); out-of-range coordinates are zero-filled by the TMA unit = the conv's padding.
+// No im2col matrix exists.  k-block kb <-> (tap = kb / cin_blocks, c0 = 64 * (kb % cin_blocks)), matching the
+// [Cout, 9*Cin] (tap, cin) weight repack.
+struct ConvGeom {
+  int enabled;
+  int cin_blocks;        // Cin / 64
+  int H, W, N;
+  int bw, bh, bn;        // tile extents, bw * bh * bn == 128
+  int tiles_w, tiles_h;  // tiles per image row / column
+};
+
 struct GemmEpilogue {
   __half* out;
   int64_t ldo;
@@ -147,9 +167,11 @@ struct GemmSmem {
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
 };
 
+// v: activated accumulator values for output columns col0 .. col0+15 of `row`; res0/res1: the residual's 2 x 8
+// columns, already in registers (prefetched while the main loop ran) or loaded here when `res_loaded` is false
 __device__ __forceinline__ void epi_store16(const GemmEpilogue& e, float (&v)[16], int row, int col0, int M, int n_out,
-                                            bool row_ok) {
-  // v: activated accumulator values for output columns col0 .. col0+15 of `row`
+                                            bool row_ok, bool res_loaded = false, uint4 res0 = make_uint4(0, 0, 0, 0),
+                                            uint4 res1 = make_uint4(0, 0, 0, 0)) {
   if (!row_ok) return;
 #pragma unroll
   for (int hlf = 0; hlf < 2; ++hlf) {
@@ -161,7 +183,9 @@ __device__ __forceinline__ void epi_store16(const GemmEpilogue& e, float (&v)[16
       if (e.residual) {
         float r[8];
         // plain (coherent) load: the residual may alias `out` (in-place  h += f(h))
-        unpack8(*reinterpret_cast<const uint4*>(e.residual + (size_t)row * e.ldr + col), r);
+        const uint4 rr = res_loaded ? (hlf ? res1 : res0)
+                                    : *reinterpret_cast<const uint4*>(e.residual + (size_t)row * e.ldr + col);
+        unpack8(rr, r);
 #pragma unroll
         for (int i = 0; i < 8; ++i) o[i] += r[i];
       }
@@ -173,7 +197,7 @@ __device__ __forceinline__ void epi_store16(const GemmEpilogue& e, float (&v)[16
 template <int BN, int STAGES>
 __global__ void __launch_bounds__(192, 1)
 gemm_f16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
-                        const GemmEpilogue epi, int M, int N, int K) {
+                        const GemmEpilogue epi, const ConvGeom cg, int M, int N, int K) {
   using S = GemmSmem<BN>;
   constexpr uint32_t TMEM_COLS = BN <= 32 ? 32 : BN <= 64 ? 64 : BN <= 128 ? 128 : 256;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -191,6 +215,14 @@ gemm_f16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid
   const int lane = threadIdx.x & 31;
   const int n0 = blockIdx.x * BN;
   const int m0 = blockIdx.y * BM;
+  // conv mode: this CTA's output tile = images [cn0, cn0+bn) x rows [ch0, ch0+bh) x columns [cw0, cw0+bw)
+  int cn0 = 0, ch0 = 0, cw0 = 0;
+  if (cg.enabled) {
+    const int t = blockIdx.y;
+    cw0 = (t % cg.tiles_w) * cg.bw;
+    ch0 = ((t / cg.tiles_w) % cg.tiles_h) * cg.bh;
+    cn0 = (t / (cg.tiles_w * cg.tiles_h)) * cg.bn;
+  }
   const int total_kb = (K + BK - 1) / BK;
   const int kb_per = (total_kb + (int)gridDim.z - 1) / (int)gridDim.z;
   const int kb_begin = (int)blockIdx.z * kb_per;
@@ -221,7 +253,12 @@ gemm_f16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid
         mbar_wait(smem_u32(&empty_bar[s]), ph ^ 1u);
         const uint32_t fb = smem_u32(&full_bar[s]);
         mbar_expect_tx(fb, S::STAGE_BYTES);
-        tma_load_2d(smem_u32(smem_a + s * S::A_BYTES), &tmap_a, fb, (kb_begin + kb) * BK, m0);
+        if (cg.enabled) {
+          const int kk = kb_begin + kb, tap = kk / cg.cin_blocks, cb = kk - tap * cg.cin_blocks;
+          tma_load_4d(smem_u32(smem_a + s * S::A_BYTES), &tmap_a, fb, cb * BK, cw0 + tap % 3 - 1, ch0 + tap / 3 - 1, cn0);
+        } else {
+          tma_load_2d(smem_u32(smem_a + s * S::A_BYTES), &tmap_a, fb, (kb_begin + kb) * BK, m0);
+        }
         tma_load_2d(smem_u32(smem_b + s * S::B_BYTES), &tmap_b, fb, (kb_begin + kb) * BK, n0);
       }
     }
@@ -248,15 +285,33 @@ gemm_f16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid
   } else {
     // ===================== epilogue (warps 2..5) =====================
     const int q = warp & 3;  // TMEM lane quarter this warp may access
-    const int row = m0 + q * 32 + lane;
-    const bool row_ok = row < M;
+    int row = m0 + q * 32 + lane;
+    bool row_ok = row < M;
+    if (cg.enabled) {   // tile row -> (image, y, x) -> pixel index
+      const int r = q * 32 + lane;
+      const int iw = r % cg.bw, ih = (r / cg.bw) % cg.bh, in = r / (cg.bw * cg.bh);
+      row_ok = cn0 + in < cg.N;
+      row = ((cn0 + in) * cg.H + ch0 + ih) * cg.W + cw0 + iw;
+    }
+    // the epilogue warps are idle during the main loop: fetch this row's residual tile now so its latency is
+    // hidden behind the MMAs instead of being paid once per 16-column chunk
+    uint4 res[BN / 8];
+    const bool prefetch_res = epi.residual != nullptr && gridDim.z == 1 && epi.act != L2D_ACT_GEGLU;
+    if (prefetch_res) {
+#pragma unroll
+      for (int i = 0; i < BN / 8; ++i) {
+        res[i] = make_uint4(0, 0, 0, 0);
+        if (row_ok && n0 + i * 8 < N) res[i] = *reinterpret_cast<const uint4*>(epi.residual + (size_t)row * epi.ldr + n0 + i * 8);
+      }
+    }
     mbar_wait(smem_u32(tmem_full_bar), 0);
     tc_fence_after();
     const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
     const __half* rg = (epi.rowgroup_bias && row_ok)
                            ? epi.rowgroup_bias + (size_t)(row / epi.rows_per_group) * epi.rg_ld : nullptr;
     // bias / per-image bias / activation / residual / fp16 store of 16 consecutive output columns
-    auto finish16 = [&](float (&v)[16], int cc) {
+    auto finish16 = [&](float (&v)[16], int cc, bool res_loaded = false, uint4 r0 = make_uint4(0, 0, 0, 0),
+                        uint4 r1 = make_uint4(0, 0, 0, 0)) {
       const int col0 = n0 + cc * 16;
 #pragma unroll
       for (int hlf = 0; hlf < 2; ++hlf) {
@@ -280,10 +335,11 @@ gemm_f16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid
 #pragma unroll
         for (int i = 0; i < 16; ++i) v[i] = silu_f(v[i]);
       }
-      epi_store16(epi, v, row, col0, M, N, row_ok);
+      epi_store16(epi, v, row, col0, M, N, row_ok, res_loaded, r0, r1);
     };
     if (gridDim.z > 1) {
       // ---- split-K: store this split's fp32 partial tile (zeros when the split owns no k-blocks) ----
+      // (conv mode: `row` is already the pixel index; the finish kernel reads the slices by output row)
       float* wrow = epi.ws + (size_t)blockIdx.z * epi.ws_slice + (size_t)row * epi.ws_ld + n0;
 #pragma unroll 1
       for (int cc = 0; cc < BN / 16; ++cc) {
@@ -302,7 +358,7 @@ gemm_f16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid
         }
       }
     } else if (epi.act != L2D_ACT_GEGLU) {
-#pragma unroll 1
+#pragma unroll
       for (int cc = 0; cc < BN / 16; ++cc) {
         uint32_t r[16];
         tmem_ld16(taddr + cc * 16, r);
@@ -310,7 +366,7 @@ gemm_f16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid
         float v[16];
 #pragma unroll
         for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
-        finish16(v, cc);
+        finish16(v, cc, prefetch_res, res[cc * 2], res[cc * 2 + 1]);
       }
     } else {
       // GEGLU: tile columns [0,BN/2) = value half, [BN/2,BN) = matching gate half (weights interleaved
@@ -501,6 +557,47 @@ static GemmPlan gemm_plan(int m, int n, int k, bool allow_split, int force_bn) {
 
 int gemm_pick_tile_n(int m, int n, int k) { return gemm_plan(m, n, k, false, 0).bn; }
 
+// channels-last activation [N,H,W,C] as a 4-D tensor map, box = [bn, bh, bw, 64 channels], 128B swizzle
+static int get_tmap_conv(const void* ptr, int N, int H, int W, int C, int bw, int bh, int bn, CUtensorMap* out) {
+  static std::unordered_map<TmapKey, CUtensorMap, TmapKeyHash> cache;
+  static std::mutex mu;
+  TmapKey key{ptr, (int64_t)N * 1000003 + H, (int64_t)W * 1000003 + C, (int64_t)bw * 65536 + bh * 256 + bn, -4};
+  std::lock_guard<std::mutex> lk(mu);
+  auto it = cache.find(key);
+  if (it != cache.end()) {
+    *out = it->second;
+    return L2D_OK;
+  }
+  PFN_encodeTiled enc = get_encode();
+  if (!enc) return fail(L2D_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available (driver too old?)");
+  cuuint64_t gdim[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
+  cuuint64_t gstr[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
+  cuuint32_t box[4] = {(cuuint32_t)BK, (cuuint32_t)bw, (cuuint32_t)bh, (cuuint32_t)bn};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUtensorMap m;
+  CUresult r = enc(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(ptr), gdim, gstr, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(L2D_ERR_CUDA, "cuTensorMapEncodeTiled(4D) failed, CUresult " + std::to_string((int)r));
+  if (cache.size() > 65536) cache.clear();
+  cache.emplace(key, m);
+  *out = m;
+  return L2D_OK;
+}
+
+static int pow2_divisor(int x, int cap) {
+  int p = 1;
+  while (p * 2 <= cap && x % (p * 2) == 0) p *= 2;
+  return p;
+}
+
+bool conv3x3_implicit_supported(int n_img, int h, int w, int cin) {
+  if (cin % 64 != 0) return false;
+  const int bw = pow2_divisor(w, 128), bh = pow2_divisor(h, 128 / bw);
+  const int bn = 128 / (bw * bh);
+  return bn <= 256 && bw * bh * bn == 128 && (bn == 1 || n_img >= 1);
+}
+
 static float* g_ws = nullptr;
 
 static int ensure_splitk_workspace() {
@@ -510,8 +607,8 @@ static int ensure_splitk_workspace() {
 }
 
 template <int BN, int STAGES>
-static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmEpilogue& e, int M, int N, int K, int splits,
-                       cudaStream_t st) {
+static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmEpilogue& e, const ConvGeom& cg, int M,
+                       int N, int K, int splits, int tiles_m, cudaStream_t st) {
   constexpr size_t smem = (size_t)STAGES * GemmSmem<BN>::STAGE_BYTES + (2 * STAGES + 2) * 8 + 1024;
   static bool configured = false;
   if (!configured) {
@@ -519,21 +616,19 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmE
                                   (int)smem));
     configured = true;
   }
-  dim3 grid(ceil_div(N, BN), ceil_div(M, BM), splits);
-  gemm_f16_tcgen05_kernel<BN, STAGES><<<grid, 192, smem, st>>>(ta, tb, e, M, N, K);
+  dim3 grid(ceil_div(N, BN), tiles_m, splits);
+  gemm_f16_tcgen05_kernel<BN, STAGES><<<grid, 192, smem, st>>>(ta, tb, e, cg, M, N, K);
   L2D_LAUNCH_CHECK();
   return L2D_OK;
 }
 
-int gemm_launch(const __half* a, int64_t lda, const __half* w, int64_t ldw, __half* out, int64_t ldo, int m, int n, int k,
-                const __half* bias, const __half* rowgroup_bias, int64_t rg_ld, int rows_per_group,
-                const __half* residual, int64_t ldr, int act, int force_bn, cudaStream_t st) {
-  const GemmPlan plan = gemm_plan(m, n, k, act != L2D_ACT_GEGLU, force_bn);
+static int gemm_dispatch(const CUtensorMap& ta, const __half* w, int64_t ldw, const ConvGeom& cg, int tiles_m, int m_pad,
+                         __half* out, int64_t ldo, int m, int n, int k, const __half* bias, const __half* rowgroup_bias,
+                         int64_t rg_ld, int rows_per_group, const __half* residual, int64_t ldr, int act,
+                         const GemmPlan& plan, cudaStream_t st) {
   const int bn = plan.bn;
-  CUtensorMap ta, tb;
-  int rc = get_tmap(a, m, k, lda, BM, &ta);
-  if (rc != L2D_OK) return rc;
-  rc = get_tmap(w, n, k, ldw, bn, &tb);
+  CUtensorMap tb;
+  int rc = get_tmap(w, n, k, ldw, bn, &tb);
   if (rc != L2D_OK) return rc;
   GemmEpilogue e{out, ldo, bias, rowgroup_bias, rg_ld, rows_per_group > 0 ? rows_per_group : 1, residual, ldr, act,
                  nullptr, 0, 0};
@@ -542,13 +637,13 @@ int gemm_launch(const __half* a, int64_t lda, const __half* w, int64_t ldw, __ha
     if (rc != L2D_OK) return rc;
     e.ws = g_ws;
     e.ws_ld = (int64_t)ceil_div(n, bn) * bn;
-    e.ws_slice = (int64_t)ceil_div(m, BM) * BM * e.ws_ld;
+    e.ws_slice = (int64_t)m_pad * e.ws_ld;
   }
   switch (bn) {
-    case 64: rc = launch_gemm<64, 6>(ta, tb, e, m, n, k, plan.splits, st); break;
-    case 128: rc = launch_gemm<128, 6>(ta, tb, e, m, n, k, plan.splits, st); break;
-    case 160: rc = launch_gemm<160, 5>(ta, tb, e, m, n, k, plan.splits, st); break;
-    case 256: rc = launch_gemm<256, 4>(ta, tb, e, m, n, k, plan.splits, st); break;
+    case 64: rc = launch_gemm<64, 6>(ta, tb, e, cg, m, n, k, plan.splits, tiles_m, st); break;
+    case 128: rc = launch_gemm<128, 6>(ta, tb, e, cg, m, n, k, plan.splits, tiles_m, st); break;
+    case 160: rc = launch_gemm<160, 5>(ta, tb, e, cg, m, n, k, plan.splits, tiles_m, st); break;
+    case 256: rc = launch_gemm<256, 4>(ta, tb, e, cg, m, n, k, plan.splits, tiles_m, st); break;
     default: return fail(L2D_ERR_INVALID, "gemm: unsupported tile_n");
   }
   if (rc != L2D_OK || plan.splits == 1) return rc;
@@ -559,11 +654,63 @@ int gemm_launch(const __half* a, int64_t lda, const __half* w, int64_t ldw, __ha
   return L2D_OK;
 }
 
+int gemm_launch(const __half* a, int64_t lda, const __half* w, int64_t ldw, __half* out, int64_t ldo, int m, int n, int k,
+                const __half* bias, const __half* rowgroup_bias, int64_t rg_ld, int rows_per_group,
+                const __half* residual, int64_t ldr, int act, int force_bn, cudaStream_t st) {
+  const GemmPlan plan = gemm_plan(m, n, k, act != L2D_ACT_GEGLU, force_bn);
+  CUtensorMap ta;
+  int rc = get_tmap(a, m, k, lda, BM, &ta);
+  if (rc != L2D_OK) return rc;
+  ConvGeom cg{};
+  const int tiles_m = ceil_div(m, BM);
+  return gemm_dispatch(ta, w, ldw, cg, tiles_m, tiles_m * BM, out, ldo, m, n, k, bias, rowgroup_bias, rg_ld, rows_per_group,
+                       residual, ldr, act, plan, st);
+}
+
+// out[N*H*W, cout] = epilogue( conv3x3(x[N,H,W,cin], w[cout, 9*cin]) ), pad 1, stride 1, x channels-last contiguous
+int conv3x3_launch(const __half* x, int n_img, int h, int w_, int cin, const __half* w, __half* out, int64_t ldo, int cout,
+                   const __half* bias, const __half* rowgroup_bias, int64_t rg_ld, int rows_per_group,
+                   const __half* residual, int64_t ldr, int act, cudaStream_t st) {
+  if (!conv3x3_implicit_supported(n_img, h, w_, cin)) return fail(L2D_ERR_INVALID, "conv3x3: shape not tileable");
+  ConvGeom cg{};
+  cg.enabled = 1;
+  cg.cin_blocks = cin / BK;
+  cg.H = h; cg.W = w_; cg.N = n_img;
+  cg.bw = pow2_divisor(w_, 128);
+  cg.bh = pow2_divisor(h, 128 / cg.bw);
+  cg.bn = 128 / (cg.bw * cg.bh);
+  cg.tiles_w = w_ / cg.bw;
+  cg.tiles_h = h / cg.bh;
+  const int tiles_m = cg.tiles_w * cg.tiles_h * ceil_div(n_img, cg.bn);
+  const int m = n_img * h * w_, k = 9 * cin;
+  // the plan's M is the padded tile count (tiles_m * 128 rows), which is what fills the SMs
+  const GemmPlan plan = gemm_plan(tiles_m * BM, cout, k, true, 0);
+  CUtensorMap ta;
+  int rc = get_tmap_conv(x, n_img, h, w_, cin, cg.bw, cg.bh, cg.bn, &ta);
+  if (rc != L2D_OK) return rc;
+  // split-K slices are indexed by output pixel row, so a slice needs m rows (>= the largest pixel index + 1)
+  return gemm_dispatch(ta, w, k, cg, tiles_m, m, out, ldo, m, cout, k, bias, rowgroup_bias, rg_ld, rows_per_group, residual,
+                       ldr, act, plan, st);
+}
+
 }  // namespace l2d
 
 using namespace l2d;
 
 extern "C" int l2d_gemm_tile_n(int m, int n, int k) { return gemm_pick_tile_n(m, n, k); }
+
+extern "C" int l2d_conv3x3(const void* x, int n_img, int h, int w, int cin, const void* weight, void* out, int64_t ldo,
+                           int cout, const void* bias, const void* rowgroup_bias, const void* residual, int64_t ldr,
+                           int act, void* stream) {
+  L2D_CHECK_ARG(x && weight && out, "null pointer");
+  L2D_CHECK_ARG(n_img > 0 && h > 0 && w > 0 && cin > 0 && cout > 0, "empty problem");
+  L2D_CHECK_ARG(cout % 8 == 0 && ldo % 8 == 0 && ldo >= cout, "Cout and ldo must be multiples of 8");
+  L2D_CHECK_ARG(act == L2D_ACT_NONE || act == L2D_ACT_SILU, "act must be none or SiLU");
+  L2D_CHECK_ARG(conv3x3_implicit_supported(n_img, h, w, cin), "need Cin % 64 == 0 and power-of-two tileable H, W");
+  return conv3x3_launch((const __half*)x, n_img, h, w, cin, (const __half*)weight, (__half*)out, ldo, cout,
+                        (const __half*)bias, (const __half*)rowgroup_bias, cout, h * w, (const __half*)residual, ldr, act,
+                        (cudaStream_t)stream);
+}
 
 extern "C" int l2d_gemm(const void* a, int64_t lda, const void* w, void* out, int64_t ldo, int m, int n, int k,
                         const void* bias, const void* rowgroup_bias, int rows_per_group, const void* residual,

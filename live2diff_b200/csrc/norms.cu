@@ -67,7 +67,7 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const __half* __restrict
 // GroupNorm statistics: grid (chunks, N).  Each block reduces a slab of pixels x all channels to
 // per-group (mean, M2) partials; the apply kernel merges the partials (Chan's formula).
 // ---------------------------------------------------------------------------------------------
-constexpr int GN_MAX_SPLIT = 32;
+constexpr int GN_MAX_SPLIT = 128;
 
 struct GnSrc {
   const __half* x1;
@@ -98,13 +98,20 @@ __global__ void __launch_bounds__(512) groupnorm_stats_kernel(GnSrc src, float* 
   const int r = threadIdx.x / nch, ch = threadIdx.x - r * nch;
   if (r < R) {
     float a[8] = {0, 0, 0, 0, 0, 0, 0, 0}, b[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    for (int p = p0 + r; p < p1; p += R) {
-      float v[8];
-      unpack8(gn_load_chunk(src, (size_t)n * hw + p, ch), v);
+    for (int p = p0 + r; p < p1; p += 4 * R) {
+      uint4 raw[4];
 #pragma unroll
-      for (int e = 0; e < 8; ++e) {
-        a[e] += v[e];
-        b[e] = fmaf(v[e], v[e], b[e]);
+      for (int i = 0; i < 4; ++i)   // 4 independent loads in flight
+        raw[i] = (p + i * R < p1) ? gn_load_chunk(src, (size_t)n * hw + p + i * R, ch) : make_uint4(0, 0, 0, 0);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        float v[8];
+        unpack8(raw[i], v);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          a[e] += v[e];
+          b[e] = fmaf(v[e], v[e], b[e]);
+        }
       }
     }
 #pragma unroll
@@ -309,7 +316,7 @@ __global__ void __launch_bounds__(256) transpose_kernel(const __half* __restrict
 // launchers
 // ---------------------------------------------------------------------------------------------
 static int pick_split(int hw) {
-  int s = hw / 128;
+  int s = hw / 32;   // ~32 pixels per block: the per-thread pixel loop stays short (it is latency-bound)
   if (s < 1) s = 1;
   if (s > GN_MAX_SPLIT) s = GN_MAX_SPLIT;
   return s;

@@ -35,6 +35,11 @@ int gemm_launch(const __half* a, int64_t lda, const __half* w, int64_t ldw, __ha
                 const __half* bias, const __half* rowgroup_bias, int64_t rg_ld, int rows_per_group,
                 const __half* residual, int64_t ldr, int act, int force_bn, cudaStream_t st);
 
+bool conv3x3_implicit_supported(int n_img, int h, int w, int cin);
+int conv3x3_launch(const __half* x, int n_img, int h, int w, int cin, const __half* weight, __half* out, int64_t ldo, int cout,
+                   const __half* bias, const __half* rowgroup_bias, int64_t rg_ld, int rows_per_group,
+                   const __half* residual, int64_t ldr, int act, cudaStream_t st);
+
 int attention_launch(const __half* q, int64_t ldq, const __half* k, int64_t ldk, const __half* v, int64_t ldv, __half* o,
                      int64_t ldo, int batch, int heads, int sq, int skv, int hd, cudaStream_t st);
 

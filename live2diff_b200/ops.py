@@ -125,6 +125,19 @@ def gemm(a, w, bias=None, rowgroup_bias=None, rows_per_group=0, residual=None, a
     return out
 
 
+def conv3x3(x, n_img, h, w, weight, bias=None, rowgroup_bias=None, residual=None, act=ACT_NONE):
+    """Implicit-GEMM conv3x3 (pad 1, stride 1).  x [N*h*w, Cin] channels-last, weight [Cout, 9*Cin] (tap, cin)."""
+    _chk(x, "x")
+    _chk(weight, "weight")
+    cin = x.shape[-1]
+    cout = weight.shape[0]
+    out = torch.empty(n_img * h * w, cout, dtype=torch.float16, device=x.device)
+    ldr = residual.stride(0) if residual is not None else 0
+    check(lib().l2d_conv3x3(ptr(x), n_img, h, w, cin, ptr(weight), ptr(out), out.stride(0), cout, ptr(bias),
+                            ptr(rowgroup_bias), ptr(residual), ldr, act, current_stream()))
+    return out
+
+
 def small_linear(x, w, b=None, silu_in=False, silu_out=False):
     _chk(x, "x")
     _chk(w, "w")

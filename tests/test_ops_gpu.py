@@ -261,3 +261,19 @@ def test_gemm_splitk_workspace_is_restored():
             bias, res = rnd(n, seed=32), rnd(m, n, seed=33)
             out = ops.gemm(a, w, bias=bias, residual=res)
             strict(out, a.float() @ w.float().t() + bias.float() + res.float(), f"split-K {m}x{n}x{k} rep {rep}")
+
+
+@pytest.mark.parametrize("n,h,w,cin,cout", [(2, 64, 64, 320, 320), (2, 32, 32, 640, 640), (2, 8, 8, 1280, 1280),
+                                            (2, 16, 16, 2560, 1280), (1, 8, 8, 64, 64), (2, 64, 96, 64, 64),
+                                            (2, 64, 64, 320, 8), (2, 4, 4, 128, 128)])
+def test_conv3x3_implicit_gemm(n, h, w, cin, cout):
+    """conv3x3 pad 1 as an implicit GEMM (4-D TMA halo boxes, zero fill = padding), incl. temb bias + residual."""
+    from live2diff_b200 import ops
+
+    x = rnd(n, cin, h, w, seed=40)
+    wt = rnd(cout, cin, 3, 3, seed=41, scale=1 / math.sqrt(9 * cin))
+    bias, temb, res = rnd(cout, seed=42, scale=0.1), rnd(n, cout, seed=43), rnd(n, cout, h, w, seed=44)
+    wr = wt.permute(0, 2, 3, 1).reshape(cout, 9 * cin).contiguous()          # (tap, cin) columns
+    out = ops.conv3x3(_nhwc(x), n, h, w, wr, bias=bias, rowgroup_bias=temb, residual=_nhwc(res))
+    ref = F.conv2d(x.float(), wt.float(), bias.float(), padding=1) + temb.float()[:, :, None, None] + res.float()
+    strict(out, _nhwc(ref), f"conv3x3 {n}x{h}x{w} {cin}->{cout}")
