@@ -407,6 +407,7 @@ extern "C" int l2d_tt_create(l2d_tt** out, const l2d_tensor* weights, int n_weig
   RC(k.pool.halfs(&k.s.qkv, m * 3 * c));
   RC(k.pool.halfs(&k.s.ff, m * 4 * c));
   RC(k.pool.alloc(reinterpret_cast<void**>(&k.s.gn_ws), (size_t)l2d_groupnorm_workspace_bytes(n_rows, groups)));
+  L2D_CUDA(cudaMemsetAsync(k.s.gn_ws, 0, (size_t)l2d_groupnorm_workspace_bytes(n_rows, groups), k.st));
   RC(k.pool.halfs(&t->x_nhwc, m * c));
   RC(k.pool.halfs(&t->y_nhwc, m * c));
   WeightTable wt;
@@ -781,6 +782,7 @@ extern "C" int l2d_unet_create(l2d_unet** out, const l2d_unet_config* cfg, const
   RC(k.pool.halfs(&s.qkv, max_mc * 3));
   RC(k.pool.halfs(&s.ff, max_mc * 4));
   RC(k.pool.alloc(reinterpret_cast<void**>(&s.gn_ws), (size_t)l2d_groupnorm_workspace_bytes(n, cfg->groups)));
+  L2D_CUDA(cudaMemsetAsync(s.gn_ws, 0, (size_t)l2d_groupnorm_workspace_bytes(n, cfg->groups), k.st));
   RC(k.pool.halfs(&u->hA, max_mc));
   RC(k.pool.halfs(&u->hB, max_mc));
   RC(k.pool.halfs(&u->map_a, max_map));

@@ -137,43 +137,47 @@ __global__ void __launch_bounds__(128) flash_attn_kernel(const FlashParams p) {
       }
     }
     // ---- online softmax (rows g and g+8 of this warp's 16) ----
+    // scores stay unscaled; the softmax scale is folded into the exp2 argument: p = 2^(s*c - m*c), one FFMA + one
+    // MUFU per score.  Only the last key tile can hold out-of-range columns.
     const int kv0 = it * FA_BN;
+    if (kv0 + FA_BN > p.skv) {
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int col = kv0 + nt * 8 + 2 * t + (e & 1);
+          if (col >= p.skv) s_acc[nt][e] = -INFINITY;
+        }
+      }
+    }
     float mx[2] = {-INFINITY, -INFINITY};
 #pragma unroll
     for (int nt = 0; nt < 8; ++nt) {
-#pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const int col = kv0 + nt * 8 + 2 * t + (e & 1);
-        float sv = s_acc[nt][e] * p.scale_log2;
-        if (col >= p.skv) sv = -INFINITY;
-        s_acc[nt][e] = sv;
-        mx[e >> 1] = fmaxf(mx[e >> 1], sv);
-      }
+      mx[0] = fmaxf(mx[0], fmaxf(s_acc[nt][0], s_acc[nt][1]));
+      mx[1] = fmaxf(mx[1], fmaxf(s_acc[nt][2], s_acc[nt][3]));
     }
-    float corr[2];
+    float corr[2], mneg[2];
 #pragma unroll
     for (int r = 0; r < 2; ++r) {
       mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 1));
       mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 2));
-      const float m_new = fmaxf(m_run[r], mx[r]);
-      corr[r] = exp2f(m_run[r] - m_new);
+      const float m_new = fmaxf(m_run[r], mx[r]);            // running max of the raw scores
+      corr[r] = exp2f((m_run[r] - m_new) * p.scale_log2);
       m_run[r] = m_new;
+      mneg[r] = -m_new * p.scale_log2;
     }
     float rs[2] = {0.f, 0.f};
     uint32_t pf[4][4];  // P as A fragments for the 4 k16 steps over keys
 #pragma unroll
     for (int nt = 0; nt < 8; ++nt) {
-      const float p0 = exp2f(s_acc[nt][0] - m_run[0]);
-      const float p1 = exp2f(s_acc[nt][1] - m_run[0]);
-      const float p2 = exp2f(s_acc[nt][2] - m_run[1]);
-      const float p3 = exp2f(s_acc[nt][3] - m_run[1]);
-      const __half2 h01 = __floats2half2_rn(p0, p1), h23 = __floats2half2_rn(p2, p3);
-      // sum what is actually multiplied (the fp16-rounded P), as the fused SDPA kernels do
-      const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
-      rs[0] += f01.x + f01.y;
-      rs[1] += f23.x + f23.y;
-      pf[nt >> 1][(nt & 1) * 2 + 0] = h2_as_u32(h01);
-      pf[nt >> 1][(nt & 1) * 2 + 1] = h2_as_u32(h23);
+      const float p0 = exp2f(fmaf(s_acc[nt][0], p.scale_log2, mneg[0]));
+      const float p1 = exp2f(fmaf(s_acc[nt][1], p.scale_log2, mneg[0]));
+      const float p2 = exp2f(fmaf(s_acc[nt][2], p.scale_log2, mneg[1]));
+      const float p3 = exp2f(fmaf(s_acc[nt][3], p.scale_log2, mneg[1]));
+      rs[0] += p0 + p1;                                       // fp32 row sum (as flash-attention does)
+      rs[1] += p2 + p3;
+      pf[nt >> 1][(nt & 1) * 2 + 0] = h2_as_u32(__floats2half2_rn(p0, p1));
+      pf[nt >> 1][(nt & 1) * 2 + 1] = h2_as_u32(__floats2half2_rn(p2, p3));
     }
 #pragma unroll
     for (int r = 0; r < 2; ++r) l_run[r] = l_run[r] * corr[r] + rs[r];

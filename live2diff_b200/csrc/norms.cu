@@ -81,13 +81,27 @@ __device__ __forceinline__ uint4 gn_load_chunk(const GnSrc& s, size_t pix, int c
   return ldg_cached(s.x2 + pix * s.c2 + (c - s.c1));
 }
 
-// partial layout: [N][split][G][2] floats (mean, M2); counts are implied (equal slabs except the last)
-__global__ void __launch_bounds__(512) groupnorm_stats_kernel(GnSrc src, float* __restrict__ partial, int hw, int G,
-                                                               int split) {
+// workspace layout (floats): partial [N][GN_MAX_SPLIT][G][2] (mean, M2 of each slab) | ab [N][2][GN_MAX_C] (per-channel
+// scale, shift) | counters [N] (ints, zero between launches).  The last slab-block of an image to finish merges the
+// slabs (Chan's formula, done as two parallel weighted sums) and writes the per-channel scale/shift, so the apply
+// kernel is a pure streaming pass.
+constexpr int GN_MAX_C = 4096;
+
+__device__ __forceinline__ float* gn_ab(float* ws, int n_img, int G, int n) {
+  return ws + (size_t)n_img * GN_MAX_SPLIT * G * 2 + (size_t)n * 2 * GN_MAX_C;
+}
+__device__ __forceinline__ int* gn_counters(float* ws, int n_img, int G) {
+  return reinterpret_cast<int*>(ws + (size_t)n_img * GN_MAX_SPLIT * G * 2 + (size_t)n_img * 2 * GN_MAX_C);
+}
+
+__global__ void __launch_bounds__(512) groupnorm_stats_kernel(GnSrc src, const __half* __restrict__ gamma,
+                                                               const __half* __restrict__ beta, float* __restrict__ ws,
+                                                               int hw, int G, int split, float eps) {
   extern __shared__ float sm[];  // [2][C] per-channel sum, sumsq
+  __shared__ int s_last;
   const int C = src.c1 + src.c2;
   const int nch = C >> 3;
-  const int n = blockIdx.y, sp = blockIdx.x;
+  const int n = blockIdx.y, sp = blockIdx.x, n_img = gridDim.y;
   const int per = (hw + split - 1) / split;
   const int p0 = sp * per, p1 = min(hw, p0 + per);
   float* s_sum = sm;
@@ -123,6 +137,7 @@ __global__ void __launch_bounds__(512) groupnorm_stats_kernel(GnSrc src, float* 
   __syncthreads();
   const int cpg = C / G;
   const float cnt = (float)(p1 - p0) * (float)cpg;
+  float* partial = ws;
   for (int g = threadIdx.x; g < G; g += blockDim.x) {
     float s = 0.f, q = 0.f;
     for (int i = 0; i < cpg; ++i) {
@@ -131,57 +146,81 @@ __global__ void __launch_bounds__(512) groupnorm_stats_kernel(GnSrc src, float* 
     }
     const float mean = cnt > 0.f ? s / cnt : 0.f;
     const float m2 = fmaxf(q - s * mean, 0.f);
-    float* o = partial + (((size_t)n * split + sp) * G + g) * 2;
+    float* o = partial + (((size_t)n * GN_MAX_SPLIT + sp) * G + g) * 2;
     o[0] = mean;
     o[1] = m2;
   }
+  // ---- last slab of image n merges all slabs and publishes per-channel scale/shift ----
+  __threadfence();
+  __syncthreads();
+  int* counters = gn_counters(ws, n_img, G);
+  if (threadIdx.x == 0) {
+    const int prev = atomicAdd(&counters[n], 1);
+    s_last = prev == split - 1;
+    if (s_last) counters[n] = 0;
+  }
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  float* ab = gn_ab(ws, n_img, G, n);
+  for (int g = warp; g < G; g += nwarps) {   // one warp per group: two weighted sums over the slabs
+    float wsum = 0.f, wmean = 0.f;
+    for (int s2 = lane; s2 < split; s2 += 32) {
+      const int q0 = s2 * per, q1 = min(hw, q0 + per);
+      const float c = (float)max(q1 - q0, 0) * (float)cpg;
+      const float* src2 = partial + (((size_t)n * GN_MAX_SPLIT + s2) * G + g) * 2;
+      wsum += c;
+      wmean += c * __ldcg(src2);
+    }
+    wsum = warp_sum(wsum);
+    const float mean = warp_sum(wmean) / wsum;
+    float m2 = 0.f;
+    for (int s2 = lane; s2 < split; s2 += 32) {
+      const int q0 = s2 * per, q1 = min(hw, q0 + per);
+      const float c = (float)max(q1 - q0, 0) * (float)cpg;
+      const float* src2 = partial + (((size_t)n * GN_MAX_SPLIT + s2) * G + g) * 2;
+      const float d = __ldcg(src2) - mean;
+      m2 += __ldcg(src2 + 1) + c * d * d;
+    }
+    const float rstd = rsqrtf(warp_sum(m2) / wsum + eps);
+    for (int i = lane; i < cpg; i += 32) {
+      const int c = g * cpg + i;
+      const float ga = __half2float(gamma[c]) * rstd;
+      ab[c] = ga;
+      ab[GN_MAX_C + c] = __half2float(beta[c]) - mean * ga;
+    }
+  }
 }
 
-// Apply: y = act((x - mean_g) * rstd_g * gamma_c + beta_c); mode 0 writes NHWC, mode 1 writes the
-// 3x3 im2col matrix (pad 1, given stride) of the normalised tensor.
+// Apply: y = act(x * scale_c + shift_c); mode 0 writes NHWC, mode 1 writes the 3x3 im2col matrix (pad 1, given
+// stride) of the normalised tensor.
 struct GnApplyParams {
   GnSrc src;
-  const __half* gamma;
-  const __half* beta;
-  const float* partial;
+  const float* ab;   // [N][2][GN_MAX_C]
   __half* y;
-  int h, w, G, split;
-  float eps;
+  int h, w;
   int silu, mode, stride;
 };
 
+__device__ __forceinline__ void gn_norm8(float (&v)[8], const float* __restrict__ ab, int c0, int silu) {
+  const float4 a0 = __ldg(reinterpret_cast<const float4*>(ab + c0)), a1 = __ldg(reinterpret_cast<const float4*>(ab + c0 + 4));
+  const float4 b0 = __ldg(reinterpret_cast<const float4*>(ab + GN_MAX_C + c0));
+  const float4 b1 = __ldg(reinterpret_cast<const float4*>(ab + GN_MAX_C + c0 + 4));
+  const float A[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+  const float B[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    const float t = fmaf(v[e], A[e], B[e]);
+    v[e] = silu ? silu_f(t) : t;
+  }
+}
+
 __global__ void __launch_bounds__(256) groupnorm_apply_kernel(const GnApplyParams p) {
-  extern __shared__ float sm[];  // A[C], B[C]
   const int C = p.src.c1 + p.src.c2;
   const int hw = p.h * p.w;
   const int n = blockIdx.y;
-  const int cpg = C / p.G;
-  float* sA = sm;
-  float* sB = sm + C;
-  // merge the split partials of every group of image n
-  for (int g = threadIdx.x; g < p.G; g += blockDim.x) {
-    const int per = (hw + p.split - 1) / p.split;
-    float mean = 0.f, m2 = 0.f, cnt = 0.f;
-    for (int s = 0; s < p.split; ++s) {
-      const int p0 = s * per, p1 = min(hw, p0 + per);
-      const float c = (float)max(p1 - p0, 0) * (float)cpg;
-      if (c <= 0.f) continue;
-      const float* src = p.partial + (((size_t)n * p.split + s) * p.G + g) * 2;
-      const float d = src[0] - mean;
-      const float tot = cnt + c;
-      m2 += src[1] + d * d * cnt * c / tot;
-      mean += d * c / tot;
-      cnt = tot;
-    }
-    const float rstd = rsqrtf(m2 / cnt + p.eps);
-    for (int i = 0; i < cpg; ++i) {
-      const int c = g * cpg + i;
-      const float ga = __half2float(p.gamma[c]) * rstd;
-      sA[c] = ga;
-      sB[c] = __half2float(p.beta[c]) - mean * ga;
-    }
-  }
-  __syncthreads();
+  const float* ab = p.ab + (size_t)n * 2 * GN_MAX_C;
   const int nch = C >> 3;
   if (p.mode == 0) {
     const size_t total = (size_t)hw * nch;
@@ -190,11 +229,7 @@ __global__ void __launch_bounds__(256) groupnorm_apply_kernel(const GnApplyParam
       const size_t pix = (size_t)n * hw + i / nch;
       float v[8];
       unpack8(gn_load_chunk(p.src, pix, ch), v);
-#pragma unroll
-      for (int e = 0; e < 8; ++e) {
-        float t = fmaf(v[e], sA[ch * 8 + e], sB[ch * 8 + e]);
-        v[e] = p.silu ? silu_f(t) : t;
-      }
+      gn_norm8(v, ab, ch * 8, p.silu);
       *reinterpret_cast<uint4*>(p.y + pix * C + ch * 8) = pack8(v);
     }
   } else {
@@ -211,11 +246,7 @@ __global__ void __launch_bounds__(256) groupnorm_apply_kernel(const GnApplyParam
       if (iy >= 0 && iy < p.h && ix >= 0 && ix < p.w) {
         float v[8];
         unpack8(gn_load_chunk(p.src, (size_t)n * hw + (size_t)iy * p.w + ix, ch), v);
-#pragma unroll
-        for (int e = 0; e < 8; ++e) {
-          float t = fmaf(v[e], sA[ch * 8 + e], sB[ch * 8 + e]);
-          v[e] = p.silu ? silu_f(t) : t;
-        }
+        gn_norm8(v, ab, ch * 8, p.silu);
         o = pack8(v);
       }
       *reinterpret_cast<uint4*>(p.y + ((size_t)n * ho * wo + opix) * K + (size_t)tap * C + ch * 8) = o;
@@ -328,27 +359,21 @@ int groupnorm_launch(const __half* x1, int c1, const __half* x2, int c2, const _
   const int C = c1 + c2, hw = h * w, nch = C / 8;
   const int split = pick_split(hw);
   GnSrc src{x1, x2, c1, c2};
-  int threads = 512;
-  if (nch > threads) return fail(L2D_ERR_INVALID, "groupnorm: C > 4096");
-  static size_t cfg_stats = 0, cfg_apply = 0;
+  const int threads = 512;
+  if (nch > threads || C > GN_MAX_C) return fail(L2D_ERR_INVALID, "groupnorm: C > 4096");
+  static size_t cfg_stats = 0;
   const size_t smem = (size_t)2 * C * sizeof(float);
-  if (smem > 48 * 1024) {
-    if (smem > cfg_stats) {
-      L2D_CUDA(cudaFuncSetAttribute(groupnorm_stats_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      cfg_stats = smem;
-    }
-    if (smem > cfg_apply) {
-      L2D_CUDA(cudaFuncSetAttribute(groupnorm_apply_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      cfg_apply = smem;
-    }
+  if (smem > 48 * 1024 && smem > cfg_stats) {
+    L2D_CUDA(cudaFuncSetAttribute(groupnorm_stats_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    cfg_stats = smem;
   }
-  groupnorm_stats_kernel<<<dim3(split, n_img), threads, smem, st>>>(src, ws, hw, G, split);
+  groupnorm_stats_kernel<<<dim3(split, n_img), threads, smem, st>>>(src, gamma, beta, ws, hw, G, split, eps);
   L2D_LAUNCH_CHECK();
-  GnApplyParams p{src, gamma, beta, ws, y, h, w, G, split, eps, silu, mode, stride};
+  GnApplyParams p{src, ws + (size_t)n_img * GN_MAX_SPLIT * G * 2, y, h, w, silu, mode, stride};
   size_t work = mode == 0 ? (size_t)hw * nch : (size_t)(h / stride) * (w / stride) * 9 * nch;
   int blocks = (int)std::min<size_t>((work + 255) / 256, 148 * 8);
   if (blocks < 1) blocks = 1;
-  groupnorm_apply_kernel<<<dim3(blocks, n_img), 256, smem, st>>>(p);
+  groupnorm_apply_kernel<<<dim3(blocks, n_img), 256, 0, st>>>(p);
   L2D_LAUNCH_CHECK();
   return L2D_OK;
 }
@@ -370,7 +395,8 @@ extern "C" int l2d_layernorm(const void* x, const void* gamma, const void* beta,
 }
 
 extern "C" int64_t l2d_groupnorm_workspace_bytes(int n_img, int groups) {
-  return (int64_t)n_img * GN_MAX_SPLIT * groups * 2 * sizeof(float);
+  return ((int64_t)n_img * GN_MAX_SPLIT * groups * 2 + (int64_t)n_img * 2 * GN_MAX_C) * sizeof(float) +
+         (int64_t)n_img * sizeof(int) + 64;
 }
 
 extern "C" int l2d_groupnorm(const void* x1, int c1, const void* x2, int c2, const void* gamma, const void* beta,

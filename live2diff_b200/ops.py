@@ -51,7 +51,7 @@ def groupnorm(x1, gamma, beta, n_img, h, w, groups, eps, silu=False, x2=None, im
     c1 = x1.shape[-1]
     c2 = 0 if x2 is None else x2.shape[-1]
     c = c1 + c2
-    ws = torch.empty(lib().l2d_groupnorm_workspace_bytes(n_img, groups), dtype=torch.uint8, device=x1.device)
+    ws = torch.zeros(lib().l2d_groupnorm_workspace_bytes(n_img, groups), dtype=torch.uint8, device=x1.device)
     if im2col:
         y = torch.empty(n_img * (h // stride) * (w // stride), 9 * c, dtype=torch.float16, device=x1.device)
     else:
