@@ -167,6 +167,33 @@ struct GemmSmem {
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
 };
 
+// v: activated accumulator values for output columns col0 .. col0+15 of `row`; res0/res1: the residual's 2 x 8
+// columns, already in registers (prefetched while the main loop ran) or loaded here when `res_loaded` is false
+__device__ __forceinline__ void epi_store16(const GemmEpilogue& e, float (&v)[16], int row, int col0, int M, int n_out,
+                                            bool row_ok, bool res_loaded = false, uint4 res0 = make_uint4(0, 0, 0, 0),
+                                            uint4 res1 = make_uint4(0, 0, 0, 0)) {
+  if (!row_ok) return;
+#pragma unroll
+  for (int hlf = 0; hlf < 2; ++hlf) {
+    const int col = col0 + hlf * 8;
+    if (col < n_out) {
+      float o[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) o[i] = v[hlf * 8 + i];
+      if (e.residual) {
+        float r[8];
+        // plain (coherent) load: the residual may alias `out` (in-place  h += f(h))
+        const uint4 rr = res_loaded ? (hlf ? res1 : res0)
+                                    : *reinterpret_cast<const uint4*>(e.residual + (size_t)row * e.ldr + col);
+        unpack8(rr, r);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) o[i] += r[i];
+      }
+      *reinterpret_cast<uint4*>(e.out + (size_t)row * e.ldo + col) = pack8(o);
+    }
+  }
+}
+
 template <int BN, int STAGES>
 __global__ void __launch_bounds__(192, 1)
 gemm_f16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
@@ -257,31 +284,62 @@ gemm_f16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid
     }
   } else {
     // ===================== epilogue (warps 2..5) =====================
-    // Phase 1 (thread <-> accumulator row): TMEM -> registers, + bias + per-image bias, activation, round to fp16,
-    //          stage the warp's 32 x BN_OUT block in shared memory (the pipeline stages are free by now).
-    // Phase 2 (lanes <-> 16-byte column groups of one row): coalesced residual read + add + 128-bit stores, so every
-    //          global transaction is a full row segment instead of 32 scattered 32-byte pieces.
     const int q = warp & 3;  // TMEM lane quarter this warp may access
-    const int r_tile = q * 32 + lane;
-    auto out_row = [&](int r, bool& ok) -> int {   // tile row -> output row (pixel index in conv mode)
-      if (cg.enabled) {
-        const int iw = r % cg.bw, ih = (r / cg.bw) % cg.bh, in = r / (cg.bw * cg.bh);
-        ok = cn0 + in < cg.N;
-        return ((cn0 + in) * cg.H + ch0 + ih) * cg.W + cw0 + iw;
+    int row = m0 + q * 32 + lane;
+    bool row_ok = row < M;
+    if (cg.enabled) {   // tile row -> (image, y, x) -> pixel index
+      const int r = q * 32 + lane;
+      const int iw = r % cg.bw, ih = (r / cg.bw) % cg.bh, in = r / (cg.bw * cg.bh);
+      row_ok = cn0 + in < cg.N;
+      row = ((cn0 + in) * cg.H + ch0 + ih) * cg.W + cw0 + iw;
+    }
+    // the epilogue warps are idle during the main loop: fetch this row's residual tile now so its latency is
+    // hidden behind the MMAs instead of being paid once per 16-column chunk
+    uint4 res[BN / 8];
+    const bool prefetch_res = epi.residual != nullptr && gridDim.z == 1 && epi.act != L2D_ACT_GEGLU;
+    if (prefetch_res) {
+#pragma unroll
+      for (int i = 0; i < BN / 8; ++i) {
+        res[i] = make_uint4(0, 0, 0, 0);
+        if (row_ok && n0 + i * 8 < N) res[i] = *reinterpret_cast<const uint4*>(epi.residual + (size_t)row * epi.ldr + n0 + i * 8);
       }
-      ok = m0 + r < M;
-      return m0 + r;
-    };
-    bool row_ok;
-    const int row = out_row(r_tile, row_ok);
+    }
     mbar_wait(smem_u32(tmem_full_bar), 0);
     tc_fence_after();
     const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
     const __half* rg = (epi.rowgroup_bias && row_ok)
                            ? epi.rowgroup_bias + (size_t)(row / epi.rows_per_group) * epi.rg_ld : nullptr;
+    // bias / per-image bias / activation / residual / fp16 store of 16 consecutive output columns
+    auto finish16 = [&](float (&v)[16], int cc, bool res_loaded = false, uint4 r0 = make_uint4(0, 0, 0, 0),
+                        uint4 r1 = make_uint4(0, 0, 0, 0)) {
+      const int col0 = n0 + cc * 16;
+#pragma unroll
+      for (int hlf = 0; hlf < 2; ++hlf) {
+        const int col = col0 + hlf * 8;
+        if (col < N) {
+          if (epi.bias) {
+            float b[8];
+            unpack8(ldg_cached(epi.bias + col), b);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[hlf * 8 + i] += b[i];
+          }
+          if (rg) {
+            float b[8];
+            unpack8(ldg_cached(rg + col), b);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[hlf * 8 + i] += b[i];
+          }
+        }
+      }
+      if (epi.act == L2D_ACT_SILU) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] = silu_f(v[i]);
+      }
+      epi_store16(epi, v, row, col0, M, N, row_ok, res_loaded, r0, r1);
+    };
     if (gridDim.z > 1) {
-      // ---- split-K: store this split's fp32 partial tile (zeros when the split owns no k-blocks); the slices are
-      //      indexed by output row, summed by splitk_finish_kernel ----
+      // ---- split-K: store this split's fp32 partial tile (zeros when the split owns no k-blocks) ----
+      // (conv mode: `row` is already the pixel index; the finish kernel reads the slices by output row)
       float* wrow = epi.ws + (size_t)blockIdx.z * epi.ws_slice + (size_t)row * epi.ws_ld + n0;
 #pragma unroll 1
       for (int cc = 0; cc < BN / 16; ++cc) {
@@ -299,124 +357,49 @@ gemm_f16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid
             *reinterpret_cast<uint4*>(wrow + cc * 16 + q4 * 4) = make_uint4(r[q4 * 4], r[q4 * 4 + 1], r[q4 * 4 + 2], r[q4 * 4 + 3]);
         }
       }
-    } else {
-      const bool geglu = epi.act == L2D_ACT_GEGLU;
-      const int bn_out = geglu ? BN / 2 : BN;              // output columns of this tile
-      const int n_out = geglu ? N / 2 : N;                 // output columns of the matrix
-      const int nout0 = geglu ? (int)blockIdx.x * (BN / 2) : n0;
-      constexpr int PITCH = BN * 2 + 16;                   // bytes; +16 keeps the 16-byte row stores conflict-free
-      uint8_t* stage = smem + (size_t)q * 32 * PITCH;      // this warp's 32 rows
-      // ---------------- phase 1 ----------------
-      if (!geglu) {
-#pragma unroll 1
-        for (int cc = 0; cc < BN / 16; ++cc) {
-          uint32_t r[16];
-          tmem_ld16(taddr + cc * 16, r);
-          tmem_ld_wait();
-          float v[16];
+    } else if (epi.act != L2D_ACT_GEGLU) {
 #pragma unroll
-          for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
-          const int col0 = n0 + cc * 16;
+      for (int cc = 0; cc < BN / 16; ++cc) {
+        uint32_t r[16];
+        tmem_ld16(taddr + cc * 16, r);
+        tmem_ld_wait();
+        float v[16];
 #pragma unroll
-          for (int hlf = 0; hlf < 2; ++hlf) {
-            const int col = col0 + hlf * 8;
-            if (col < N) {
-              if (epi.bias) {
-                float b[8];
-                unpack8(ldg_cached(epi.bias + col), b);
-#pragma unroll
-                for (int i = 0; i < 8; ++i) v[hlf * 8 + i] += b[i];
-              }
-              if (rg) {
-                float b[8];
-                unpack8(ldg_cached(rg + col), b);
-#pragma unroll
-                for (int i = 0; i < 8; ++i) v[hlf * 8 + i] += b[i];
-              }
-            }
-          }
-          if (epi.act == L2D_ACT_SILU) {
-#pragma unroll
-            for (int i = 0; i < 16; ++i) v[i] = silu_f(v[i]);
-          }
-          float lo[8], hi[8];
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            lo[i] = v[i];
-            hi[i] = v[8 + i];
-          }
-          *reinterpret_cast<uint4*>(stage + (size_t)lane * PITCH + cc * 32) = pack8(lo);
-          *reinterpret_cast<uint4*>(stage + (size_t)lane * PITCH + cc * 32 + 16) = pack8(hi);
-        }
-      } else {
-        // GEGLU: tile columns [0,BN/2) = value half, [BN/2,BN) = matching gate half (weights interleaved by
-        // l2d_geglu_interleave)
-        constexpr int HB = BN / 2;
-#pragma unroll 1
-        for (int cc = 0; cc < HB / 16; ++cc) {
-          uint32_t rh[16], rgt[16];
-          tmem_ld16(taddr + cc * 16, rh);
-          tmem_ld16(taddr + HB + cc * 16, rgt);
-          tmem_ld_wait();
-          const int colh = n0 + cc * 16;       // column in the interleaved weight (value half)
-          const int colg = n0 + HB + cc * 16;  // gate half
-          float v[16];
-#pragma unroll
-          for (int hlf = 0; hlf < 2; ++hlf) {
-            float bh[8], bg[8];
-#pragma unroll
-            for (int i = 0; i < 8; ++i) bh[i] = bg[i] = 0.f;
-            if (epi.bias && colh + hlf * 8 < N) {
-              unpack8(ldg_cached(epi.bias + colh + hlf * 8), bh);
-              unpack8(ldg_cached(epi.bias + colg + hlf * 8), bg);
-            }
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              // the reference rounds the projection to fp16 before h * gelu(g) (GEGLU.forward on an fp16 Linear output)
-              const float hval = __half2float(__float2half_rn(__uint_as_float(rh[hlf * 8 + i]) + bh[i]));
-              const float gval = __half2float(__float2half_rn(__uint_as_float(rgt[hlf * 8 + i]) + bg[i]));
-              v[hlf * 8 + i] = hval * gelu_erf_f(gval);
-            }
-          }
-          float lo[8], hi[8];
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            lo[i] = v[i];
-            hi[i] = v[8 + i];
-          }
-          *reinterpret_cast<uint4*>(stage + (size_t)lane * PITCH + cc * 32) = pack8(lo);
-          *reinterpret_cast<uint4*>(stage + (size_t)lane * PITCH + cc * 32 + 16) = pack8(hi);
-        }
+        for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+        finish16(v, cc, prefetch_res, res[cc * 2], res[cc * 2 + 1]);
       }
-      __syncwarp();
-      // ---------------- phase 2 ----------------
-      const int lanes_per_row = bn_out / 8;                  // 16-byte groups per output row of the tile (8..32)
-      const int rows_per_it = 32 / lanes_per_row;            // rows one warp instruction covers (1..4)
-      const int sub = lane / lanes_per_row, g8 = lane - sub * lanes_per_row;
-      const bool lane_on = sub < rows_per_it;
-      const int col = nout0 + g8 * 8;
-      const bool col_ok = lane_on && col < n_out;
-#pragma unroll 2
-      for (int rr = 0; rr < 32; rr += rows_per_it) {
-        const int rl = rr + sub;                             // row within this warp's 32
-        bool ok = false;
-        int orow = 0;
-        if (lane_on && rl < 32) orow = out_row(q * 32 + rl, ok);
-        if (ok && col_ok) {
-          uint4 val = *reinterpret_cast<const uint4*>(stage + (size_t)rl * PITCH + g8 * 16);
-          if (epi.residual) {
-            // plain (coherent) load: the residual may alias `out` (in-place  h += f(h)); each element is read and
-            // written by the same thread
-            const uint4 rsd = *reinterpret_cast<const uint4*>(epi.residual + (size_t)orow * epi.ldr + col);
-            float a[8], b[8];
-            unpack8(val, a);
-            unpack8(rsd, b);
+    } else {
+      // GEGLU: tile columns [0,BN/2) = value half, [BN/2,BN) = matching gate half (weights interleaved
+      // by l2d_geglu_interleave); output columns blockIdx.x*BN/2 + ...
+      constexpr int HB = BN / 2;
+      const int n_out = N / 2;
+#pragma unroll 1
+      for (int cc = 0; cc < HB / 16; ++cc) {
+        uint32_t rh[16], rgt[16];
+        tmem_ld16(taddr + cc * 16, rh);
+        tmem_ld16(taddr + HB + cc * 16, rgt);
+        tmem_ld_wait();
+        const int colh = n0 + cc * 16;       // column in the interleaved weight (value half)
+        const int colg = n0 + HB + cc * 16;  // gate half
+        float v[16];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) a[i] += b[i];
-            val = pack8(a);
+        for (int hlf = 0; hlf < 2; ++hlf) {
+          float bh[8], bg[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) bh[i] = bg[i] = 0.f;
+          if (epi.bias && colh + hlf * 8 < N) {
+            unpack8(ldg_cached(epi.bias + colh + hlf * 8), bh);
+            unpack8(ldg_cached(epi.bias + colg + hlf * 8), bg);
           }
-          *reinterpret_cast<uint4*>(epi.out + (size_t)orow * epi.ldo + col) = val;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            // the reference rounds the projection to fp16 before h * gelu(g) (GEGLU.forward on an fp16 Linear output)
+            const float hval = __half2float(__float2half_rn(__uint_as_float(rh[hlf * 8 + i]) + bh[i]));
+            const float gval = __half2float(__float2half_rn(__uint_as_float(rgt[hlf * 8 + i]) + bg[i]));
+            v[hlf * 8 + i] = hval * gelu_erf_f(gval);
+          }
         }
+        epi_store16(epi, v, row, blockIdx.x * HB + cc * 16, M, n_out, row_ok && (colh < N));
       }
     }
     tc_fence_before();
