@@ -98,6 +98,9 @@ int l2d_nhwc_to_nchw(const void* x, const void* residual_nchw, void* y, int n_im
 int l2d_gemm(const void* a, int64_t lda, const void* w, void* out, int64_t ldo, int m, int n, int k,
              const void* bias, const void* rowgroup_bias, int rows_per_group, const void* residual,
              int64_t ldr, int act, void* stream);
+/* Developer hook: when non-NULL, every GEMM CTA writes 8 clock64() stamps (start, setup done, first stage landed,
+ * last MMA issued, accumulator ready, epilogue done, all warps joined, unused) to timeline[cta*8 ..]; NULL disables. */
+void l2d_gemm_set_debug(void* timeline);
 /* Implicit-GEMM 3x3 convolution, pad 1, stride 1 (no im2col matrix): x [N,h,w,Cin] channels-last contiguous,
  * weight [Cout, 9*Cin] with columns ordered (tap = ky*3+kx, cin), out rows = pixels (n*h*w + y*w + x), `ldo` elements
  * per row.  Epilogue as l2d_gemm (rowgroup_bias [N, Cout] is per image).  Needs Cin % 64 == 0 and h, w whose

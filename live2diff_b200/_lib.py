@@ -51,6 +51,7 @@ SIGNATURES = {
     "l2d_gemm": (i32, [vp, i64, vp, vp, i64, i32, i32, i32, vp, vp, i32, vp, i64, i32, vp]),
     "l2d_conv3x3": (i32, [vp, i32, i32, i32, i32, vp, vp, i64, i32, vp, vp, vp, i64, i32, vp]),
     "l2d_gemm_tile_n": (i32, [i32, i32, i32]),
+    "l2d_gemm_set_debug": (None, [vp]),
     "l2d_geglu_interleave": (i32, [vp, vp, vp, vp, i32, i32, i32, vp]),
     "l2d_small_linear": (i32, [vp, vp, vp, vp, i32, i32, i32, i32, i32, vp]),
     "l2d_timestep_embedding": (i32, [vp, vp, i32, i32, vp]),

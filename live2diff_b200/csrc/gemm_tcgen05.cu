@@ -6,18 +6,19 @@
 // 1x1 convs (attention.py:62,87; resnet.py:227) and, fed by the im2col kernels, the 3x3 convs of
 // resnet.py:57-65,92,141,194,214.
 //
-// Structure (one 128 x BN output tile per CTA, 192 threads):
+// Structure (one 128 x BN output tile per CTA, 320 threads):
 //   warp 0   : TMA producer  -- cp.async.bulk.tensor 2D loads of A[128x64] and W[BNx64] tiles
 //              (128B swizzle) into a STAGES-deep shared-memory ring, mbarrier complete_tx
 //   warp 1   : TMEM allocator + MMA issuer -- one elected lane issues tcgen05.mma.cta_group::1
 //              .kind::f16 (M=128, N=BN, K=16) from shared-memory descriptors; tcgen05.commit
 //              releases ring slots and finally signals the accumulator-ready barrier
-//   warps 2-5: epilogue -- tcgen05.ld 32x32b TMEM -> registers, fused bias / per-image bias (temb) /
+//   warps 2-9: epilogue -- tcgen05.ld 32x32b TMEM -> registers, fused bias / per-image bias (temb) /
 //              SiLU / GEGLU / residual, 128-bit global stores
 // Partial tiles rely on TMA out-of-bounds zero fill (loads) and predicated stores.
 #include <cuda.h>
 
 #include <algorithm>
+#include <cstdlib>
 #include <mutex>
 #include <unordered_map>
 
@@ -158,6 +159,7 @@ struct GemmEpilogue {
   float* ws;
   int64_t ws_ld;
   int64_t ws_slice;   // elements per split slice = M_pad * ws_ld
+  long long* dbg;     // optional per-CTA timeline (8 clock64 stamps per CTA), see l2d_gemm_set_debug
 };
 
 template <int BN>
@@ -167,39 +169,20 @@ struct GemmSmem {
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
 };
 
-// v: activated accumulator values for output columns col0 .. col0+15 of `row`; res0/res1: the residual's 2 x 8
-// columns, already in registers (prefetched while the main loop ran) or loaded here when `res_loaded` is false
-__device__ __forceinline__ void epi_store16(const GemmEpilogue& e, float (&v)[16], int row, int col0, int M, int n_out,
-                                            bool row_ok, bool res_loaded = false, uint4 res0 = make_uint4(0, 0, 0, 0),
-                                            uint4 res1 = make_uint4(0, 0, 0, 0)) {
-  if (!row_ok) return;
-#pragma unroll
-  for (int hlf = 0; hlf < 2; ++hlf) {
-    const int col = col0 + hlf * 8;
-    if (col < n_out) {
-      float o[8];
-#pragma unroll
-      for (int i = 0; i < 8; ++i) o[i] = v[hlf * 8 + i];
-      if (e.residual) {
-        float r[8];
-        // plain (coherent) load: the residual may alias `out` (in-place  h += f(h))
-        const uint4 rr = res_loaded ? (hlf ? res1 : res0)
-                                    : *reinterpret_cast<const uint4*>(e.residual + (size_t)row * e.ldr + col);
-        unpack8(rr, r);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) o[i] += r[i];
-      }
-      *reinterpret_cast<uint4*>(e.out + (size_t)row * e.ldo + col) = pack8(o);
-    }
-  }
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
 
+// Persistent kernel: grid = min(#tiles, #SMs); every CTA walks tiles t = blockIdx.x, +gridDim.x, ... (N-tile fastest,
+// then M-tile, then K-split).  The smem operand ring runs continuously across tiles and the accumulator is
+// double-buffered in TMEM, so tile i's epilogue overlaps tile i+1's TMA loads and MMAs.
 template <int BN, int STAGES>
-__global__ void __launch_bounds__(192, 1)
+__global__ void __launch_bounds__(320, 1)
 gemm_f16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
-                        const GemmEpilogue epi, const ConvGeom cg, int M, int N, int K) {
+                        const GemmEpilogue epi, const ConvGeom cg, int M, int N, int K, int tiles_n, int tiles_m,
+                        int splits) {
   using S = GemmSmem<BN>;
-  constexpr uint32_t TMEM_COLS = BN <= 32 ? 32 : BN <= 64 ? 64 : BN <= 128 ? 128 : 256;
+  constexpr uint32_t TMEM_COLS = 2 * BN <= 128 ? 128 : 2 * BN <= 256 ? 256 : 512;   // two accumulator stages
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // 1024 B alignment is required by the 128B swizzle atom (8 rows x 128 B)
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -208,26 +191,41 @@ gemm_f16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * S::STAGE_BYTES);
   uint64_t* full_bar = bars;
   uint64_t* empty_bar = bars + STAGES;
-  uint64_t* tmem_full_bar = bars + 2 * STAGES;
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 1);
+  uint64_t* tmem_full_bar = bars + 2 * STAGES;        // [2]
+  uint64_t* tmem_empty_bar = bars + 2 * STAGES + 2;   // [2]
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int n0 = blockIdx.x * BN;
-  const int m0 = blockIdx.y * BM;
-  // conv mode: this CTA's output tile = images [cn0, cn0+bn) x rows [ch0, ch0+bh) x columns [cw0, cw0+bw)
-  int cn0 = 0, ch0 = 0, cw0 = 0;
-  if (cg.enabled) {
-    const int t = blockIdx.y;
-    cw0 = (t % cg.tiles_w) * cg.bw;
-    ch0 = ((t / cg.tiles_w) % cg.tiles_h) * cg.bh;
-    cn0 = (t / (cg.tiles_w * cg.tiles_h)) * cg.bn;
-  }
   const int total_kb = (K + BK - 1) / BK;
-  const int kb_per = (total_kb + (int)gridDim.z - 1) / (int)gridDim.z;
-  const int kb_begin = (int)blockIdx.z * kb_per;
-  const int num_kb = max(0, min(total_kb, kb_begin + kb_per) - kb_begin);   // k-blocks of this split (may be 0)
+  const int kb_per = (total_kb + splits - 1) / splits;
+  const int total_tiles = tiles_n * tiles_m * splits;
+  const int my_tiles = ((int)blockIdx.x < total_tiles) ? (total_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
 
+  struct Tile {
+    int n0, m0, mt, z, kb_begin, num_kb, cn0, ch0, cw0;
+  };
+  auto decode = [&](int i) {
+    const int t = (int)blockIdx.x + i * (int)gridDim.x;
+    Tile tl;
+    tl.z = t / (tiles_n * tiles_m);
+    const int rem = t - tl.z * (tiles_n * tiles_m);
+    tl.mt = rem / tiles_n;
+    tl.n0 = (rem - tl.mt * tiles_n) * BN;
+    tl.m0 = tl.mt * BM;
+    tl.kb_begin = tl.z * kb_per;
+    tl.num_kb = max(0, min(total_kb, tl.kb_begin + kb_per) - tl.kb_begin);
+    tl.cn0 = tl.ch0 = tl.cw0 = 0;
+    if (cg.enabled) {   // output tile = images [cn0, cn0+bn) x rows [ch0, ch0+bh) x columns [cw0, cw0+bw)
+      tl.cw0 = (tl.mt % cg.tiles_w) * cg.bw;
+      tl.ch0 = ((tl.mt / cg.tiles_w) % cg.tiles_h) * cg.bh;
+      tl.cn0 = (tl.mt / (cg.tiles_w * cg.tiles_h)) * cg.bn;
+    }
+    return tl;
+  };
+
+  long long* dbg = epi.dbg ? epi.dbg + (size_t)blockIdx.x * 8 : nullptr;   // timeline of this CTA's first tile
+  if (dbg && threadIdx.x == 0) dbg[0] = clock64();
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmap_a);
     prefetch_tmap(&tmap_b);
@@ -235,7 +233,10 @@ gemm_f16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid
       mbar_init(smem_u32(&full_bar[s]), 1);
       mbar_init(smem_u32(&empty_bar[s]), 1);
     }
-    mbar_init(smem_u32(tmem_full_bar), 1);
+    for (int a2 = 0; a2 < 2; ++a2) {
+      mbar_init(smem_u32(&tmem_full_bar[a2]), 1);
+      mbar_init(smem_u32(&tmem_empty_bar[a2]), 8);   // one arrival per epilogue warp
+    }
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(smem_u32(tmem_ptr_smem), TMEM_COLS);
@@ -243,168 +244,247 @@ gemm_f16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
+  if (dbg && threadIdx.x == 0) dbg[1] = clock64();   // setup (barrier init, TMEM alloc) done
 
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
-      for (int kb = 0; kb < num_kb; ++kb) {
-        const int s = kb % STAGES;
-        const uint32_t ph = (uint32_t)(kb / STAGES) & 1u;
-        mbar_wait(smem_u32(&empty_bar[s]), ph ^ 1u);
-        const uint32_t fb = smem_u32(&full_bar[s]);
-        mbar_expect_tx(fb, S::STAGE_BYTES);
-        if (cg.enabled) {
-          const int kk = kb_begin + kb, tap = kk / cg.cin_blocks, cb = kk - tap * cg.cin_blocks;
-          tma_load_4d(smem_u32(smem_a + s * S::A_BYTES), &tmap_a, fb, cb * BK, cw0 + tap % 3 - 1, ch0 + tap / 3 - 1, cn0);
-        } else {
-          tma_load_2d(smem_u32(smem_a + s * S::A_BYTES), &tmap_a, fb, (kb_begin + kb) * BK, m0);
+      int it = 0;   // running k-block counter: the operand ring never drains between tiles
+      for (int i = 0; i < my_tiles; ++i) {
+        const Tile tl = decode(i);
+        for (int kb = 0; kb < tl.num_kb; ++kb, ++it) {
+          const int s = it % STAGES;
+          const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
+          mbar_wait(smem_u32(&empty_bar[s]), ph ^ 1u);
+          const uint32_t fb = smem_u32(&full_bar[s]);
+          mbar_expect_tx(fb, S::STAGE_BYTES);
+          const int kk = tl.kb_begin + kb;
+          if (cg.enabled) {
+            const int tap = kk / cg.cin_blocks, cb = kk - tap * cg.cin_blocks;
+            tma_load_4d(smem_u32(smem_a + s * S::A_BYTES), &tmap_a, fb, cb * BK, tl.cw0 + tap % 3 - 1, tl.ch0 + tap / 3 - 1,
+                        tl.cn0);
+          } else {
+            tma_load_2d(smem_u32(smem_a + s * S::A_BYTES), &tmap_a, fb, kk * BK, tl.m0);
+          }
+          tma_load_2d(smem_u32(smem_b + s * S::B_BYTES), &tmap_b, fb, kk * BK, tl.n0);
         }
-        tma_load_2d(smem_u32(smem_b + s * S::B_BYTES), &tmap_b, fb, (kb_begin + kb) * BK, n0);
       }
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
     if (lane == 0) {
       constexpr uint32_t idesc = make_idesc(BN);
-      for (int kb = 0; kb < num_kb; ++kb) {
-        const int s = kb % STAGES;
-        const uint32_t ph = (uint32_t)(kb / STAGES) & 1u;
-        mbar_wait(smem_u32(&full_bar[s]), ph);
+      int it = 0;
+      for (int i = 0; i < my_tiles; ++i) {
+        const Tile tl = decode(i);
+        const int as = i & 1;
+        // the epilogue must have drained this accumulator stage (tile i-2)
+        mbar_wait(smem_u32(&tmem_empty_bar[as]), ((uint32_t)(i >> 1) & 1u) ^ 1u);
         tc_fence_after();
-        const uint64_t da = make_sw128_desc(smem_u32(smem_a + s * S::A_BYTES));
-        const uint64_t db = make_sw128_desc(smem_u32(smem_b + s * S::B_BYTES));
+        const uint32_t tacc = tmem_base + (uint32_t)(as * BN);
+        for (int kb = 0; kb < tl.num_kb; ++kb, ++it) {
+          const int s = it % STAGES;
+          const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
+          mbar_wait(smem_u32(&full_bar[s]), ph);
+          if (dbg && it == 0) dbg[2] = clock64();        // first operand stage landed
+          tc_fence_after();
+          const uint64_t da = make_sw128_desc(smem_u32(smem_a + s * S::A_BYTES));
+          const uint64_t db = make_sw128_desc(smem_u32(smem_b + s * S::B_BYTES));
 #pragma unroll
-        for (int k = 0; k < BK / 16; ++k) {
-          // advance 16 elements (32 B) along K inside the swizzle atom: +2 in the (>>4) address field
-          umma_f16(tmem_base, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (kb | k) != 0);
+          for (int k = 0; k < BK / 16; ++k) {
+            // advance 16 elements (32 B) along K inside the swizzle atom: +2 in the (>>4) address field
+            umma_f16(tacc, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (kb | k) != 0);
+          }
+          umma_commit(smem_u32(&empty_bar[s]));  // slot free once these MMAs have read it
         }
-        umma_commit(smem_u32(&empty_bar[s]));  // slot free once these MMAs have read it
+        umma_commit(smem_u32(&tmem_full_bar[as]));   // accumulator complete (fires immediately when num_kb == 0)
+        if (dbg && i == 0) dbg[3] = clock64();        // last MMA of the first tile issued
       }
-      umma_commit(smem_u32(tmem_full_bar));    // accumulator complete (fires immediately when num_kb == 0)
     }
   } else {
-    // ===================== epilogue (warps 2..5) =====================
-    const int q = warp & 3;  // TMEM lane quarter this warp may access
-    int row = m0 + q * 32 + lane;
-    bool row_ok = row < M;
-    if (cg.enabled) {   // tile row -> (image, y, x) -> pixel index
-      const int r = q * 32 + lane;
-      const int iw = r % cg.bw, ih = (r / cg.bw) % cg.bh, in = r / (cg.bw * cg.bh);
-      row_ok = cn0 + in < cg.N;
-      row = ((cn0 + in) * cg.H + ch0 + ih) * cg.W + cw0 + iw;
-    }
-    // the epilogue warps are idle during the main loop: fetch this row's residual tile now so its latency is
-    // hidden behind the MMAs instead of being paid once per 16-column chunk
-    uint4 res[BN / 8];
-    const bool prefetch_res = epi.residual != nullptr && gridDim.z == 1 && epi.act != L2D_ACT_GEGLU;
-    if (prefetch_res) {
-#pragma unroll
-      for (int i = 0; i < BN / 8; ++i) {
-        res[i] = make_uint4(0, 0, 0, 0);
-        if (row_ok && n0 + i * 8 < N) res[i] = *reinterpret_cast<const uint4*>(epi.residual + (size_t)row * epi.ldr + n0 + i * 8);
+    // ===================== epilogue (warps 2..9) =====================
+    // 8 warps: warp w may touch TMEM lanes 32*(w%4)..+31 only, so two warps share each lane quarter and split the
+    // tile's columns (h = 0: first half, h = 1: second half).
+    const int q = warp & 3;             // TMEM lane quarter
+    const int h = (warp - 2) >> 2;      // column half handled by this warp
+    constexpr int NCH = BN / 16;        // 16-column chunks of the tile
+    const bool geglu = epi.act == L2D_ACT_GEGLU;
+    // chunk range of this warp (GEGLU: chunks of the value half; the matching gate chunk is cc + NCH/2)
+    const int nch_eff = geglu ? NCH / 2 : NCH;
+    const int cc_begin = h == 0 ? 0 : (nch_eff + 1) / 2;
+    const int cc_end = h == 0 ? (nch_eff + 1) / 2 : nch_eff;
+    for (int i = 0; i < my_tiles; ++i) {
+      const Tile tl = decode(i);
+      const int as = i & 1;
+      const int n0 = tl.n0;
+      int row = tl.m0 + q * 32 + lane;
+      bool row_ok = row < M;
+      if (cg.enabled) {   // tile row -> (image, y, x) -> pixel index
+        const int r = q * 32 + lane;
+        const int iw = r % cg.bw, ih = (r / cg.bw) % cg.bh, in = r / (cg.bw * cg.bh);
+        row_ok = tl.cn0 + in < cg.N;
+        row = ((tl.cn0 + in) * cg.H + tl.ch0 + ih) * cg.W + tl.cw0 + iw;
       }
-    }
-    mbar_wait(smem_u32(tmem_full_bar), 0);
-    tc_fence_after();
-    const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
-    const __half* rg = (epi.rowgroup_bias && row_ok)
-                           ? epi.rowgroup_bias + (size_t)(row / epi.rows_per_group) * epi.rg_ld : nullptr;
-    // bias / per-image bias / activation / residual / fp16 store of 16 consecutive output columns
-    auto finish16 = [&](float (&v)[16], int cc, bool res_loaded = false, uint4 r0 = make_uint4(0, 0, 0, 0),
-                        uint4 r1 = make_uint4(0, 0, 0, 0)) {
-      const int col0 = n0 + cc * 16;
+      const bool use_res = epi.residual != nullptr && splits == 1 && !geglu && row_ok;
+      const __half* res_ptr = use_res ? epi.residual + (size_t)row * epi.ldr + n0 : nullptr;
+      const __half* rg_ptr = (epi.rowgroup_bias && row_ok)
+                                 ? epi.rowgroup_bias + (size_t)(row / epi.rows_per_group) * epi.rg_ld + n0 : nullptr;
+      const __half* bias_ptr = epi.bias ? epi.bias + n0 : nullptr;
+      // first chunk's residual is requested before the accumulator wait; each iteration requests the next one
+      uint4 res0 = make_uint4(0, 0, 0, 0), res1 = res0;
+      if (res_ptr && n0 + cc_begin * 16 < N) {
+        res0 = *reinterpret_cast<const uint4*>(res_ptr + cc_begin * 16);          // plain loads: may alias `out`
+        if (n0 + cc_begin * 16 + 8 < N) res1 = *reinterpret_cast<const uint4*>(res_ptr + cc_begin * 16 + 8);
+      }
+      mbar_wait(smem_u32(&tmem_full_bar[as]), (uint32_t)(i >> 1) & 1u);
+      if (dbg && i == 0 && threadIdx.x == 64) dbg[4] = clock64();   // accumulator ready
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN);
+      if (splits > 1) {
+        // ---- split-K: store this split's fp32 partial tile (zeros when the split owns no k-blocks); slices are
+        //      indexed by output row and summed by splitk_finish_kernel ----
+        float* wrow = epi.ws + (size_t)tl.z * epi.ws_slice + (size_t)row * epi.ws_ld + n0;
+#pragma unroll 1
+        for (int cc = cc_begin; cc < cc_end; ++cc) {
+          uint32_t r[16];
+          if (tl.num_kb > 0) {
+            tmem_ld16(taddr + cc * 16, r);
+            tmem_ld_wait();
+          } else {
 #pragma unroll
-      for (int hlf = 0; hlf < 2; ++hlf) {
-        const int col = col0 + hlf * 8;
-        if (col < N) {
-          if (epi.bias) {
-            float b[8];
-            unpack8(ldg_cached(epi.bias + col), b);
-#pragma unroll
-            for (int i = 0; i < 8; ++i) v[hlf * 8 + i] += b[i];
+            for (int e = 0; e < 16; ++e) r[e] = 0u;
           }
-          if (rg) {
-            float b[8];
-            unpack8(ldg_cached(rg + col), b);
+          if (row_ok) {
 #pragma unroll
-            for (int i = 0; i < 8; ++i) v[hlf * 8 + i] += b[i];
+            for (int q4 = 0; q4 < 4; ++q4)
+              *reinterpret_cast<uint4*>(wrow + cc * 16 + q4 * 4) = make_uint4(r[q4 * 4], r[q4 * 4 + 1], r[q4 * 4 + 2], r[q4 * 4 + 3]);
           }
         }
-      }
-      if (epi.act == L2D_ACT_SILU) {
-#pragma unroll
-        for (int i = 0; i < 16; ++i) v[i] = silu_f(v[i]);
-      }
-      epi_store16(epi, v, row, col0, M, N, row_ok, res_loaded, r0, r1);
-    };
-    if (gridDim.z > 1) {
-      // ---- split-K: store this split's fp32 partial tile (zeros when the split owns no k-blocks) ----
-      // (conv mode: `row` is already the pixel index; the finish kernel reads the slices by output row)
-      float* wrow = epi.ws + (size_t)blockIdx.z * epi.ws_slice + (size_t)row * epi.ws_ld + n0;
+      } else if (!geglu) {
+        __half* out_ptr = epi.out + (size_t)row * epi.ldo + n0;
 #pragma unroll 1
-      for (int cc = 0; cc < BN / 16; ++cc) {
-        uint32_t r[16];
-        if (num_kb > 0) {
-          tmem_ld16(taddr + cc * 16, r);
+        for (int cc = cc_begin; cc < cc_end; ++cc) {
+          const int c0 = cc * 16;                        // column offset inside the tile
+          uint32_t r[16];
+          tmem_ld16(taddr + c0, r);
+          // request the next chunk's residual while the TMEM load is in flight
+          uint4 nres0 = make_uint4(0, 0, 0, 0), nres1 = nres0;
+          if (res_ptr && cc + 1 < cc_end && n0 + c0 + 16 < N) {
+            nres0 = *reinterpret_cast<const uint4*>(res_ptr + c0 + 16);
+            if (n0 + c0 + 24 < N) nres1 = *reinterpret_cast<const uint4*>(res_ptr + c0 + 24);
+          }
           tmem_ld_wait();
-        } else {
+          float v[16];
 #pragma unroll
-          for (int i = 0; i < 16; ++i) r[i] = 0u;
+          for (int e = 0; e < 16; ++e) v[e] = __uint_as_float(r[e]);
+          const bool lo_ok = n0 + c0 < N, hi_ok = n0 + c0 + 8 < N;
+          if (bias_ptr) {
+            float b[8];
+            if (lo_ok) {
+              unpack8(ldg_cached(bias_ptr + c0), b);
+#pragma unroll
+              for (int e = 0; e < 8; ++e) v[e] += b[e];
+            }
+            if (hi_ok) {
+              unpack8(ldg_cached(bias_ptr + c0 + 8), b);
+#pragma unroll
+              for (int e = 0; e < 8; ++e) v[8 + e] += b[e];
+            }
+          }
+          if (rg_ptr) {
+            float b[8];
+            if (lo_ok) {
+              unpack8(ldg_cached(rg_ptr + c0), b);
+#pragma unroll
+              for (int e = 0; e < 8; ++e) v[e] += b[e];
+            }
+            if (hi_ok) {
+              unpack8(ldg_cached(rg_ptr + c0 + 8), b);
+#pragma unroll
+              for (int e = 0; e < 8; ++e) v[8 + e] += b[e];
+            }
+          }
+          if (epi.act == L2D_ACT_SILU) {
+#pragma unroll
+            for (int e = 0; e < 16; ++e) v[e] = silu_f(v[e]);
+          }
+          if (use_res) {
+            float b[8];
+            unpack8(res0, b);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) v[e] += b[e];
+            unpack8(res1, b);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) v[8 + e] += b[e];
+          }
+          if (row_ok) {
+            float lo[8], hi[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+              lo[e] = v[e];
+              hi[e] = v[8 + e];
+            }
+            if (lo_ok) *reinterpret_cast<uint4*>(out_ptr + c0) = pack8(lo);
+            if (hi_ok) *reinterpret_cast<uint4*>(out_ptr + c0 + 8) = pack8(hi);
+          }
+          res0 = nres0;
+          res1 = nres1;
         }
-        if (row_ok) {
-#pragma unroll
-          for (int q4 = 0; q4 < 4; ++q4)
-            *reinterpret_cast<uint4*>(wrow + cc * 16 + q4 * 4) = make_uint4(r[q4 * 4], r[q4 * 4 + 1], r[q4 * 4 + 2], r[q4 * 4 + 3]);
-        }
-      }
-    } else if (epi.act != L2D_ACT_GEGLU) {
-#pragma unroll
-      for (int cc = 0; cc < BN / 16; ++cc) {
-        uint32_t r[16];
-        tmem_ld16(taddr + cc * 16, r);
-        tmem_ld_wait();
-        float v[16];
-#pragma unroll
-        for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
-        finish16(v, cc, prefetch_res, res[cc * 2], res[cc * 2 + 1]);
-      }
-    } else {
-      // GEGLU: tile columns [0,BN/2) = value half, [BN/2,BN) = matching gate half (weights interleaved
-      // by l2d_geglu_interleave); output columns blockIdx.x*BN/2 + ...
-      constexpr int HB = BN / 2;
-      const int n_out = N / 2;
+      } else {
+        // GEGLU: tile columns [0,BN/2) = value half, [BN/2,BN) = matching gate half (weights interleaved by
+        // l2d_geglu_interleave); output columns (n0/2) + ...
+        constexpr int HB = BN / 2;
+        const int n_out = N / 2;
+        const int oc0 = n0 / 2;
+        __half* out_ptr = epi.out + (size_t)row * epi.ldo + oc0;
 #pragma unroll 1
-      for (int cc = 0; cc < HB / 16; ++cc) {
-        uint32_t rh[16], rgt[16];
-        tmem_ld16(taddr + cc * 16, rh);
-        tmem_ld16(taddr + HB + cc * 16, rgt);
-        tmem_ld_wait();
-        const int colh = n0 + cc * 16;       // column in the interleaved weight (value half)
-        const int colg = n0 + HB + cc * 16;  // gate half
-        float v[16];
+        for (int cc = cc_begin; cc < cc_end; ++cc) {
+          uint32_t rh[16], rgt[16];
+          tmem_ld16(taddr + cc * 16, rh);
+          tmem_ld16(taddr + HB + cc * 16, rgt);
+          tmem_ld_wait();
+          const int colh = n0 + cc * 16;       // column in the interleaved weight (value half)
+          float v[16];
 #pragma unroll
-        for (int hlf = 0; hlf < 2; ++hlf) {
-          float bh[8], bg[8];
+          for (int hlf = 0; hlf < 2; ++hlf) {
+            float bh[8], bg[8];
 #pragma unroll
-          for (int i = 0; i < 8; ++i) bh[i] = bg[i] = 0.f;
-          if (epi.bias && colh + hlf * 8 < N) {
-            unpack8(ldg_cached(epi.bias + colh + hlf * 8), bh);
-            unpack8(ldg_cached(epi.bias + colg + hlf * 8), bg);
+            for (int e = 0; e < 8; ++e) bh[e] = bg[e] = 0.f;
+            if (bias_ptr && colh + hlf * 8 < N) {
+              unpack8(ldg_cached(bias_ptr + cc * 16 + hlf * 8), bh);
+              unpack8(ldg_cached(bias_ptr + HB + cc * 16 + hlf * 8), bg);
+            }
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+              // the reference rounds the projection to fp16 before h * gelu(g) (GEGLU.forward on an fp16 Linear output)
+              const float hval = __half2float(__float2half_rn(__uint_as_float(rh[hlf * 8 + e]) + bh[e]));
+              const float gval = __half2float(__float2half_rn(__uint_as_float(rgt[hlf * 8 + e]) + bg[e]));
+              v[hlf * 8 + e] = hval * gelu_erf_f(gval);
+            }
           }
+          if (row_ok && colh < N) {
+            const int oc = oc0 + cc * 16;
+            float lo[8], hi[8];
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            // the reference rounds the projection to fp16 before h * gelu(g) (GEGLU.forward on an fp16 Linear output)
-            const float hval = __half2float(__float2half_rn(__uint_as_float(rh[hlf * 8 + i]) + bh[i]));
-            const float gval = __half2float(__float2half_rn(__uint_as_float(rgt[hlf * 8 + i]) + bg[i]));
-            v[hlf * 8 + i] = hval * gelu_erf_f(gval);
+            for (int e = 0; e < 8; ++e) {
+              lo[e] = v[e];
+              hi[e] = v[8 + e];
+            }
+            if (oc < n_out) *reinterpret_cast<uint4*>(out_ptr + cc * 16) = pack8(lo);
+            if (oc + 8 < n_out) *reinterpret_cast<uint4*>(out_ptr + cc * 16 + 8) = pack8(hi);
           }
         }
-        epi_store16(epi, v, row, blockIdx.x * HB + cc * 16, M, n_out, row_ok && (colh < N));
       }
+      // this warp has read everything it needs from accumulator stage `as`: hand it back to the MMA warp
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(&tmem_empty_bar[as]));
+      if (dbg && i == 0 && threadIdx.x == 64) dbg[5] = clock64();   // epilogue of the first tile done (warp 2)
     }
-    tc_fence_before();
   }
+  tc_fence_before();
   __syncthreads();
+  if (dbg && threadIdx.x == 0) dbg[6] = clock64();
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, TMEM_COLS);
@@ -599,6 +679,7 @@ bool conv3x3_implicit_supported(int n_img, int h, int w, int cin) {
 }
 
 static float* g_ws = nullptr;
+static long long* g_dbg = nullptr;
 
 static int ensure_splitk_workspace() {
   if (g_ws) return L2D_OK;
@@ -609,15 +690,17 @@ static int ensure_splitk_workspace() {
 template <int BN, int STAGES>
 static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmEpilogue& e, const ConvGeom& cg, int M,
                        int N, int K, int splits, int tiles_m, cudaStream_t st) {
-  constexpr size_t smem = (size_t)STAGES * GemmSmem<BN>::STAGE_BYTES + (2 * STAGES + 2) * 8 + 1024;
+  constexpr size_t smem = (size_t)STAGES * GemmSmem<BN>::STAGE_BYTES + (2 * STAGES + 6) * 8 + 1024;
   static bool configured = false;
   if (!configured) {
     L2D_CUDA(cudaFuncSetAttribute(gemm_f16_tcgen05_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)smem));
     configured = true;
   }
-  dim3 grid(ceil_div(N, BN), tiles_m, splits);
-  gemm_f16_tcgen05_kernel<BN, STAGES><<<grid, 192, smem, st>>>(ta, tb, e, cg, M, N, K);
+  const int tiles_n = ceil_div(N, BN);
+  const int total = tiles_n * tiles_m * splits;
+  const int grid = total < kNumSms ? total : kNumSms;
+  gemm_f16_tcgen05_kernel<BN, STAGES><<<grid, 320, smem, st>>>(ta, tb, e, cg, M, N, K, tiles_n, tiles_m, splits);
   L2D_LAUNCH_CHECK();
   return L2D_OK;
 }
@@ -631,7 +714,7 @@ static int gemm_dispatch(const CUtensorMap& ta, const __half* w, int64_t ldw, co
   int rc = get_tmap(w, n, k, ldw, bn, &tb);
   if (rc != L2D_OK) return rc;
   GemmEpilogue e{out, ldo, bias, rowgroup_bias, rg_ld, rows_per_group > 0 ? rows_per_group : 1, residual, ldr, act,
-                 nullptr, 0, 0};
+                 nullptr, 0, 0, g_dbg};
   if (plan.splits > 1) {
     rc = ensure_splitk_workspace();
     if (rc != L2D_OK) return rc;
@@ -698,6 +781,10 @@ int conv3x3_launch(const __half* x, int n_img, int h, int w_, int cin, const __h
 using namespace l2d;
 
 extern "C" int l2d_gemm_tile_n(int m, int n, int k) { return gemm_pick_tile_n(m, n, k); }
+
+extern "C" void l2d_gemm_set_debug(void* timeline) {
+  l2d::g_dbg = static_cast<long long*>(timeline);
+}
 
 extern "C" int l2d_conv3x3(const void* x, int n_img, int h, int w, int cin, const void* weight, void* out, int64_t ldo,
                            int cout, const void* bias, const void* rowgroup_bias, const void* residual, int64_t ldr,
