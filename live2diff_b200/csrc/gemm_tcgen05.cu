@@ -637,6 +637,11 @@ static GemmPlan gemm_plan(int m, int n, int k, bool allow_split, int force_bn) {
 
 int gemm_pick_tile_n(int m, int n, int k) { return gemm_plan(m, n, k, false, 0).bn; }
 
+// exported for the K1 tensor-core kernel (kv_attn_mma.cu): 2-D map, box [box_rows, 64 columns], 128B swizzle
+int get_tmap_2d(const void* ptr, int64_t rows, int64_t cols, int64_t ld, int box_rows, CUtensorMap* out) {
+  return get_tmap(ptr, rows, cols, ld, box_rows, out);
+}
+
 // channels-last activation [N,H,W,C] as a 4-D tensor map, box = [bn, bh, bw, 64 channels], 128B swizzle
 static int get_tmap_conv(const void* ptr, int N, int H, int W, int C, int bw, int bh, int bn, CUtensorMap* out) {
   static std::unordered_map<TmapKey, CUtensorMap, TmapKeyHash> cache;

@@ -274,6 +274,9 @@ kv_attn_kernel(const KvAttnParams p, const int n_slots, const int slot_bytes, co
 static int g_num_sms = 0;
 
 int kv_attn_launch(const KvAttnParams& p0, cudaStream_t stream) {
+  // window of 16 slots and 64-aligned channels (every level of the UNet at the default config): tensor-core
+  // formulation in kv_attn_mma.cu; other geometries (L = 4 / 32, unusual widths) take the scalar kernel below
+  if (kv_attn_mma_supported(p0)) return kv_attn_mma_launch(p0, stream);
   KvAttnParams p = p0;
   p.T = p.C / 8;
   p.hd8 = (p.C / p.heads) / 8;

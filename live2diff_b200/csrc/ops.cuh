@@ -25,6 +25,8 @@ struct KvAttnParams {
   float scale;
 };
 int kv_attn_launch(const KvAttnParams& p, cudaStream_t stream);
+bool kv_attn_mma_supported(const KvAttnParams& p);
+int kv_attn_mma_launch(const KvAttnParams& p, cudaStream_t stream);
 
 int groupnorm_launch(const __half* x1, int c1, const __half* x2, int c2, const __half* gamma, const __half* beta,
                      __half* y, float* ws, int n_img, int h, int w, int G, float eps, int silu, int mode, int stride,
