@@ -56,6 +56,10 @@ int l2d_kv_attn(const void* q, const void* k_new, const void* v_new, int64_t qkv
                 const int64_t* pe_idx, const int64_t* update_idx, void* out,
                 int n_rows, int hw, int window, int channels, int heads, void* stream);
 
+/* Developer hook: when non-NULL, every CTA of the (L == 16) K1 kernel writes cycles spent waiting for TMA data,
+ * appending/staging, computing, storing, and its tile count to timeline[cta*8 ..]; NULL disables. */
+void l2d_kv_attn_set_debug(void* timeline);
+
 /* ---------------------------------------------------------------------------------------------
  * Op-level kernels (row-major fp16 activations, "tokens x channels" = NHWC).
  * ------------------------------------------------------------------------------------------- */

@@ -41,6 +41,7 @@ SIGNATURES = {
     "l2d_last_error": (C.c_char_p, []),
     "l2d_launch_count": (i64, []),
     "l2d_kv_attn": (i32, [vp, vp, vp, i64, vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, vp]),
+    "l2d_kv_attn_set_debug": (None, [vp]),
     "l2d_layernorm": (i32, [vp, vp, vp, vp, i32, i32, f32, vp]),
     "l2d_groupnorm_workspace_bytes": (i64, [i32, i32]),
     "l2d_groupnorm": (i32, [vp, i32, vp, i32, vp, vp, vp, vp, i32, i32, i32, i32, f32, i32, i32, i32, vp]),

@@ -321,6 +321,9 @@ int kv_attn_launch(const KvAttnParams& p0, cudaStream_t stream) {
 
 }  // namespace l2d
 
+namespace l2d { void kv_attn_set_debug(long long* ptr); }
+extern "C" void l2d_kv_attn_set_debug(void* timeline) { l2d::kv_attn_set_debug(static_cast<long long*>(timeline)); }
+
 extern "C" int l2d_kv_attn(const void* q, const void* k_new, const void* v_new, int64_t qkv_ld, void* kv_cache,
                            const void* q_pe, const void* k_pe, const void* v_pe, const void* mask,
                            const int64_t* pe_idx, const int64_t* update_idx, void* out, int n_rows, int hw,

@@ -1,0 +1,41 @@
+"""Per-CTA phase breakdown of the K1 (L == 16) kernel via l2d_kv_attn_set_debug, plus isolated timing per level."""
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.abspath(os.path.join(os.path.dirname(__file__), "..")))
+from live2diff_b200 import _lib, ops  # noqa: E402
+
+dev = "cuda:0"
+lib = _lib.lib()
+for (n, hw, c) in [(2, 4096, 320), (2, 1024, 640), (2, 256, 1280), (2, 64, 1280)]:
+    L, heads = 16, 8
+    q, k, v = [torch.randn(n, hw, c, device=dev).half() for _ in range(3)]
+    caches = [torch.randn(n, 2, hw, L, c, device=dev).half() for _ in range(3)]     # rotate: no L2 reuse at level 0
+    pe = [torch.randn(L, c, device=dev).half() for _ in range(3)]
+    mask = torch.zeros(n, L, device=dev).half()
+    pi = torch.arange(L, device=dev).repeat(n, 1)
+    up = torch.tensor([9, 12][:n], device=dev)
+    for i in range(3):
+        ops.kv_attn(q, k, v, caches[i % 3], pe[0], pe[1], pe[2], mask, pi, up, heads)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(12):
+        ops.kv_attn(q, k, v, caches[i % 3], pe[0], pe[1], pe[2], mask, pi, up, heads)
+    e1.record()
+    torch.cuda.synchronize()
+    us = e0.elapsed_time(e1) / 12 * 1e3
+    gb = n * hw * c * (2 * L + 4) * 2 / 1e9
+    tl = torch.zeros(296, 8, dtype=torch.int64, device=dev)
+    lib.l2d_kv_attn_set_debug(tl.data_ptr())
+    ops.kv_attn(q, k, v, caches[0], pe[0], pe[1], pe[2], mask, pi, up, heads)
+    torch.cuda.synchronize()
+    lib.l2d_kv_attn_set_debug(0)
+    t = tl.cpu().double()
+    t = t[t[:, 4] > 0]
+    per = t[:, :4].sum(0) / t[:, 4].sum()
+    sub = t[:, 5:8].sum(0) / t[:, 4].sum()
+    print(f"N{n} hw{hw} C{c}: {us:7.1f} us  {gb / us * 1e6:7.0f} GB/s | per tile cycles: wait {per[0]:.0f} patch {per[1]:.0f} "
+          f"compute {per[2]:.0f} (qk {sub[0]:.0f} softmax {sub[1]:.0f} pv {sub[2]:.0f}) store {per[3]:.0f}  (tiles/CTA {float(t[:, 4].mean()):.1f})")
