@@ -1,17 +1,18 @@
-// K1, tensor-core formulation (window L == 16, C % 64 == 0, C <= 640, heads <= 8): same semantics as kv_attn.cu
+// K1, tensor-core formulation (window L == 16, C % 64 == 0, heads <= 8): same semantics as kv_attn.cu
 // (stream_motion_module.py:117-194) at a fraction of the issue slots per byte.
 //
 // Why: the scalar kernel needs ~2000 warp-instructions per 80 KB tile (fp16->fp32 converts + FMAs per element); with
-// the few warps an SM can hold next to a 160 KB ring that caps it near 25 % of HBM bandwidth (profiles/).  Here a
-// warp owns a PIXEL and one mma.sync.m16n8k16 evaluates 16 slots x 16 channels for all 8 heads at once (heads on the
-// N dimension through a block-diagonal q matrix; see the kernel comment).  K+pe / V+pe are formed on the A fragments
-// with HADD2, i.e. with the reference's fp16 rounding; P is rounded to fp16 for P.V like the fused SDPA kernels the
-// reference dispatches to.
+// the few warps an SM can hold next to a 160 KB ring that caps it near 25 % of HBM bandwidth (profiles/).  Here one
+// mma.sync.m16n8k16 evaluates 16 slots x 16 channels for all 8 heads at once (heads on the N dimension through a
+// block-diagonal q matrix; see the kernel comment).  K+pe / V+pe are formed on the A fragments with HADD2, i.e. with
+// the reference's fp16 rounding; P is rounded to fp16 for P.V like the fused SDPA kernels the reference dispatches to.
 //
-// Data movement: the cache [N,2,hw,L,C] viewed as a matrix [N*2*hw*L rows, C cols]; a tile of P pixels is
-// R = P*16 consecutive rows of the K plane and of the V plane, fetched as 64-column TMA boxes with the 128B swizzle
-// (cp.async.bulk.tensor.2d -> conflict-free ldmatrix) into a 2-stage ring, completion on mbarriers; the freshly
-// projected k/v/q of the next tile are prefetched into registers during the current tile's math.
+// Data movement: the cache [N,2,hw,L,C] viewed as a matrix [N*2*hw*L rows, C cols]; a tile is P pixels (P*C = 1280 at
+// the UNet's widths); its K plane and its V plane are each R = P*16 consecutive rows, fetched as 64-column TMA boxes
+// with the 128B swizzle (cp.async.bulk.tensor.2d -> conflict-free ldmatrix) into a ring of NB plane buffers.
+// Warp-specialised pipeline: warp 8 is the TMA producer (full/empty mbarriers per buffer); the 8 math warps are split
+// into P pixel groups of W = 8/P warps that only synchronise among themselves (named barriers), so groups drift apart
+// and overlap each other's latencies.  The freshly projected k/v/q of the next tile are prefetched into registers.
 // Precondition (as in the reference, whose cache is zero-initialised): masked slots hold finite values.
 #include <cuda.h>
 
@@ -29,6 +30,9 @@ __device__ __forceinline__ void km_mbar_init(uint32_t bar, uint32_t count) {
 }
 __device__ __forceinline__ void km_mbar_expect_tx(uint32_t bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void km_mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
 __device__ __forceinline__ void km_mbar_wait(uint32_t bar, uint32_t parity) {
   uint32_t done = 0, spins = 0;
@@ -55,207 +59,315 @@ __device__ __forceinline__ void km_tma_2d(uint32_t dst, const CUtensorMap* map, 
       ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1)
       : "memory");
 }
-// (not volatile / no memory clobber: within the compute phase the ring is read-only, and leaving the scheduler free
-// to interleave the independent per-pixel chains is what hides the ldmatrix -> HADD2 -> mma -> shuffle latencies)
+// named barrier among `count` threads (a pixel group, or the 8 math warps)
+__device__ __forceinline__ void km_bar(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
+// (volatile keeps the program order against the barriers in NVVM; ptxas schedules the loads freely inside a phase)
 __device__ __forceinline__ void km_ldsm(uint32_t addr, uint32_t (&r)[4]) {
-  asm("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
                : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
                : "r"(addr));
 }
 __device__ __forceinline__ void km_ldsm_t(uint32_t addr, uint32_t (&r)[4]) {
-  asm("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
                : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
                : "r"(addr));
 }
 __device__ __forceinline__ void km_mma(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
-  asm(
-      "mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+  asm("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
       : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
       : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
-__device__ __forceinline__ void km_st_pred(uint32_t addr, __half v, bool pred) {
-  asm volatile("{ .reg .pred p; setp.ne.b32 p, %2, 0; @p st.shared.b16 [%0], %1; }" ::"r"(addr),
-               "h"(*reinterpret_cast<const unsigned short*>(&v)), "r"((int)pred)
-               : "memory");
+__device__ __forceinline__ void km_mma0(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {   // C = 0
+  asm("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%10,%10,%10,%10};"
+      : "=f"(d[0]), "=f"(d[1]), "=f"(d[2]), "=f"(d[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1), "f"(0.f));
 }
 __device__ __forceinline__ uint32_t km_hadd2(uint32_t a, uint32_t b) { return h2_as_u32(__hadd2(u32_as_h2(a), u32_as_h2(b))); }
 
 constexpr int KM_L = 16;
-constexpr int KM_STAGES = 2;
+constexpr int KM_THREADS = 288;     // 8 math warps + the TMA warp
+constexpr int KM_OT = 20;           // bytes per channel row of the O^T staging (8 heads x fp16 + 4 pad: conflict-free gather)
 
-// swizzled byte offset of 16-byte chunk `chunk` (= channel / 8) of tile row `row` inside one plane of a stage:
+// swizzled byte offset of 16-byte chunk `chunk` (= channel / 8) of tile row `row` inside one plane:
 // 64-column blocks of R rows x 128 B, 128B swizzle = chunk-in-block XOR (row % 8)
 __device__ __forceinline__ uint32_t km_off(int row, int chunk, int R) {
   return (uint32_t)((chunk >> 3) * (R * 128) + row * 128 + (((chunk & 7) ^ (row & 7)) << 4));
 }
 
-// One warp per PIXEL, the 8 heads on the N = 8 dimension of the MMA:
+// Fragment addressing of the specialised kernels.  Warp `sub` of a pixel group takes k-steps ks = sub + W*i, i.e. the
+// 16-byte chunks c0 + 2*W*i with c0 = 2*sub + j (j = which half of the k-step the lane's ldmatrix row addresses), so the
+// offset of step i is a per-lane base plus a compile-time constant:
+//   W = 2: chunk = c0 + 4i  -> block i/2, chunk-in-block c0 (+4 for odd i: one xor on the swizzled chunk)
+//   W = 4: chunk = c0 + 8i  -> block i,   chunk-in-block c0
+//   W = 8: chunk = c0 + 16i -> block 2i + c0/8, chunk-in-block c0 % 8
+struct KmFrag {
+  uint32_t e, o;
+};
+template <int W>
+__device__ __forceinline__ KmFrag km_frag(int row, int c0, int R) {
+  KmFrag f;
+  const int r7 = row & 7;
+  if (W == 8) {
+    f.e = (uint32_t)((c0 >> 3) * (R * 128) + row * 128 + (((c0 & 7) ^ r7) << 4));
+    f.o = f.e;
+  } else {
+    f.e = (uint32_t)(row * 128 + ((c0 ^ r7) << 4));
+    f.o = (uint32_t)(row * 128 + (((c0 ^ r7) ^ 4) << 4));
+  }
+  return f;
+}
+template <int W>
+__device__ __forceinline__ uint32_t km_frag_off(const KmFrag& f, int i, int R) {
+  if (W == 2) return (uint32_t)((i >> 1) * (R * 128)) + ((i & 1) ? f.o : f.e);
+  if (W == 4) return (uint32_t)(i * (R * 128)) + f.e;
+  return (uint32_t)(2 * i * (R * 128)) + f.e;
+}
+
+// The 8 heads sit on the N = 8 dimension of the MMA:
 //   S[16 slots x 8 heads] = K~[16 x C] . Qblk[C x 8]     Qblk[c][h] = q~[c] if channel c belongs to head h else 0
 //   O^T[C x 8 heads]      = V~^T[C x 16] . P[16 x 8]      row c of O^T is read at column head(c)
-// so every B column does useful work, the softmax of all heads runs in one set of registers (scores of slot g /
-// g+8 and heads 2t / 2t+1 per lane; the reduction over slots is 3 xor-shuffles for all 8 heads at once), and one pixel
-// costs C/16 k-steps of (2 ldmatrix + 4 HADD2 + 1 mma) for the scores and again for P.V.
+// so every B column does useful work, the softmax of all heads runs in one set of registers (scores of slot g / g+8
+// and heads 2t / 2t+1 per lane; the reduction over slots is 3 xor-shuffles for all 8 heads at once), and one pixel
+// costs C/16 k-steps of (2 ldmatrix + 4 HADD2 + 1 mma) for the scores and again for P.V.  The k-steps of a pixel are
+// dealt round-robin to the W warps of its group; partial scores meet in shared memory.
 // PE: the row's K_pe[pi[j]] / V_pe[pi[j]] windows are staged once per row n in shared memory in the same swizzled
 // [16 x C] layout as a pixel's K / V window, so the PE fragments come from the same ldmatrix addresses.
-__global__ void __launch_bounds__(288, 1)
-kv_attn_mma_kernel(const __grid_constant__ CUtensorMap tmap, const KvAttnParams p, const int tiles_per_row, const int ncb,
-                   long long* dbg) {
+// O^T staging: after the scores the pixel's K window is dead; O^T rows (KM_OT bytes per channel) reuse it.
+// CT/PT: compile-time C and pixels per tile (0 = run-time geometry, any C <= 640); NB: plane buffers in the ring.
+template <int CT, int PT, int NB>
+__global__ void __launch_bounds__(KM_THREADS, 1)
+kv_attn_mma_kernel(const __grid_constant__ CUtensorMap tmap, const KvAttnParams p, const int tiles_per_row, long long* dbg) {
   extern __shared__ __align__(1024) uint8_t km_smem_raw[];
   // align by pointer arithmetic (an integer round trip would turn every later access into a generic LD/ST)
   uint8_t* smem = km_smem_raw + ((1024u - (km_smem_u32(km_smem_raw) & 1023u)) & 1023u);
-  const int C = p.C, P = p.P, R = P * KM_L, T = C >> 3;
-  const int hd = C / p.heads;
+  constexpr bool SPEC = CT != 0;
+  constexpr int WT = SPEC ? 8 / (PT ? PT : 1) : 1;
+  constexpr int NKW = SPEC ? (CT / 16) / WT : 1;             // k-steps per warp (10 at every UNet width)
+  const int C = SPEC ? CT : p.C, P = SPEC ? PT : p.P;
+  const int W = 8 / P, R = P * KM_L, T = C >> 3, ncb = C >> 6, nks = C >> 4;
   const uint32_t plane_bytes = (uint32_t)ncb * R * 128;          // K (or V) rows of one tile
-  const uint32_t stage_bytes = 2 * plane_bytes;
   const uint32_t pe_plane = (uint32_t)ncb * KM_L * 128;          // one [16 x C] PE window
   uint8_t* ring = smem;
-  uint8_t* pek = ring + (size_t)KM_STAGES * stage_bytes;         // K_pe[pi[j]] window of the current row n
+  uint8_t* pek = ring + (size_t)NB * plane_bytes;                // K_pe[pi[j]] window of the current row n
   uint8_t* pev = pek + pe_plane;
-  __half* s_q = reinterpret_cast<__half*>(pev + pe_plane);                            // [P][C]  q + Q_pe
-  __half* s_out = s_q + (size_t)P * C;                                                // [P][C]
-  float* s_mask = reinterpret_cast<float*>(s_out + (size_t)P * C);                    // [16]
-  int* s_pi = reinterpret_cast<int*>(s_mask + KM_L);                                  // [16]
-  uint8_t* s_head = reinterpret_cast<uint8_t*>(s_pi + KM_L);                          // [T] head of each 8-channel chunk
-  float* s_part = reinterpret_cast<float*>(s_head + 192);                             // [8 warps][32 lanes][4] partial scores
-  uint64_t* bars = reinterpret_cast<uint64_t*>(s_part + 8 * 32 * 4);   // 8-byte aligned: every size above is a multiple of 8
-  __shared__ int s_u;
+  __half* s_q = reinterpret_cast<__half*>(pev + pe_plane);       // [P][C]  q + Q_pe
+  __half* s_qpe = s_q + (size_t)P * C;                           // [C]     Q_pe[pi[u]] of the current row n
+  float* s_part = reinterpret_cast<float*>(s_qpe + C);           // [8 warps][32 lanes][4] partial scores
+  float* s_mask = s_part + 8 * 32 * 4;                           // [16]
+  int* s_pi = reinterpret_cast<int*>(s_mask + KM_L);             // [16]
+  int* s_misc = s_pi + KM_L;                                     // [0] = write slot u of the current row n
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_misc + 4);      // full[NB], empty[NB]
+  uint8_t* s_head = reinterpret_cast<uint8_t*>(bars + 2 * NB);   // [T] head of each 8-channel chunk
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int g = lane >> 2, t = lane & 3;
   const int total_tiles = tiles_per_row * p.n_rows;
-  const int my_tiles = ((int)blockIdx.x < total_tiles) ? (total_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
-  if (my_tiles == 0) return;
+  const int t_begin = (int)(((long long)total_tiles * blockIdx.x) / gridDim.x);
+  const int t_end = (int)(((long long)total_tiles * (blockIdx.x + 1)) / gridDim.x);
+  const int my_tiles = t_end - t_begin;                          // contiguous range: at most one row change per CTA
+  const uint32_t bar0 = km_smem_u32(bars);
+  auto full_bar = [&](int b) { return bar0 + 8u * b; };
+  auto empty_bar = [&](int b) { return bar0 + 8u * (NB + b); };
 
-  auto issue = [&](int i) {   // tile i of this CTA -> stage i % 2: ncb K boxes + ncb V boxes
-    if (i >= my_tiles) return;
-    const int tile = (int)blockIdx.x + i * (int)gridDim.x;
-    const int n = tile / tiles_per_row, p0 = (tile - n * tiles_per_row) * P;
-    const int st = i % KM_STAGES;
-    const uint32_t bar = km_smem_u32(&bars[st]);
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic accesses to the stage precede the refill
-    km_mbar_expect_tx(bar, stage_bytes);
-    const int krow = ((n * 2) * p.hw + p0) * KM_L, vrow = ((n * 2 + 1) * p.hw + p0) * KM_L;
-    const uint32_t base = km_smem_u32(ring + (size_t)st * stage_bytes);
-    for (int b2 = 0; b2 < ncb; ++b2) {
-      km_tma_2d(base + b2 * (R * 128), &tmap, bar, b2 * 64, krow);
-      km_tma_2d(base + plane_bytes + b2 * (R * 128), &tmap, bar, b2 * 64, vrow);
-    }
-  };
-  constexpr int PRODUCER_TID = 256;             // warp 8 never does math, so TMA issue does not delay it
   if (tid == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap) : "memory");
-    for (int s2 = 0; s2 < KM_STAGES; ++s2) km_mbar_init(km_smem_u32(&bars[s2]), 1);
+    for (int b = 0; b < NB; ++b) {
+      km_mbar_init(full_bar(b), 1);
+      km_mbar_init(empty_bar(b), 8);                             // one arrival per math warp
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    for (int i = 0; i < KM_STAGES; ++i) issue(i);
   }
-  for (int c = tid; c < T; c += blockDim.x) s_head[c] = (uint8_t)((c * 8) / hd);
+  {
+    const int hd = C / p.heads;
+    for (int c = tid; c < T; c += blockDim.x) s_head[c] = (uint8_t)((c * 8) / hd);
+  }
+  __syncthreads();
+  if (my_tiles <= 0) return;
 
-  // k/v/q chunk of the NEXT tile, requested one tile ahead (thread <-> chunk, as in the append phase)
-  uint4 pf_k = make_uint4(0, 0, 0, 0), pf_v = pf_k, pf_q = pf_k;
-  auto load_qkv = [&](int n, int p0, int np) {
-    if (tid < np * T) {
-      const int pl = tid / T, c = tid - pl * T;
-      const size_t row = (size_t)n * p.hw + p0 + pl;
-      pf_k = ldg_cached(p.k_new + row * p.ld + (size_t)c * 8);
-      pf_v = ldg_cached(p.v_new + row * p.ld + (size_t)c * 8);
-      pf_q = ldg_cached(p.q + row * p.ld + (size_t)c * 8);
+  if (warp == 8) {   // ---- TMA producer: planes in order K(0) V(0) K(1) V(1) ...; plane s lives in buffer s % NB ----
+    if (lane == 0) {
+      const int planes = 2 * my_tiles;
+      for (int s = 0; s < planes; ++s) {
+        const int b = s % NB, use = s / NB;
+        if (use > 0) km_mbar_wait(empty_bar(b), (uint32_t)(use - 1) & 1u);
+        const int tile = t_begin + (s >> 1);
+        const int n = tile / tiles_per_row, p0 = (tile - n * tiles_per_row) * P;
+        const int row0 = ((n * 2 + (s & 1)) * p.hw + p0) * KM_L;
+        km_mbar_expect_tx(full_bar(b), plane_bytes);
+        const uint32_t dst = km_smem_u32(ring + (size_t)b * plane_bytes);
+        for (int b2 = 0; b2 < ncb; ++b2) km_tma_2d(dst + b2 * (R * 128), &tmap, full_bar(b), b2 * 64, row0);
+      }
+    }
+    return;
+  }
+
+  // ---- math warps: group pl = warp / W owns pixel pl of every tile ----
+  const int pl = warp / W, sub = warp - pl * W;
+  const int GT = W * 32;                                         // threads of a pixel group
+  const int gbar = 1 + pl;                                       // the group's named barrier
+  const int cg = sub * 32 + lane;                                // the 16-byte chunk this thread appends / stages
+  const bool has_chunk = cg < T;
+  const int g = lane >> 2, t = lane & 3, mi = lane >> 3, r8 = lane & 7;
+  const int rowk = (mi & 1) * 8 + r8, jq = mi >> 1;              // K~ tile: matrices (slots lo/hi) x (channels lo/hi)
+  const int rowv = (mi >> 1) * 8 + r8, jv = mi & 1;              // V~^T tile (transposed load)
+  const int nkw = SPEC ? NKW : (nks - sub + W - 1) / W;
+
+  // per-lane addressing constants of the specialised kernels (see km_frag)
+  KmFrag fk, fpk, fv, fpv;
+  uint32_t ot_base = 0;                                          // O^T staging: row 16*ks + g, unit t
+  uint32_t qm[2 * NKW];                                          // Qblk column masks of this lane's head g
+  if constexpr (SPEC) {
+    constexpr int RT = PT * KM_L;
+    fk = km_frag<WT>(pl * KM_L + rowk, 2 * sub + jq, RT);
+    fpk = km_frag<WT>(rowk, 2 * sub + jq, KM_L);
+    fv = km_frag<WT>(pl * KM_L + rowv, 2 * sub + jv, RT);
+    fpv = km_frag<WT>(rowv, 2 * sub + jv, KM_L);
+    if (WT == 8) ot_base = (uint32_t)(pl * 2048 + (sub >> 2) * (RT * 128) + (16 * (sub & 3) + g) * KM_OT + 4 * t);
+    else ot_base = (uint32_t)(pl * 2048 + (16 * sub + g) * KM_OT + 4 * t);
+#pragma unroll
+    for (int i = 0; i < NKW; ++i) {
+      qm[2 * i] = (int)s_head[2 * (sub + WT * i)] == g ? 0xffffffffu : 0u;
+      qm[2 * i + 1] = (int)s_head[2 * (sub + WT * i) + 1] == g ? 0xffffffffu : 0u;
+    }
+  }
+  auto ot_off = [&](int i) -> uint32_t {                         // byte offset of O^T row (16*ks + g), unit t
+    if constexpr (SPEC) {
+      constexpr int RT = PT * KM_L;
+      if (WT == 2) return ot_base + (uint32_t)((i >> 1) * (RT * 128) + (i & 1) * (32 * KM_OT));
+      if (WT == 4) return ot_base + (uint32_t)(i * (RT * 128));
+      return ot_base + (uint32_t)(2 * i * (RT * 128));
+    } else {
+      const int c = 16 * (sub + W * i) + g;
+      return (uint32_t)((c >> 6) * (R * 128) + pl * 2048 + (c & 63) * KM_OT + 4 * t);
     }
   };
-  int cur_n = -1;
-  const int nks = C >> 4;                       // 16-channel k-steps (= d-tiles) per pixel
-  const int mi = lane >> 3, r8 = lane & 7;
 
-  long long d_wait = 0, d_patch = 0, d_comp = 0, d_store = 0, d_t0 = 0, d_t1 = 0, d_qk = 0, d_sm = 0, d_pv = 0;   // developer timeline (thread 0)
+  // k/v/q chunk of the NEXT tile, requested one tile ahead
+  uint4 pf_k = make_uint4(0, 0, 0, 0), pf_v = pf_k, pf_q = pf_k;
+  auto load_kq = [&](int tile2) {
+    const int n2 = tile2 / tiles_per_row, q0 = (tile2 - n2 * tiles_per_row) * P;
+    if (has_chunk && q0 + pl < p.hw) {
+      const size_t row = (size_t)n2 * p.hw + q0 + pl;
+      pf_k = ldg_cached(p.k_new + row * p.ld + (size_t)cg * 8);
+      pf_q = ldg_cached(p.q + row * p.ld + (size_t)cg * 8);
+    }
+  };
+  auto load_v = [&](int tile2) {
+    const int n2 = tile2 / tiles_per_row, q0 = (tile2 - n2 * tiles_per_row) * P;
+    if (has_chunk && q0 + pl < p.hw) {
+      const size_t row = (size_t)n2 * p.hw + q0 + pl;
+      pf_v = ldg_cached(p.v_new + row * p.ld + (size_t)cg * 8);
+    }
+  };
+  load_kq(t_begin);
+  load_v(t_begin);
+
+  int cur_n = -1;
+  const bool tl = dbg != nullptr && tid == 0;
+  long long d_wait = 0, d_patch = 0, d_qk = 0, d_mid = 0, d_pv = 0, d_store = 0, d_t = 0, d_wv = 0, d_bar2 = 0, d_gather = 0;   // developer timeline
+  auto stamp = [&](long long& acc) {
+    if (tl) {
+      const long long c = clock64();
+      acc += c - d_t;
+      d_t = c;
+    }
+  };
+
   for (int i = 0; i < my_tiles; ++i) {
-    const int tile = (int)blockIdx.x + i * (int)gridDim.x;
+    const int tile = t_begin + i;
     const int n = tile / tiles_per_row, p0 = (tile - n * tiles_per_row) * P;
-    const int np = min(P, p.hw - p0);
-    if (n != cur_n) {   // block-uniform: per-row schedule + PE windows
-      __syncthreads();
+    const bool active = p0 + pl < p.hw;
+    if (n != cur_n) {   // block-uniform: per-row schedule, Q_pe row and PE windows (all 8 math warps)
+      km_bar(15, 256);
       if (tid < KM_L) {
         s_pi[tid] = static_cast<int>(p.pe_idx[(size_t)n * KM_L + tid]);
         s_mask[tid] = __half2float(p.mask[(size_t)n * KM_L + tid]);
       }
-      if (tid == 0) s_u = static_cast<int>(p.update_idx[n]);
-      cur_n = n;
-      __syncthreads();
-      for (int idx = tid; idx < KM_L * T; idx += blockDim.x) {
+      if (tid == 0) s_misc[0] = static_cast<int>(p.update_idx[n]);
+      km_bar(15, 256);
+      const int u0 = s_misc[0];
+      for (int idx = tid; idx < KM_L * T; idx += 256) {
         const int j = idx / T, c = idx - j * T;
         const uint32_t off = km_off(j, c, KM_L);
         *reinterpret_cast<uint4*>(pek + off) = ldg_cached(p.k_pe + (size_t)s_pi[j] * p.pe_ld + (size_t)c * 8);
         *reinterpret_cast<uint4*>(pev + off) = ldg_cached(p.v_pe + (size_t)s_pi[j] * p.pe_ld + (size_t)c * 8);
       }
+      for (int c = tid; c < T; c += 256)
+        *reinterpret_cast<uint4*>(s_qpe + (size_t)c * 8) = ldg_cached(p.q_pe + (size_t)s_pi[u0] * p.pe_ld + (size_t)c * 8);
+      km_bar(15, 256);
+      cur_n = n;
     }
-    const int u = s_u;
-    const int st = i % KM_STAGES;
-    uint8_t* kplane = ring + (size_t)st * stage_bytes;
-    uint8_t* vplane = kplane + plane_bytes;
-    if (dbg && tid == 0) d_t0 = clock64();
-    km_mbar_wait(km_smem_u32(&bars[st]), (uint32_t)(i / KM_STAGES) & 1u);
-    if (dbg && tid == 0) { const long long c = clock64(); d_wait += c - d_t0; d_t0 = c; }
-
-    // ---- append (HBM + ring patch) and q~ staging: thread <-> one 16-byte chunk of one pixel.  The chunk's k/v/q were
-    //      requested during the previous tile's compute phase (registers pf_*), so no global latency is exposed here ----
-    if (i == 0) load_qkv(n, p0, np);
-    if (tid < np * T) {
-      const int pl = tid / T, c = tid - pl * T;
-      const uint4 qv = hadd8(pf_q, ldg_cached(p.q_pe + (size_t)s_pi[u] * p.pe_ld + (size_t)c * 8));   // q + Q_pe[pi[u]] -> fp16
-      __half* kdst = p.cache + ((((size_t)n * 2) * p.hw + p0 + pl) * KM_L + u) * C + (size_t)c * 8;
-      *reinterpret_cast<uint4*>(kdst) = pf_k;                                              // PE-free append (:117-119)
-      *reinterpret_cast<uint4*>(kdst + (size_t)p.hw * KM_L * C) = pf_v;
-      const uint32_t off = km_off(pl * KM_L + u, c, R);
-      *reinterpret_cast<uint4*>(kplane + off) = pf_k;                                      // the window sees the new slot
-      *reinterpret_cast<uint4*>(vplane + off) = pf_v;
-      *reinterpret_cast<uint4*>(s_q + (size_t)pl * C + (size_t)c * 8) = qv;
-    }
-    __syncthreads();
-    if (dbg && tid == 0) { const long long c = clock64(); d_patch += c - d_t0; d_t0 = c; }
-    if (i + 1 < my_tiles) {   // request the next tile's k/v/q now; they land while this tile is computed
-      const int tile2 = tile + (int)gridDim.x;
-      const int n2 = tile2 / tiles_per_row, q0 = (tile2 - n2 * tiles_per_row) * P;
-      load_qkv(n2, q0, min(P, p.hw - q0));
-    }
-
-    // ---- W = 8 / P warps per pixel: the k-steps of the score MMA chain and the d-tiles of P.V are dealt round-robin to
-    //      the pixel's warps (shorter dependent chains, more warps in flight); partial scores meet in shared memory ----
-    const int W = 8 / P;                         // P is a power of two <= 8
-    if (warp < 8 && warp / W < np) {
-      const int pl = warp / W, sub = warp - pl * W;
-      const uint32_t kbase = km_smem_u32(kplane), vbase = km_smem_u32(vplane);
-      const uint32_t pkb = km_smem_u32(pek), pvb = km_smem_u32(pev);
-      const __half* qrow = s_q + (size_t)pl * C;
-      // scores: rows = slots, columns = heads; two accumulators halve the dependent mma chain
-      float acc[4] = {0.f, 0.f, 0.f, 0.f}, acc2[4] = {0.f, 0.f, 0.f, 0.f};
-      const int rowk = (mi & 1) * 8 + r8;              // slot addressed by this lane for the K~ tile
-      auto qk_step = [&](int ks, float (&dst)[4]) {
-        uint32_t a[4], pe[4];
-        // matrices: (slots 0-7, ch 0-7) (slots 8-15, ch 0-7) (slots 0-7, ch 8-15) (slots 8-15, ch 8-15)
-        const int chunk = 2 * ks + (mi >> 1);
-        km_ldsm(kbase + km_off(pl * KM_L + rowk, chunk, R), a);
-        km_ldsm(pkb + km_off(rowk, chunk, KM_L), pe);
-#pragma unroll
-        for (int r = 0; r < 4; ++r) a[r] = km_hadd2(a[r], pe[r]);             // K + K_pe -> fp16
-        // B = Qblk: lane (g, t) holds rows (channels) ks*16 + 2t, +1 (b0) and + 8 (b1) of column (head) g
-        const uint32_t q0 = *reinterpret_cast<const uint32_t*>(qrow + ks * 16 + 2 * t);
-        const uint32_t q1 = *reinterpret_cast<const uint32_t*>(qrow + ks * 16 + 8 + 2 * t);
-        const uint32_t b0 = (int)s_head[2 * ks] == g ? q0 : 0u;
-        const uint32_t b1 = (int)s_head[2 * ks + 1] == g ? q1 : 0u;
-        km_mma(dst, a, b0, b1);
-      };
-      int ks = sub;
-#pragma unroll 2
-      for (; ks + W < nks; ks += 2 * W) {
-        qk_step(ks, acc);
-        qk_step(ks + W, acc2);
+    const int u = s_misc[0];
+    const int sK = 2 * i, sV = 2 * i + 1;
+    const int bK = sK % NB, bV = sV % NB;
+    uint8_t* kplane = ring + (size_t)bK * plane_bytes;
+    uint8_t* vplane = ring + (size_t)bV * plane_bytes;
+    if (tl) d_t = clock64();
+    km_mbar_wait(full_bar(bK), (uint32_t)(sK / NB) & 1u);
+    stamp(d_wait);
+    if (active) {
+      // ---- K append (HBM + window patch) and q~ staging: thread <-> one 16-byte chunk of the group's pixel ----
+      if (has_chunk) {
+        __half* kdst = p.cache + ((((size_t)n * 2) * p.hw + p0 + pl) * KM_L + u) * C + (size_t)cg * 8;
+        *reinterpret_cast<uint4*>(kdst) = pf_k;                                              // PE-free append (:117-119)
+        *reinterpret_cast<uint4*>(kplane + km_off(pl * KM_L + u, cg, R)) = pf_k;             // the window sees the new slot
+        *reinterpret_cast<uint4*>(s_q + (size_t)pl * C + (size_t)cg * 8) =
+            hadd8(pf_q, *reinterpret_cast<const uint4*>(s_qpe + (size_t)cg * 8));            // q + Q_pe[pi[u]] -> fp16
       }
-      if (ks < nks) qk_step(ks, acc);
+      km_bar(gbar, GT);
+      stamp(d_patch);
+      if (i + 1 < my_tiles) load_kq(tile + 1);
+
+      // ---- scores: rows = slots, columns = heads; two accumulators halve the dependent mma chain ----
+      float acc[4] = {0.f, 0.f, 0.f, 0.f}, acc2[4] = {0.f, 0.f, 0.f, 0.f};
+      {
+        const uint32_t kb = km_smem_u32(kplane), pkb = km_smem_u32(pek);
+        const __half* qrow = s_q + (size_t)pl * C + sub * 16 + 2 * t;
+        auto qk_step = [&](int ii, uint32_t koff, uint32_t pkoff, uint32_t m0, uint32_t m1, float (&dst)[4]) {
+          uint32_t a[4], pe[4];
+          // matrices: (slots 0-7, ch 0-7) (slots 8-15, ch 0-7) (slots 0-7, ch 8-15) (slots 8-15, ch 8-15)
+          km_ldsm(kb + koff, a);
+          km_ldsm(pkb + pkoff, pe);
+#pragma unroll
+          for (int r = 0; r < 4; ++r) a[r] = km_hadd2(a[r], pe[r]);             // K + K_pe -> fp16
+          // B = Qblk: lane (g, t) holds rows (channels) ks*16 + 2t, +1 (b0) and + 8 (b1) of column (head) g
+          const uint32_t q0 = *reinterpret_cast<const uint32_t*>(qrow + ii * (W * 16));
+          const uint32_t q1 = *reinterpret_cast<const uint32_t*>(qrow + ii * (W * 16) + 8);
+          km_mma(dst, a, q0 & m0, q1 & m1);
+        };
+        if constexpr (SPEC) {
+          constexpr int RT = PT * KM_L;
+#pragma unroll
+          for (int ii = 0; ii < NKW; ++ii) {
+            if (ii & 1) qk_step(ii, km_frag_off<WT>(fk, ii, RT), km_frag_off<WT>(fpk, ii, KM_L), qm[2 * ii], qm[2 * ii + 1], acc2);
+            else qk_step(ii, km_frag_off<WT>(fk, ii, RT), km_frag_off<WT>(fpk, ii, KM_L), qm[2 * ii], qm[2 * ii + 1], acc);
+          }
+        } else {
+#pragma unroll 2
+          for (int ii = 0; ii < nkw; ++ii) {
+            const int ks = sub + W * ii;
+            const uint32_t m0 = (int)s_head[2 * ks] == g ? 0xffffffffu : 0u;
+            const uint32_t m1 = (int)s_head[2 * ks + 1] == g ? 0xffffffffu : 0u;
+            qk_step(ii, km_off(pl * KM_L + rowk, 2 * ks + jq, R), km_off(rowk, 2 * ks + jq, KM_L), m0, m1, acc);
+          }
+        }
+      }
 #pragma unroll
       for (int r = 0; r < 4; ++r) acc[r] += acc2[r];
-      if (dbg && tid == 0) { const long long c = clock64(); d_qk += c - d_t0; d_t1 = c; }
+      if (W > 1) *reinterpret_cast<float4*>(s_part + ((size_t)warp * 32 + lane) * 4) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+      stamp(d_qk);
+
+      // ---- V append + patch (the V plane was requested one plane after K), then the group meets ----
+      km_mbar_wait(full_bar(bV), (uint32_t)(sV / NB) & 1u);
+      if (has_chunk) {
+        __half* vdst = p.cache + ((((size_t)n * 2 + 1) * p.hw + p0 + pl) * KM_L + u) * C + (size_t)cg * 8;
+        *reinterpret_cast<uint4*>(vdst) = pf_v;
+        *reinterpret_cast<uint4*>(vplane + km_off(pl * KM_L + u, cg, R)) = pf_v;
+      }
+      stamp(d_wv);
+      km_bar(gbar, GT);
+      stamp(d_bar2);
+      if (i + 1 < my_tiles) load_v(tile + 1);
       if (W > 1) {   // sum the partial scores of this pixel's warps
-        float* mine = s_part + ((size_t)warp * 32 + lane) * 4;
-        *reinterpret_cast<float4*>(mine) = make_float4(acc[0], acc[1], acc[2], acc[3]);
-        asm volatile("bar.sync %0, %1;" ::"r"(1 + pl), "r"(W * 32) : "memory");
         acc[0] = acc[1] = acc[2] = acc[3] = 0.f;
         for (int w2 = 0; w2 < W; ++w2) {
           const float4 v4 = *reinterpret_cast<const float4*>(s_part + ((size_t)(pl * W + w2) * 32 + lane) * 4);
@@ -280,7 +392,7 @@ kv_attn_mma_kernel(const __grid_constant__ CUtensorMap tmap, const KvAttnParams 
         suma += __shfl_xor_sync(0xffffffffu, suma, o);
         sumb += __shfl_xor_sync(0xffffffffu, sumb, o);
       }
-      const float inva = 1.f / suma, invb = 1.f / sumb;
+      const float inva = __frcp_rn(suma), invb = __frcp_rn(sumb);            // sums are in [1, 16]
       const float pr0 = s0 * inva, pr1 = s1 * invb, pr2 = s2 * inva, pr3 = s3 * invb;   // P[slot g | g+8][head 2t | 2t+1]
       // B = P[16 slots x 8 heads]: lane (g, t) needs head g, slots 2t, 2t+1 (b0) and 2t+8, 2t+9 (b1).
       // P[slot s][head h] lives in lane (s % 8) * 4 + h / 2, register (s / 8) * 2 + h % 2.
@@ -292,49 +404,89 @@ kv_attn_mma_kernel(const __grid_constant__ CUtensorMap tmap, const KvAttnParams 
       const bool odd = g & 1;
       const uint32_t pb0 = h2_as_u32(__floats2half2_rn(odd ? a1 : a0, odd ? b1f : b0f));   // slots 2t, 2t+1
       const uint32_t pb1 = h2_as_u32(__floats2half2_rn(odd ? c1 : c0, odd ? d1f : d0f));   // slots 2t+8, 2t+9
-      if (dbg && tid == 0) { const long long c = clock64(); d_sm += c - d_t1; d_t1 = c; }
-      // O^T: rows = channels, columns = heads; row c is taken at column head(c)
-      __half* orow = s_out + (size_t)pl * C;
-      const int rowv = (mi >> 1) * 8 + r8;             // slot addressed by this lane for the V~^T tile
-#pragma unroll 4
-      for (int dt = sub; dt < nks; dt += W) {
-        uint32_t a[4], pe[4];
-        // V~^T tile: matrices (slots 0-7, d 0-7) (slots 0-7, d 8-15) (slots 8-15, d 0-7) (slots 8-15, d 8-15), transposed
-        const int chunk = 2 * dt + (mi & 1);
-        km_ldsm_t(vbase + km_off(pl * KM_L + rowv, chunk, R), a);
-        km_ldsm_t(pvb + km_off(rowv, chunk, KM_L), pe);
+      stamp(d_mid);
+
+      // ---- O^T: rows = channels, columns = heads; every lane parks its two head columns of rows g and g + 8 in the
+      //      pixel's (dead) K window, the gather below picks column head(c) ----
+      {
+        const uint32_t vb = km_smem_u32(vplane), pvb = km_smem_u32(pev);
+        auto pv_step = [&](uint32_t voff, uint32_t pvoff, uint32_t ooff) {
+          uint32_t a[4], pe[4];
+          // V~^T tile: matrices (slots 0-7, d 0-7) (slots 0-7, d 8-15) (slots 8-15, d 0-7) (slots 8-15, d 8-15), transposed
+          km_ldsm_t(vb + voff, a);
+          km_ldsm_t(pvb + pvoff, pe);
 #pragma unroll
-        for (int r = 0; r < 4; ++r) a[r] = km_hadd2(a[r], pe[r]);             // V + V_pe -> fp16
-        float o[4] = {0.f, 0.f, 0.f, 0.f};
-        km_mma(o, a, pb0, pb1);
-        // lane (g, t): o[0] = O^T[dt*16+g][2t], o[1] = [..][2t+1], o[2] = O^T[dt*16+8+g][2t], o[3] = [..][2t+1]
-        const int h0 = s_head[2 * dt], h1 = s_head[2 * dt + 1];
-        const __half v0 = __float2half_rn((h0 & 1) ? o[1] : o[0]), v1 = __float2half_rn((h1 & 1) ? o[3] : o[2]);
-        km_st_pred(km_smem_u32(orow + dt * 16 + g), v0, (h0 >> 1) == t);       // predicated, no divergent branch
-        km_st_pred(km_smem_u32(orow + dt * 16 + 8 + g), v1, (h1 >> 1) == t);
+          for (int r = 0; r < 4; ++r) a[r] = km_hadd2(a[r], pe[r]);             // V + V_pe -> fp16
+          float o[4];
+          km_mma0(o, a, pb0, pb1);
+          // lane (g, t): o[0] = O^T[dt*16+g][2t], o[1] = [..][2t+1], o[2] = O^T[dt*16+8+g][2t], o[3] = [..][2t+1]
+          *reinterpret_cast<uint32_t*>(kplane + ooff) = h2_as_u32(__floats2half2_rn(o[0], o[1]));
+          *reinterpret_cast<uint32_t*>(kplane + ooff + 8 * KM_OT) = h2_as_u32(__floats2half2_rn(o[2], o[3]));
+        };
+        if constexpr (SPEC) {
+          constexpr int RT = PT * KM_L;
+#pragma unroll
+          for (int ii = 0; ii < NKW; ++ii) pv_step(km_frag_off<WT>(fv, ii, RT), km_frag_off<WT>(fpv, ii, KM_L), ot_off(ii));
+        } else {
+#pragma unroll 2
+          for (int ii = 0; ii < nkw; ++ii) {
+            const int dt = sub + W * ii;
+            pv_step(km_off(pl * KM_L + rowv, 2 * dt + jv, R), km_off(rowv, 2 * dt + jv, KM_L), ot_off(ii));
+          }
+        }
       }
-      if (dbg && tid == 0) { const long long c = clock64(); d_pv += c - d_t1; }
+      km_bar(gbar, GT);
+      stamp(d_pv);
+      // ---- gather column head(c) of O^T and store the pixel's output row (two channels per thread) ----
+      {
+        __half* orow = p.out + ((size_t)n * p.hw + p0 + pl) * C;
+        const uint8_t* otp = kplane + pl * 2048;
+        for (int cp = cg; 2 * cp < C; cp += GT) {
+          const int c = 2 * cp;
+          const uint8_t* src = otp + (c >> 6) * (R * 128) + (c & 63) * KM_OT + 2 * (int)s_head[c >> 3];
+          const uint32_t lo = *reinterpret_cast<const unsigned short*>(src);
+          const uint32_t hi = *reinterpret_cast<const unsigned short*>(src + KM_OT);
+          *reinterpret_cast<uint32_t*>(orow + c) = lo | (hi << 16);
+        }
+      }
+      stamp(d_gather);
+    } else {   // ragged last tile of a row: nothing to compute, but stay inside the pipeline depth (empty counts)
+      km_mbar_wait(full_bar(bV), (uint32_t)(sV / NB) & 1u);
+      if (i + 1 < my_tiles) {
+        load_kq(tile + 1);
+        load_v(tile + 1);
+      }
     }
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // ring patches precede the async refill
-    __syncthreads();
-    if (dbg && tid == 0) { const long long c = clock64(); d_comp += c - d_t0; d_t0 = c; }
-    if (tid == PRODUCER_TID) issue(i + KM_STAGES);                 // stage consumed: fetch the tile after next
-    // ---- coalesced 128-bit stores of the tile's output rows ----
-    for (int idx = tid; idx < np * T; idx += blockDim.x) {
-      const int pl = idx / T, c = idx - pl * T;
-      const size_t row = (size_t)n * p.hw + p0 + pl;
-      *reinterpret_cast<uint4*>(p.out + row * C + (size_t)c * 8) = *reinterpret_cast<const uint4*>(s_out + (size_t)pl * C + (size_t)c * 8);
+    // ---- release both planes: window patches and O^T staging (generic proxy) precede the async refill ----
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncwarp();
+    if (lane == 0) {
+      km_mbar_arrive(empty_bar(bK));
+      km_mbar_arrive(empty_bar(bV));
     }
-    if (dbg && tid == 0) d_store += clock64() - d_t0;
+    stamp(d_store);
   }
-  if (dbg && tid == 0) {
-    long long* o = dbg + (size_t)blockIdx.x * 8;
-    o[0] = d_wait; o[1] = d_patch; o[2] = d_comp; o[3] = d_store; o[4] = my_tiles; o[5] = d_qk; o[6] = d_sm; o[7] = d_pv;
+  if (tl) {
+    long long* o = dbg + (size_t)blockIdx.x * 16;
+    o[0] = d_wait; o[1] = d_patch; o[2] = d_qk; o[3] = d_wv; o[4] = my_tiles;
+    o[5] = d_bar2; o[6] = d_mid; o[7] = d_pv; o[8] = d_gather; o[9] = d_store;
   }
 }
 
 int g_km_sms = 0;
 long long* g_km_dbg = nullptr;
+
+template <int CT, int PT, int NB>
+int km_launch(const CUtensorMap& tm, const KvAttnParams& p, int tiles_per_row, int grid, size_t smem, cudaStream_t stream) {
+  static size_t configured = 0;
+  if (smem > configured) {
+    L2D_CUDA(cudaFuncSetAttribute(kv_attn_mma_kernel<CT, PT, NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = smem;
+  }
+  kv_attn_mma_kernel<CT, PT, NB><<<grid, KM_THREADS, smem, stream>>>(tm, p, tiles_per_row, g_km_dbg);
+  L2D_LAUNCH_CHECK();
+  return L2D_OK;
+}
 
 }  // namespace
 
@@ -342,9 +494,10 @@ void kv_attn_set_debug(long long* ptr) { g_km_dbg = ptr; }
 
 bool kv_attn_mma_supported(const KvAttnParams& p) {
   const int hd = p.heads > 0 ? p.C / p.heads : 0;
-  // C <= 640: ring (2 x 80 KB) + the row's two PE windows (<= 40 KB) fit one SM; wider levels use the scalar kernel
-  return p.L == KM_L && p.C % 64 == 0 && p.C <= 640 && p.heads >= 1 && p.heads <= 8 && p.C % p.heads == 0 &&
-         hd % 8 == 0 && p.pe_ld % 8 == 0;
+  // C <= 640: ring of 4 x 40 KB planes + the row's two PE windows (<= 40 KB); C = 1280: 3 planes + 80 KB of PE windows.
+  // Other widths / window lengths take the scalar kernel.
+  return p.L == KM_L && p.C % 64 == 0 && (p.C <= 640 || p.C == 1280) && p.heads >= 1 && p.heads <= 8 &&
+         p.C % p.heads == 0 && hd % 8 == 0 && p.pe_ld % 8 == 0;
 }
 
 int kv_attn_mma_launch(const KvAttnParams& p0, cudaStream_t stream) {
@@ -352,18 +505,17 @@ int kv_attn_mma_launch(const KvAttnParams& p0, cudaStream_t stream) {
   const int hd = p.C / p.heads;
   p.T = p.C / 8;
   p.hd8 = hd / 8;
-  int P = 1280 / p.C;                        // 80 KB of K+V per tile: 4 / 2 pixels at C = 320 / 640
-  if (P >= 8) P = 8; else if (P >= 4) P = 4; else if (P >= 2) P = 2; else P = 1;
-  if (P < 1) P = 1;
-  if (P > 8) P = 8;                          // 8 math warps, 8 / P of them per pixel
-  while (P > p.hw) P >>= 1;                  // (stays a power of two)
+  int P = 1280 / p.C;                        // 80 KB of K+V per tile: 4 / 2 / 1 pixels at C = 320 / 640 / 1280
+  if (P >= 8) P = 8; else if (P >= 4) P = 4; else if (P >= 2) P = 2; else P = 1;   // 8 math warps, 8 / P per pixel
+  while (P > p.hw) P >>= 1;
   if (P < 1) P = 1;
   p.P = P;
   p.scale = 1.0f / sqrtf((float)hd);
   const int ncb = p.C / 64;
-  const size_t stage_bytes = (size_t)2 * ncb * P * KM_L * 128;
-  const size_t smem = KM_STAGES * stage_bytes + (size_t)2 * ncb * KM_L * 128 + (size_t)2 * P * p.C * sizeof(__half) +
-                      KM_L * 8 + 192 + 8 * 32 * 16 + KM_STAGES * 8 + 64 + 1024;
+  const int NB = p.C == 1280 ? 3 : 4;
+  const size_t plane_bytes = (size_t)ncb * P * KM_L * 128;
+  const size_t smem = NB * plane_bytes + (size_t)2 * ncb * KM_L * 128 + (size_t)P * p.C * sizeof(__half) +
+                      (size_t)p.C * sizeof(__half) + 8 * 32 * 16 + KM_L * 8 + 16 + 2 * NB * 8 + 192 + 1024;
   if (smem > 227 * 1024) return fail(L2D_ERR_INVALID, "kv_attn(mma): tile does not fit in shared memory");
   CUtensorMap tm;
   const int64_t rows = (int64_t)p.n_rows * 2 * p.hw * KM_L;
@@ -374,17 +526,14 @@ int kv_attn_mma_launch(const KvAttnParams& p0, cudaStream_t stream) {
     L2D_CUDA(cudaGetDevice(&dev));
     L2D_CUDA(cudaDeviceGetAttribute(&g_km_sms, cudaDevAttrMultiProcessorCount, dev));
   }
-  static size_t configured = 0;
-  if (smem > configured) {
-    L2D_CUDA(cudaFuncSetAttribute(kv_attn_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = smem;
-  }
   const int tiles_per_row = ceil_div(p.hw, P);
   const int total = tiles_per_row * p.n_rows;
   const int grid = total < g_km_sms ? total : g_km_sms;
-  kv_attn_mma_kernel<<<grid, 288, smem, stream>>>(tm, p, tiles_per_row, ncb, g_km_dbg);
-  L2D_LAUNCH_CHECK();
-  return L2D_OK;
+  if (p.C == 320 && P == 4) return km_launch<320, 4, 4>(tm, p, tiles_per_row, grid, smem, stream);
+  if (p.C == 640 && P == 2) return km_launch<640, 2, 4>(tm, p, tiles_per_row, grid, smem, stream);
+  if (p.C == 1280 && P == 1) return km_launch<1280, 1, 3>(tm, p, tiles_per_row, grid, smem, stream);
+  if (p.C > 640) return fail(L2D_ERR_INVALID, "kv_attn(mma): unsupported geometry");
+  return km_launch<0, 0, 4>(tm, p, tiles_per_row, grid, smem, stream);
 }
 
 }  // namespace l2d

@@ -28,14 +28,16 @@ for (n, hw, c) in [(2, 4096, 320), (2, 1024, 640), (2, 256, 1280), (2, 64, 1280)
     torch.cuda.synchronize()
     us = e0.elapsed_time(e1) / 12 * 1e3
     gb = n * hw * c * (2 * L + 4) * 2 / 1e9
-    tl = torch.zeros(296, 8, dtype=torch.int64, device=dev)
+    tl = torch.zeros(296, 16, dtype=torch.int64, device=dev)
     lib.l2d_kv_attn_set_debug(tl.data_ptr())
     ops.kv_attn(q, k, v, caches[0], pe[0], pe[1], pe[2], mask, pi, up, heads)
     torch.cuda.synchronize()
     lib.l2d_kv_attn_set_debug(0)
     t = tl.cpu().double()
     t = t[t[:, 4] > 0]
-    per = t[:, :4].sum(0) / t[:, 4].sum()
-    sub = t[:, 5:8].sum(0) / t[:, 4].sum()
-    print(f"N{n} hw{hw} C{c}: {us:7.1f} us  {gb / us * 1e6:7.0f} GB/s | per tile cycles: wait {per[0]:.0f} patch {per[1]:.0f} "
-          f"compute {per[2]:.0f} (qk {sub[0]:.0f} softmax {sub[1]:.0f} pv {sub[2]:.0f}) store {per[3]:.0f}  (tiles/CTA {float(t[:, 4].mean()):.1f})")
+    per = t.sum(0) / t[:, 4].sum()
+    names = {0: "waitK", 1: "patchK+bar", 2: "qk", 3: "waitV+patchV", 5: "bar2", 6: "softmax", 7: "pv+bar", 8: "gather", 9: "release"}
+    body = " ".join(f"{v} {per[k]:.0f}" for k, v in names.items())
+    tot = sum(float(per[k]) for k in names)
+    print(f"N{n} hw{hw} C{c}: {us:7.1f} us  {gb / us * 1e6:7.0f} GB/s | cycles per tile (thread 0): {body} | total {tot:.0f}  "
+          f"(tiles/CTA {float(t[:, 4].mean()):.1f})")
