@@ -59,6 +59,9 @@ __device__ __forceinline__ void km_tma_2d(uint32_t dst, const CUtensorMap* map, 
       ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1)
       : "memory");
 }
+__device__ __forceinline__ void km_cp_async16(uint32_t dst, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
 // named barrier among `count` threads (a pixel group, or the 8 math warps)
 __device__ __forceinline__ void km_bar(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
 // (volatile keeps the program order against the barriers in NVVM; ptxas schedules the loads freely inside a phase)
@@ -156,17 +159,31 @@ kv_attn_mma_kernel(const __grid_constant__ CUtensorMap tmap, const KvAttnParams 
   float* s_mask = s_part + 8 * 32 * 4;                           // [16]
   int* s_pi = reinterpret_cast<int*>(s_mask + KM_L);             // [16]
   int* s_misc = s_pi + KM_L;                                     // [0] = write slot u of the current row n
-  uint64_t* bars = reinterpret_cast<uint64_t*>(s_misc + 4);      // full[NB], empty[NB]
-  uint8_t* s_head = reinterpret_cast<uint8_t*>(bars + 2 * NB);   // [T] head of each 8-channel chunk
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_misc + 4);      // full[NB], empty[NB], go
+  uint8_t* s_head = reinterpret_cast<uint8_t*>(bars + 2 * NB + 1);   // [T] head of each 8-channel chunk
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  long long d_entry = 0, d_gt0 = 0;
+  if (dbg != nullptr && tid == 0) {
+    d_entry = clock64();
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(d_gt0));
+  }
   const int total_tiles = tiles_per_row * p.n_rows;
-  const int t_begin = (int)(((long long)total_tiles * blockIdx.x) / gridDim.x);
-  const int t_end = (int)(((long long)total_tiles * (blockIdx.x + 1)) / gridDim.x);
-  const int my_tiles = t_end - t_begin;                          // contiguous range: at most one row change per CTA
+  // contiguous tile range per CTA; when the grid divides into the rows no CTA straddles a row change (one PE staging)
+  int t_begin, t_end;
+  if ((int)gridDim.x % p.n_rows == 0) {
+    const int cpr = (int)gridDim.x / p.n_rows, n0 = (int)blockIdx.x / cpr, r0 = (int)blockIdx.x - n0 * cpr;
+    t_begin = n0 * tiles_per_row + (int)(((long long)tiles_per_row * r0) / cpr);
+    t_end = n0 * tiles_per_row + (int)(((long long)tiles_per_row * (r0 + 1)) / cpr);
+  } else {
+    t_begin = (int)(((long long)total_tiles * blockIdx.x) / gridDim.x);
+    t_end = (int)(((long long)total_tiles * (blockIdx.x + 1)) / gridDim.x);
+  }
+  const int my_tiles = t_end - t_begin;
   const uint32_t bar0 = km_smem_u32(bars);
   auto full_bar = [&](int b) { return bar0 + 8u * b; };
   auto empty_bar = [&](int b) { return bar0 + 8u * (NB + b); };
+  const uint32_t go_bar = bar0 + 8u * (2 * NB);                  // math warps -> producer: the row's PE copies are queued
 
   if (tid == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap) : "memory");
@@ -174,6 +191,7 @@ kv_attn_mma_kernel(const __grid_constant__ CUtensorMap tmap, const KvAttnParams 
       km_mbar_init(full_bar(b), 1);
       km_mbar_init(empty_bar(b), 8);                             // one arrival per math warp
     }
+    km_mbar_init(go_bar, 8);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   {
@@ -186,6 +204,9 @@ kv_attn_mma_kernel(const __grid_constant__ CUtensorMap tmap, const KvAttnParams 
   if (warp == 8) {   // ---- TMA producer: planes in order K(0) V(0) K(1) V(1) ...; plane s lives in buffer s % NB ----
     if (lane == 0) {
       const int planes = 2 * my_tiles;
+      // the first burst (NB planes from every SM) would put ~20 MB in front of the math warps' small dependent loads
+      // (index tensors -> PE rows): let those be queued first
+      km_mbar_wait(go_bar, 0);
       for (int s = 0; s < planes; ++s) {
         const int b = s % NB, use = s / NB;
         if (use > 0) km_mbar_wait(empty_bar(b), (uint32_t)(use - 1) & 1u);
@@ -262,6 +283,7 @@ kv_attn_mma_kernel(const __grid_constant__ CUtensorMap tmap, const KvAttnParams 
   load_v(t_begin);
 
   int cur_n = -1;
+  bool pe_pending = false;
   const bool tl = dbg != nullptr && tid == 0;
   long long d_wait = 0, d_patch = 0, d_qk = 0, d_mid = 0, d_pv = 0, d_store = 0, d_t = 0, d_wv = 0, d_bar2 = 0, d_gather = 0;   // developer timeline
   auto stamp = [&](long long& acc) {
@@ -272,28 +294,36 @@ kv_attn_mma_kernel(const __grid_constant__ CUtensorMap tmap, const KvAttnParams 
     }
   };
 
+  const long long d_loop0 = tl ? clock64() : 0;
   for (int i = 0; i < my_tiles; ++i) {
     const int tile = t_begin + i;
     const int n = tile / tiles_per_row, p0 = (tile - n * tiles_per_row) * P;
     const bool active = p0 + pl < p.hw;
-    if (n != cur_n) {   // block-uniform: per-row schedule, Q_pe row and PE windows (all 8 math warps)
-      km_bar(15, 256);
+    if (n != cur_n) {   // block-uniform: per-row schedule; PE windows and Q_pe row by cp.async (all 8 math warps)
+      if (cur_n >= 0) km_bar(15, 256);                         // every group is done with the previous row's windows
       if (tid < KM_L) {
         s_pi[tid] = static_cast<int>(p.pe_idx[(size_t)n * KM_L + tid]);
         s_mask[tid] = __half2float(p.mask[(size_t)n * KM_L + tid]);
       }
       if (tid == 0) s_misc[0] = static_cast<int>(p.update_idx[n]);
       km_bar(15, 256);
+      // window slot j <- table row pe_idx[n][j], copied asynchronously (no registers, no wait here): the copies are
+      // queued ahead of the producer's first burst and land while the first K plane is in flight
       const int u0 = s_misc[0];
       for (int idx = tid; idx < KM_L * T; idx += 256) {
         const int j = idx / T, c = idx - j * T;
         const uint32_t off = km_off(j, c, KM_L);
-        *reinterpret_cast<uint4*>(pek + off) = ldg_cached(p.k_pe + (size_t)s_pi[j] * p.pe_ld + (size_t)c * 8);
-        *reinterpret_cast<uint4*>(pev + off) = ldg_cached(p.v_pe + (size_t)s_pi[j] * p.pe_ld + (size_t)c * 8);
+        km_cp_async16(km_smem_u32(pek + off), p.k_pe + (size_t)s_pi[j] * p.pe_ld + (size_t)c * 8);
+        km_cp_async16(km_smem_u32(pev + off), p.v_pe + (size_t)s_pi[j] * p.pe_ld + (size_t)c * 8);
       }
       for (int c = tid; c < T; c += 256)
-        *reinterpret_cast<uint4*>(s_qpe + (size_t)c * 8) = ldg_cached(p.q_pe + (size_t)s_pi[u0] * p.pe_ld + (size_t)c * 8);
-      km_bar(15, 256);
+        km_cp_async16(km_smem_u32(s_qpe + (size_t)c * 8), p.q_pe + (size_t)s_pi[u0] * p.pe_ld + (size_t)c * 8);
+      asm volatile("cp.async.commit_group;" ::: "memory");
+      if (cur_n < 0) {
+        __syncwarp();
+        if (lane == 0) km_mbar_arrive(go_bar);
+      }
+      pe_pending = true;
       cur_n = n;
     }
     const int u = s_misc[0];
@@ -303,6 +333,11 @@ kv_attn_mma_kernel(const __grid_constant__ CUtensorMap tmap, const KvAttnParams 
     uint8_t* vplane = ring + (size_t)bV * plane_bytes;
     if (tl) d_t = clock64();
     km_mbar_wait(full_bar(bK), (uint32_t)(sK / NB) & 1u);
+    if (pe_pending) {   // first tile of a row: this thread's PE copies have landed; meet so everyone's are visible
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+      km_bar(15, 256);
+      pe_pending = false;
+    }
     stamp(d_wait);
     if (active) {
       // ---- K append (HBM + window patch) and q~ staging: thread <-> one 16-byte chunk of the group's pixel ----
@@ -470,6 +505,11 @@ kv_attn_mma_kernel(const __grid_constant__ CUtensorMap tmap, const KvAttnParams 
     long long* o = dbg + (size_t)blockIdx.x * 16;
     o[0] = d_wait; o[1] = d_patch; o[2] = d_qk; o[3] = d_wv; o[4] = my_tiles;
     o[5] = d_bar2; o[6] = d_mid; o[7] = d_pv; o[8] = d_gather; o[9] = d_store;
+    o[10] = d_loop0 - d_entry;            // prologue: barrier init, head table, first prefetch
+    o[11] = clock64() - d_entry;          // whole CTA
+    long long gt1;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt1));
+    o[12] = d_gt0; o[13] = gt1;
   }
 }
 
@@ -515,7 +555,7 @@ int kv_attn_mma_launch(const KvAttnParams& p0, cudaStream_t stream) {
   const int NB = p.C == 1280 ? 3 : 4;
   const size_t plane_bytes = (size_t)ncb * P * KM_L * 128;
   const size_t smem = NB * plane_bytes + (size_t)2 * ncb * KM_L * 128 + (size_t)P * p.C * sizeof(__half) +
-                      (size_t)p.C * sizeof(__half) + 8 * 32 * 16 + KM_L * 8 + 16 + 2 * NB * 8 + 192 + 1024;
+                      (size_t)p.C * sizeof(__half) + 8 * 32 * 16 + KM_L * 8 + 16 + (2 * NB + 1) * 8 + 192 + 1024;
   if (smem > 227 * 1024) return fail(L2D_ERR_INVALID, "kv_attn(mma): tile does not fit in shared memory");
   CUtensorMap tm;
   const int64_t rows = (int64_t)p.n_rows * 2 * p.hw * KM_L;
@@ -528,7 +568,8 @@ int kv_attn_mma_launch(const KvAttnParams& p0, cudaStream_t stream) {
   }
   const int tiles_per_row = ceil_div(p.hw, P);
   const int total = tiles_per_row * p.n_rows;
-  const int grid = total < g_km_sms ? total : g_km_sms;
+  int grid = total < g_km_sms ? total : g_km_sms;
+  if (grid >= p.n_rows) grid -= grid % p.n_rows;                // whole CTAs per row: no CTA stages two rows' PE windows
   if (p.C == 320 && P == 4) return km_launch<320, 4, 4>(tm, p, tiles_per_row, grid, smem, stream);
   if (p.C == 640 && P == 2) return km_launch<640, 2, 4>(tm, p, tiles_per_row, grid, smem, stream);
   if (p.C == 1280 && P == 1) return km_launch<1280, 1, 3>(tm, p, tiles_per_row, grid, smem, stream);

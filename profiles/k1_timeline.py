@@ -20,10 +20,20 @@ for (n, hw, c) in [(2, 4096, 320), (2, 1024, 640), (2, 256, 1280), (2, 64, 1280)
     for i in range(3):
         ops.kv_attn(q, k, v, caches[i % 3], pe[0], pe[1], pe[2], mask, pi, up, heads)
     torch.cuda.synchronize()
+    # 12 launches replayed from a CUDA graph: no Python / launch-queue time inside the measurement
+    gr = torch.cuda.CUDAGraph()
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        with torch.cuda.graph(gr, stream=side):
+            for i in range(12):
+                ops.kv_attn(q, k, v, caches[i % 3], pe[0], pe[1], pe[2], mask, pi, up, heads)
+    torch.cuda.current_stream().wait_stream(side)
+    gr.replay()
+    torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for i in range(12):
-        ops.kv_attn(q, k, v, caches[i % 3], pe[0], pe[1], pe[2], mask, pi, up, heads)
+    gr.replay()
     e1.record()
     torch.cuda.synchronize()
     us = e0.elapsed_time(e1) / 12 * 1e3
@@ -39,5 +49,9 @@ for (n, hw, c) in [(2, 4096, 320), (2, 1024, 640), (2, 256, 1280), (2, 64, 1280)
     names = {0: "waitK", 1: "patchK+bar", 2: "qk", 3: "waitV+patchV", 5: "bar2", 6: "softmax", 7: "pv+bar", 8: "gather", 9: "release"}
     body = " ".join(f"{v} {per[k]:.0f}" for k, v in names.items())
     tot = sum(float(per[k]) for k in names)
+    span = (t[:, 13].max() - t[:, 12].min()) / 1e3
+    cta = t[:, 11].mean()
+    print(f"   kernel span (globaltimer) {span:.1f} us; CTA lifetime {cta:.0f} cycles, prologue {t[:, 10].mean():.0f}, "
+          f"loop {float((t[:, [0,1,2,3,5,6,7,8,9]].sum(1)).mean()):.0f}")
     print(f"N{n} hw{hw} C{c}: {us:7.1f} us  {gb / us * 1e6:7.0f} GB/s | cycles per tile (thread 0): {body} | total {tot:.0f}  "
           f"(tiles/CTA {float(t[:, 4].mean()):.1f})")

@@ -93,14 +93,10 @@ def test_unet_tiny_stream_vs_reference_golden():
     referee(sums, g["kv_sums"], sums16, "unet_tiny kv sums", slack=3.0, floor=2e-3)
 
 
-@pytest.mark.parametrize("graph", [False, True])
-def test_unet_sd15_size_vs_oracle(graph):
-    """BASELINE config 2 (512x512 -> 64x64 latent, N=2, L=16, SD1.5 widths, random weights): two steady-state
-    steps against the fp32 oracle (evaluated on the GPU for speed), torch-fp16 restatement as referee."""
+def _unet_case(d, n, h, w, graph, steps, tag, t_list, kv_probe=(0, 13, 39)):
     from live2diff_b200.unet_step import B200UNetStep
 
-    d = UNetDims()
-    n, h, w = 2, 64, 64
+    L, sink = d.window_size, d.sink_size
     sd = random_state_dict(d, seed=0)
     unet = B200UNetStep(sd, d, n, h, w, use_cuda_graph=graph)
     sd32 = {k: v.to(DEV) for k, v in sd.items()}
@@ -112,12 +108,12 @@ def test_unet_sd15_size_vs_oracle(graph):
         c.copy_(torch.randn(c.shape, generator=gen).half())
     kv32 = [c.float() for c in kv]
     kv16 = [c.clone() for c in kv]
-    ab, pe, up = S.init_schedule(n, 16, 8)
-    for _ in range(20):
-        S.update_schedule(ab, pe, up, 16, 8)
+    ab, pe, up = S.init_schedule(n, L, sink)
+    for _ in range(L + 4):
+        S.update_schedule(ab, pe, up, L, sink)
     ctx = torch.randn(n, 77, 768, generator=gen).half().to(DEV)
-    t = torch.tensor([399, 199], device=DEV)
-    for step in range(3 if graph else 2):
+    t = torch.tensor(t_list, device=DEV)
+    for step in range(steps):
         x = torch.randn(n, 4, 1, h, w, generator=gen).half().to(DEV)
         dep = torch.randn(n, 4, 1, h, w, generator=gen).half().to(DEV)
         m16, pi, ui = ab.half().to(DEV), pe.to(DEV), up.to(DEV)
@@ -125,13 +121,33 @@ def test_unet_sd15_size_vs_oracle(graph):
                    pe_idx=pi, update_idx=ui)["sample"]
         y32 = O.unet_forward(sd32, odims(d), x.float(), t, ctx.float(), m16.float(), dep.float(), kv32, pi, ui)
         y16 = O.unet_forward(sd16, odims(d), x, t, ctx, m16, dep, kv16, pi, ui)
-        referee(out, y32, y16, f"unet_sd15 graph={graph} step {step}", slack=2.5)
-        S.update_schedule(ab, pe, up, 16, 8)
+        referee(out, y32, y16, f"{tag} graph={graph} step {step}", slack=2.5)
+        S.update_schedule(ab, pe, up, L, sink)
     # the caches evolved identically (same slots written, values within fp16 chain error)
-    for i in (0, 13, 39):
-        referee(kv[i], kv32[i], kv16[i], f"unet_sd15 kv[{i}]", slack=2.5)
+    for i in kv_probe:
+        referee(kv[i], kv32[i], kv16[i], f"{tag} kv[{i}]", slack=2.5)
     assert unet.launches_per_step > 0
-    print(f"[info] launches/step={unet.launches_per_step} engine bytes={unet.device_bytes / 2**30:.2f} GiB")
+    print(f"[info] {tag}: launches/step={unet.launches_per_step} engine bytes={unet.device_bytes / 2**30:.2f} GiB")
+
+
+@pytest.mark.parametrize("graph", [False, True])
+def test_unet_sd15_size_vs_oracle(graph):
+    """BASELINE config 2 (512x512 -> 64x64 latent, N=2, L=16, SD1.5 widths, random weights): two steady-state
+    steps against the fp32 oracle (evaluated on the GPU for speed), torch-fp16 restatement as referee."""
+    _unet_case(UNetDims(), 2, 64, 64, graph, 3 if graph else 2, "unet_sd15", [399, 199])
+
+
+def test_unet_config3_768x512_vs_oracle():
+    """BASELINE config 3 geometry (768x512 -> 96x64 latent, non-square: h != w through conv halos, GroupNorm, the
+    2x down/up samplers and the KV-cache pixel order), depth latent on, N=2, L=16."""
+    _unet_case(UNetDims(), 2, 64, 96, True, 2, "unet_cfg3_96x64", [399, 199])
+
+
+def test_unet_config4_long_cache_vs_oracle():
+    """BASELINE config 4 (4 denoise rows, KV window 32 = 8 sink + 24 rolling; 11.3 GiB of cache): K1 runs its
+    general-window kernel, every per-row schedule differs."""
+    d = UNetDims(window_size=32, sink_size=8, pe_max_len=32)   # base_config.yaml has max_len 24: config 4 needs >= 32
+    _unet_case(d, 4, 64, 64, True, 2, "unet_cfg4_N4_L32", [699, 499, 299, 99], kv_probe=(0, 39))
 
 
 def test_stream_pipeline_vs_stream_oracle():
