@@ -194,10 +194,12 @@ typedef struct l2d_unet_step_args {
 
 int l2d_unet_create(l2d_unet** out, const l2d_unet_config* cfg, const l2d_tensor* weights, int n_weights);
 int l2d_unet_step(l2d_unet* u, const l2d_unet_step_args* args, void* stream);
-/* One eager (non-graph) step with CUDA events around every launch, summed per kernel family on return
- * (synchronises the stream).  Families: 0 temporal KV-cache attention (K1), 1 tcgen05 GEMM (linears + convs),
- * 2 spatial attention, 3 LayerNorm/GroupNorm, 4 im2col (incl. GroupNorm+SiLU+im2col), 5 other.
- * ms_by_family / launches_by_family: host arrays of 6.  This is a real step (the KV cache advances). */
+/* Per-family kernel time of one step: the step is run eagerly once per family with CUDA events around that family's
+ * launches only (so the host stays ahead of the GPU and the stream runs back to back, as in the graph replay), and
+ * the event times are summed per family on return (synchronises the stream).  Families: 0 temporal KV-cache
+ * attention (K1), 1 tcgen05 GEMM (linears + convs), 2 spatial attention, 3 LayerNorm/GroupNorm, 4 im2col (incl.
+ * GroupNorm+SiLU+im2col), 5 other.  ms_by_family / launches_by_family: host arrays of 6.  The passes are real,
+ * idempotent steps on the same inputs (the KV cache advances once: the same slot is rewritten with the same k/v). */
 #define L2D_N_FAMILIES 6
 int l2d_unet_profile_step(l2d_unet* u, const l2d_unet_step_args* args, void* stream, float* ms_by_family,
                           int32_t* launches_by_family);

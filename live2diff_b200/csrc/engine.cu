@@ -156,6 +156,7 @@ enum Family { FAM_KV = 0, FAM_GEMM = 1, FAM_ATTN = 2, FAM_NORM = 3, FAM_IM2COL =
 // Per-kernel-family CUDA-event timing of one eager step (bench.py's roofline numbers come from here)
 struct Profiler {
   bool on = false;
+  int only = -1;   // family timed in this pass (-1: all)
   std::vector<cudaEvent_t> pool;
   size_t used = 0;
   std::vector<std::pair<size_t, size_t>> spans[FAM_COUNT];   // indices into pool (start, stop)
@@ -188,14 +189,15 @@ struct Core {
     Core& c;
     size_t i0 = 0;
     int fam;
+    bool live() const { return c.prof.on && (c.prof.only < 0 || c.prof.only == fam); }
     Scope(Core& core, int f) : c(core), fam(f) {
-      if (c.prof.on) {
+      if (live()) {
         i0 = c.prof.next();
         cudaEventRecord(c.prof.pool[i0], c.st);
       }
     }
     ~Scope() {
-      if (c.prof.on) {
+      if (live()) {
         const size_t i1 = c.prof.next();
         cudaEventRecord(c.prof.pool[i1], c.st);
         c.prof.spans[fam].push_back({i0, i1});
@@ -1033,10 +1035,18 @@ extern "C" int l2d_unet_profile_step(l2d_unet* u, const l2d_unet_step_args* a, v
   L2D_CHECK_ARG(a->n_kv == u->n_kv && a->kv_cache, "bad kv-cache table");
   Core& k = u->core;
   k.st = (cudaStream_t)stream;
+  // One eager pass per family, events only around that family's launches: the host then stays ahead of the GPU, the
+  // stream runs back to back like the graph replay, and an event pair brackets the kernel (plus its launch gap) rather
+  // than host enqueue time.  Passes are idempotent: same inputs, the same slot of every cache rewritten with the same k/v.
   k.prof.reset();
   k.prof.on = true;
-  const int rc = run_step(u, a);
+  int rc = L2D_OK;
+  for (int f = 0; f < FAM_COUNT && rc == L2D_OK; ++f) {
+    k.prof.only = f;
+    rc = run_step(u, a);
+  }
   k.prof.on = false;
+  k.prof.only = -1;
   if (rc != L2D_OK) return rc;
   L2D_CUDA(cudaStreamSynchronize(k.st));
   for (int f = 0; f < FAM_COUNT; ++f) {

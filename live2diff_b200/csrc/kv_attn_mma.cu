@@ -89,7 +89,6 @@ __device__ __forceinline__ uint32_t km_hadd2(uint32_t a, uint32_t b) { return h2
 
 constexpr int KM_L = 16;
 constexpr int KM_THREADS = 288;     // 8 math warps + the TMA warp
-constexpr int KM_OT = 20;           // bytes per channel row of the O^T staging (8 heads x fp16 + 4 pad: conflict-free gather)
 
 // swizzled byte offset of 16-byte chunk `chunk` (= channel / 8) of tile row `row` inside one plane:
 // 64-column blocks of R rows x 128 B, 128B swizzle = chunk-in-block XOR (row % 8)
@@ -135,7 +134,9 @@ __device__ __forceinline__ uint32_t km_frag_off(const KmFrag& f, int i, int R) {
 // dealt round-robin to the W warps of its group; partial scores meet in shared memory.
 // PE: the row's K_pe[pi[j]] / V_pe[pi[j]] windows are staged once per row n in shared memory in the same swizzled
 // [16 x C] layout as a pixel's K / V window, so the PE fragments come from the same ldmatrix addresses.
-// O^T staging: after the scores the pixel's K window is dead; O^T rows (KM_OT bytes per channel) reuse it.
+// O^T staging: the 16 bytes (8 heads) of O^T row c = 16*ks + r overwrite the V window at (slot r, channels 16*ks..+7),
+// bytes only this warp reads and has already consumed for that very k-step; swizzled like the window, so the writes and
+// the gather are conflict-free.  The K plane is therefore free right after the scores and is released early.
 // CT/PT: compile-time C and pixels per tile (0 = run-time geometry, any C <= 640); NB: plane buffers in the ring.
 template <int CT, int PT, int NB>
 __global__ void __launch_bounds__(KM_THREADS, 1)
@@ -155,7 +156,8 @@ kv_attn_mma_kernel(const __grid_constant__ CUtensorMap tmap, const KvAttnParams 
   uint8_t* pev = pek + pe_plane;
   __half* s_q = reinterpret_cast<__half*>(pev + pe_plane);       // [P][C]  q + Q_pe
   __half* s_qpe = s_q + (size_t)P * C;                           // [C]     Q_pe[pi[u]] of the current row n
-  float* s_part = reinterpret_cast<float*>(s_qpe + C);           // [8 warps][32 lanes][4] partial scores
+  __half* s_vn = s_qpe + C;                                      // [2][P][C] freshly projected v of this / the next tile
+  float* s_part = reinterpret_cast<float*>(s_vn + (size_t)2 * P * C);   // [8 warps][32 lanes][4] partial scores
   float* s_mask = s_part + 8 * 32 * 4;                           // [16]
   int* s_pi = reinterpret_cast<int*>(s_mask + KM_L);             // [16]
   int* s_misc = s_pi + KM_L;                                     // [0] = write slot u of the current row n
@@ -185,6 +187,15 @@ kv_attn_mma_kernel(const __grid_constant__ CUtensorMap tmap, const KvAttnParams 
   auto empty_bar = [&](int b) { return bar0 + 8u * (NB + b); };
   const uint32_t go_bar = bar0 + 8u * (2 * NB);                  // math warps -> producer: the row's PE copies are queued
 
+  // the first row's schedule is requested at kernel entry so its latency hides behind the prologue
+  int e_pi = 0, e_u = 0;
+  float e_mask = 0.f;
+  if (tid < KM_L && my_tiles > 0) {
+    const int n0 = t_begin / tiles_per_row;
+    e_pi = static_cast<int>(p.pe_idx[(size_t)n0 * KM_L + tid]);
+    e_mask = __half2float(p.mask[(size_t)n0 * KM_L + tid]);
+    e_u = static_cast<int>(p.update_idx[n0]);
+  }
   if (tid == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap) : "memory");
     for (int b = 0; b < NB; ++b) {
@@ -207,12 +218,15 @@ kv_attn_mma_kernel(const __grid_constant__ CUtensorMap tmap, const KvAttnParams 
       // the first burst (NB planes from every SM) would put ~20 MB in front of the math warps' small dependent loads
       // (index tensors -> PE rows): let those be queued first
       km_mbar_wait(go_bar, 0);
+      auto plane_row = [&](int s) {
+        const int tile = t_begin + (s >> 1);
+        const int n = tile / tiles_per_row, p0 = (tile - n * tiles_per_row) * P;
+        return ((n * 2 + (s & 1)) * p.hw + p0) * KM_L;
+      };
       for (int s = 0; s < planes; ++s) {
         const int b = s % NB, use = s / NB;
         if (use > 0) km_mbar_wait(empty_bar(b), (uint32_t)(use - 1) & 1u);
-        const int tile = t_begin + (s >> 1);
-        const int n = tile / tiles_per_row, p0 = (tile - n * tiles_per_row) * P;
-        const int row0 = ((n * 2 + (s & 1)) * p.hw + p0) * KM_L;
+        const int row0 = plane_row(s);
         km_mbar_expect_tx(full_bar(b), plane_bytes);
         const uint32_t dst = km_smem_u32(ring + (size_t)b * plane_bytes);
         for (int b2 = 0; b2 < ncb; ++b2) km_tma_2d(dst + b2 * (R * 128), &tmap, full_bar(b), b2 * 64, row0);
@@ -234,7 +248,7 @@ kv_attn_mma_kernel(const __grid_constant__ CUtensorMap tmap, const KvAttnParams 
 
   // per-lane addressing constants of the specialised kernels (see km_frag)
   KmFrag fk, fpk, fv, fpv;
-  uint32_t ot_base = 0;                                          // O^T staging: row 16*ks + g, unit t
+  KmFrag fo;                                                     // O^T staging: (slot g, chunk 2*ks) of the V window
   uint32_t qm[2 * NKW];                                          // Qblk column masks of this lane's head g
   if constexpr (SPEC) {
     constexpr int RT = PT * KM_L;
@@ -242,46 +256,62 @@ kv_attn_mma_kernel(const __grid_constant__ CUtensorMap tmap, const KvAttnParams 
     fpk = km_frag<WT>(rowk, 2 * sub + jq, KM_L);
     fv = km_frag<WT>(pl * KM_L + rowv, 2 * sub + jv, RT);
     fpv = km_frag<WT>(rowv, 2 * sub + jv, KM_L);
-    if (WT == 8) ot_base = (uint32_t)(pl * 2048 + (sub >> 2) * (RT * 128) + (16 * (sub & 3) + g) * KM_OT + 4 * t);
-    else ot_base = (uint32_t)(pl * 2048 + (16 * sub + g) * KM_OT + 4 * t);
+    fo = km_frag<WT>(pl * KM_L + g, 2 * sub, RT);
 #pragma unroll
     for (int i = 0; i < NKW; ++i) {
       qm[2 * i] = (int)s_head[2 * (sub + WT * i)] == g ? 0xffffffffu : 0u;
       qm[2 * i + 1] = (int)s_head[2 * (sub + WT * i) + 1] == g ? 0xffffffffu : 0u;
     }
   }
-  auto ot_off = [&](int i) -> uint32_t {                         // byte offset of O^T row (16*ks + g), unit t
+  auto ot_off = [&](int i) -> uint32_t {                         // byte offset of O^T row (16*ks + g), heads 2t, 2t+1
     if constexpr (SPEC) {
       constexpr int RT = PT * KM_L;
-      if (WT == 2) return ot_base + (uint32_t)((i >> 1) * (RT * 128) + (i & 1) * (32 * KM_OT));
-      if (WT == 4) return ot_base + (uint32_t)(i * (RT * 128));
-      return ot_base + (uint32_t)(2 * i * (RT * 128));
+      return km_frag_off<WT>(fo, i, RT) + 4 * t;
     } else {
-      const int c = 16 * (sub + W * i) + g;
-      return (uint32_t)((c >> 6) * (R * 128) + pl * 2048 + (c & 63) * KM_OT + 4 * t);
+      return km_off(pl * KM_L + g, 2 * (sub + W * i), R) + 4 * t;
     }
   };
 
   // k/v/q chunk of the NEXT tile, requested one tile ahead
-  uint4 pf_k = make_uint4(0, 0, 0, 0), pf_v = pf_k, pf_q = pf_k;
-  auto load_kq = [&](int tile2) {
+  uint4 pf_k = make_uint4(0, 0, 0, 0), pf_q = pf_k;
+  // pixel row of this group in tile `tile2` (-1: past the ragged end of a row); no division when P divides hw
+  const bool flat = (p.hw % P) == 0;
+  auto pixel_row = [&](int tile2) -> long long {
+    if (flat) return (long long)tile2 * P + pl;
     const int n2 = tile2 / tiles_per_row, q0 = (tile2 - n2 * tiles_per_row) * P;
-    if (has_chunk && q0 + pl < p.hw) {
-      const size_t row = (size_t)n2 * p.hw + q0 + pl;
-      pf_k = ldg_cached(p.k_new + row * p.ld + (size_t)cg * 8);
-      pf_q = ldg_cached(p.q + row * p.ld + (size_t)cg * 8);
+    return q0 + pl < p.hw ? (long long)n2 * p.hw + q0 + pl : -1;
+  };
+  auto load_kq = [&](int tile2) {
+    const long long row = pixel_row(tile2);
+    if (has_chunk && row >= 0) {
+      pf_k = ldg_cached(p.k_new + (size_t)row * p.ld + (size_t)cg * 8);
+      pf_q = ldg_cached(p.q + (size_t)row * p.ld + (size_t)cg * 8);
     }
   };
-  auto load_v = [&](int tile2) {
-    const int n2 = tile2 / tiles_per_row, q0 = (tile2 - n2 * tiles_per_row) * P;
-    if (has_chunk && q0 + pl < p.hw) {
-      const size_t row = (size_t)n2 * p.hw + q0 + pl;
-      pf_v = ldg_cached(p.v_new + row * p.ld + (size_t)cg * 8);
+  // v is needed half a tile later than k / q and would pin four more registers for a whole tile: it is staged through
+  // shared memory with cp.async instead (each thread copies and later reads its own chunk: no barrier involved)
+  auto load_v = [&](int tile2, int buf) {
+    const long long row = tile2 < t_end ? pixel_row(tile2) : -1;
+    if (has_chunk && row >= 0) {
+      km_cp_async16(km_smem_u32(s_vn + ((size_t)buf * P + pl) * C + (size_t)cg * 8), p.v_new + (size_t)row * p.ld + (size_t)cg * 8);
     }
+    asm volatile("cp.async.commit_group;" ::: "memory");   // one group per tile, also when empty: wait_group 1 below counts them
   };
   load_kq(t_begin);
-  load_v(t_begin);
+  load_v(t_begin, 0);
 
+  // gather addresses of this thread's (up to 3) channel pairs inside the V plane, incl. the head column: fixed per kernel
+  uint32_t g_lo[3], g_hi[3];
+#pragma unroll
+  for (int m = 0; m < 3; ++m) {
+    const int c = 2 * (cg + GT * m);
+    g_lo[m] = g_hi[m] = 0xffffffffu;
+    if (c < C) {
+      const int hb = 2 * (int)s_head[c >> 3], row = pl * KM_L + (c & 15), ch = 2 * (c >> 4);
+      g_lo[m] = km_off(row, ch, R) + hb;
+      g_hi[m] = km_off(row + 1, ch, R) + hb;
+    }
+  }
   int cur_n = -1;
   bool pe_pending = false;
   const bool tl = dbg != nullptr && tid == 0;
@@ -302,10 +332,15 @@ kv_attn_mma_kernel(const __grid_constant__ CUtensorMap tmap, const KvAttnParams 
     if (n != cur_n) {   // block-uniform: per-row schedule; PE windows and Q_pe row by cp.async (all 8 math warps)
       if (cur_n >= 0) km_bar(15, 256);                         // every group is done with the previous row's windows
       if (tid < KM_L) {
-        s_pi[tid] = static_cast<int>(p.pe_idx[(size_t)n * KM_L + tid]);
-        s_mask[tid] = __half2float(p.mask[(size_t)n * KM_L + tid]);
+        if (cur_n >= 0) {
+          e_pi = static_cast<int>(p.pe_idx[(size_t)n * KM_L + tid]);
+          e_mask = __half2float(p.mask[(size_t)n * KM_L + tid]);
+          e_u = static_cast<int>(p.update_idx[n]);
+        }
+        s_pi[tid] = e_pi;
+        s_mask[tid] = e_mask;
+        if (tid == 0) s_misc[0] = e_u;
       }
-      if (tid == 0) s_misc[0] = static_cast<int>(p.update_idx[n]);
       km_bar(15, 256);
       // window slot j <- table row pe_idx[n][j], copied asynchronously (no registers, no wait here): the copies are
       // queued ahead of the producer's first burst and land while the first K plane is in flight
@@ -351,6 +386,7 @@ kv_attn_mma_kernel(const __grid_constant__ CUtensorMap tmap, const KvAttnParams 
       km_bar(gbar, GT);
       stamp(d_patch);
       if (i + 1 < my_tiles) load_kq(tile + 1);
+      load_v(tile + 1, (i + 1) & 1);
 
       // ---- scores: rows = slots, columns = heads; two accumulators halve the dependent mma chain ----
       float acc[4] = {0.f, 0.f, 0.f, 0.f}, acc2[4] = {0.f, 0.f, 0.f, 0.f};
@@ -393,15 +429,18 @@ kv_attn_mma_kernel(const __grid_constant__ CUtensorMap tmap, const KvAttnParams 
 
       // ---- V append + patch (the V plane was requested one plane after K), then the group meets ----
       km_mbar_wait(full_bar(bV), (uint32_t)(sV / NB) & 1u);
+      asm volatile("cp.async.wait_group 1;" ::: "memory");          // this tile's v (the next tile's may be in flight)
       if (has_chunk) {
+        const uint4 pf_v = *reinterpret_cast<const uint4*>(s_vn + ((size_t)(i & 1) * P + pl) * C + (size_t)cg * 8);
         __half* vdst = p.cache + ((((size_t)n * 2 + 1) * p.hw + p0 + pl) * KM_L + u) * C + (size_t)cg * 8;
         *reinterpret_cast<uint4*>(vdst) = pf_v;
         *reinterpret_cast<uint4*>(vplane + km_off(pl * KM_L + u, cg, R)) = pf_v;
       }
       stamp(d_wv);
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // the K patch (generic proxy) precedes the async refill
       km_bar(gbar, GT);
+      if (lane == 0) km_mbar_arrive(empty_bar(bK));                   // scores done: the K plane can be refilled now
       stamp(d_bar2);
-      if (i + 1 < my_tiles) load_v(tile + 1);
       if (W > 1) {   // sum the partial scores of this pixel's warps
         acc[0] = acc[1] = acc[2] = acc[3] = 0.f;
         for (int w2 = 0; w2 < W; ++w2) {
@@ -455,8 +494,8 @@ kv_attn_mma_kernel(const __grid_constant__ CUtensorMap tmap, const KvAttnParams 
           float o[4];
           km_mma0(o, a, pb0, pb1);
           // lane (g, t): o[0] = O^T[dt*16+g][2t], o[1] = [..][2t+1], o[2] = O^T[dt*16+8+g][2t], o[3] = [..][2t+1]
-          *reinterpret_cast<uint32_t*>(kplane + ooff) = h2_as_u32(__floats2half2_rn(o[0], o[1]));
-          *reinterpret_cast<uint32_t*>(kplane + ooff + 8 * KM_OT) = h2_as_u32(__floats2half2_rn(o[2], o[3]));
+          *reinterpret_cast<uint32_t*>(vplane + ooff) = h2_as_u32(__floats2half2_rn(o[0], o[1]));
+          *reinterpret_cast<uint32_t*>(vplane + ooff + 8 * 128) = h2_as_u32(__floats2half2_rn(o[2], o[3]));   // slot g + 8
         };
         if constexpr (SPEC) {
           constexpr int RT = PT * KM_L;
@@ -475,30 +514,26 @@ kv_attn_mma_kernel(const __grid_constant__ CUtensorMap tmap, const KvAttnParams 
       // ---- gather column head(c) of O^T and store the pixel's output row (two channels per thread) ----
       {
         __half* orow = p.out + ((size_t)n * p.hw + p0 + pl) * C;
-        const uint8_t* otp = kplane + pl * 2048;
-        for (int cp = cg; 2 * cp < C; cp += GT) {
-          const int c = 2 * cp;
-          const uint8_t* src = otp + (c >> 6) * (R * 128) + (c & 63) * KM_OT + 2 * (int)s_head[c >> 3];
-          const uint32_t lo = *reinterpret_cast<const unsigned short*>(src);
-          const uint32_t hi = *reinterpret_cast<const unsigned short*>(src + KM_OT);
-          *reinterpret_cast<uint32_t*>(orow + c) = lo | (hi << 16);
+#pragma unroll
+        for (int m = 0; m < 3; ++m) {
+          if (g_lo[m] != 0xffffffffu) {
+            const uint32_t lo = *reinterpret_cast<const unsigned short*>(vplane + g_lo[m]);
+            const uint32_t hi = *reinterpret_cast<const unsigned short*>(vplane + g_hi[m]);
+            *reinterpret_cast<uint32_t*>(orow + 2 * (cg + GT * m)) = lo | (hi << 16);
+          }
         }
       }
       stamp(d_gather);
     } else {   // ragged last tile of a row: nothing to compute, but stay inside the pipeline depth (empty counts)
       km_mbar_wait(full_bar(bV), (uint32_t)(sV / NB) & 1u);
-      if (i + 1 < my_tiles) {
-        load_kq(tile + 1);
-        load_v(tile + 1);
-      }
+      if (lane == 0) km_mbar_arrive(empty_bar(bK));
+      if (i + 1 < my_tiles) load_kq(tile + 1);
+      load_v(tile + 1, (i + 1) & 1);
     }
-    // ---- release both planes: window patches and O^T staging (generic proxy) precede the async refill ----
+    // ---- release the V plane: window patch and O^T staging (generic proxy) precede the async refill ----
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     __syncwarp();
-    if (lane == 0) {
-      km_mbar_arrive(empty_bar(bK));
-      km_mbar_arrive(empty_bar(bV));
-    }
+    if (lane == 0) km_mbar_arrive(empty_bar(bV));
     stamp(d_store);
   }
   if (tl) {
@@ -555,7 +590,7 @@ int kv_attn_mma_launch(const KvAttnParams& p0, cudaStream_t stream) {
   const int NB = p.C == 1280 ? 3 : 4;
   const size_t plane_bytes = (size_t)ncb * P * KM_L * 128;
   const size_t smem = NB * plane_bytes + (size_t)2 * ncb * KM_L * 128 + (size_t)P * p.C * sizeof(__half) +
-                      (size_t)p.C * sizeof(__half) + 8 * 32 * 16 + KM_L * 8 + 16 + (2 * NB + 1) * 8 + 192 + 1024;
+                      (size_t)p.C * sizeof(__half) + (size_t)2 * P * p.C * sizeof(__half) + 8 * 32 * 16 + KM_L * 8 + 16 + (2 * NB + 1) * 8 + 192 + 1024;
   if (smem > 227 * 1024) return fail(L2D_ERR_INVALID, "kv_attn(mma): tile does not fit in shared memory");
   CUtensorMap tm;
   const int64_t rows = (int64_t)p.n_rows * 2 * p.hw * KM_L;
