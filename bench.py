@@ -319,10 +319,11 @@ def run_native(args):
         traffic = None
         tp = os.path.join(ROOT, "profiles", "k1_traffic.json")
         if os.path.exists(tp):
-            traffic = json.load(open(tp)).get("dram_bytes_per_step")
+            traffic = json.load(open(tp)).get("dram_bytes_per_launch_avg")     # ncu dram read+write, per launch
         roofline = {"kernel": "kv_attn_kernel (K1, 40 launches/step)", "bound": "hbm", "achieved": achieved,
                     "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak, "peak_source": which,
-                    "algorithmic_bytes_per_step": k1_bytes, "ms_per_step_in_kernel": k1_ms, "traffic": traffic}
+                    "algorithmic_bytes_per_step": k1_bytes, "algorithmic_bytes_per_launch": k1_bytes / fam_cnt["kv_attn"],
+                    "ms_per_step_in_kernel": k1_ms, "us_per_launch": k1_ms * 1e3 / fam_cnt["kv_attn"], "traffic": traffic}
         gemm_flops = 2.227e12 * 0.93                        # all dense contractions except the 3 attention families
         breakdown = {f: {"ms": round(fam_ms[f], 4), "launches": fam_cnt[f]} for f in fam_ms}
         tensor = {"kernel": "gemm_f16_tcgen05_kernel (all linears + convs)", "bound": "tensor",
