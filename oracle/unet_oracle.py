@@ -278,6 +278,66 @@ def temporal_transformer(sd: SD, p: str, x: Tensor, kv_caches: Sequence[Tensor],
 
 
 # --------------------------------------------------------------------------------------
+# warm-up pass: the same UNet over F frames with bidirectional temporal attention
+# --------------------------------------------------------------------------------------
+
+def warmup_temporal_attention(sd: SD, p: str, x: Tensor, kv_row: Tensor, d: UNetDims) -> Tensor:
+    """VersatileAttention.forward (motion_module.py:469-530) for tokens x [F,hw,C] of ONE clip (b = 1).
+
+    kv_row [2,hw,L,C] is one denoise row of the module's cache (`cache[idx]`, pipeline:323); slots 0..F-1
+    receive the PE-free k / v of the F warm-up frames (:488-489).  q/k/v get the PE of positions 0..F-1 through
+    the same bias-free projections (:491-499); attention is full (no mask) over the F frames of a pixel."""
+    f, hw, c = x.shape
+    xt = x.transpose(0, 1)                                            # "(b f) d c -> (b d) f c"   :481
+    q = linear(sd, p + ".to_q", xt, bias=False)
+    k = linear(sd, p + ".to_k", xt, bias=False)
+    v = linear(sd, p + ".to_v", xt, bias=False)
+    kv_row[0, :, :f] = k                                              # :488-489
+    kv_row[1, :, :f] = v
+    q_pe, k_pe, v_pe = pe_tables(sd, p, f)                            # :491-495
+    q = q + q_pe.to(x.dtype)
+    k = k + k_pe.to(x.dtype)
+    v = v + v_pe.to(x.dtype)
+    o = merge_heads(sdpa(split_heads(q, d.heads), split_heads(k, d.heads), split_heads(v, d.heads)))   # :501-516
+    return linear(sd, p + ".to_out.0", o).transpose(0, 1)             # :519-525
+
+
+def temporal_transformer_warmup(sd: SD, p: str, x: Tensor, kv_rows: Sequence[Tensor], d: UNetDims) -> Tensor:
+    """TemporalTransformer3DModel.forward_orig (motion_module.py:215-254) + TemporalTransformerBlock.forward_orig
+    (:369-399) for x [F,C,h,w] (GroupNorm per frame: the reference normalises the "(b f) c h w" view)."""
+    n, c, hh, ww = x.shape
+    h = group_norm(sd, p + ".norm", x, d.norm_groups, 1e-6)
+    t = h.permute(0, 2, 3, 1).reshape(n, hh * ww, c)
+    t = linear(sd, p + ".proj_in", t)
+    b = p + ".transformer_blocks.0"
+    for i in range(2):
+        a = warmup_temporal_attention(sd, f"{b}.attention_blocks.{i}", layer_norm(sd, f"{b}.norms.{i}", t), kv_rows[i], d)
+        t = a + t
+    t = geglu_ff(sd, b + ".ff", layer_norm(sd, b + ".ff_norm", t)) + t
+    t = linear(sd, p + ".proj_out", t)
+    return t.reshape(n, hh, ww, c).permute(0, 3, 1, 2) + x
+
+
+def unet_forward_warmup(sd: SD, d: UNetDims, sample: Tensor, timestep: Tensor, encoder_hidden_states: Tensor,
+                        depth_sample: Optional[Tensor], kv_rows: List[Tensor]) -> Tensor:
+    """UNet3DConditionWarmupModel.forward (unet_depth_warmup.py:405-590) for one clip: sample/depth_sample
+    [1,4,F,h,w], timestep [1], encoder_hidden_states [1,77,D], kv_rows = 40 views [2,hw,L,C] (`cache[idx]`).
+    Every non-temporal layer treats the F frames as batch rows (all `(b f)` rearranges), so the streaming walk
+    is reused with the frames on the batch axis and the bidirectional motion module swapped in."""
+    assert sample.dim() == 5 and sample.shape[0] == 1, "warm-up runs one clip (pipeline:310-312)"
+    f = sample.shape[2]
+    x = sample[0].transpose(0, 1)
+    dep = depth_sample[0].transpose(0, 1) if depth_sample is not None else None
+    ctx = encoder_hidden_states.expand(f, -1, -1)
+
+    def temporal(p, xx, caches):
+        return temporal_transformer_warmup(sd, p, xx, caches, d)
+
+    y = unet_forward(sd, d, x, timestep.reshape(-1)[:1], ctx, None, dep, kv_rows, None, None, temporal=temporal)
+    return y.transpose(0, 1)[None]
+
+
+# --------------------------------------------------------------------------------------
 # whole UNet step
 # --------------------------------------------------------------------------------------
 
@@ -294,8 +354,8 @@ class _Cursor:
 
 
 def unet_forward(sd: SD, d: UNetDims, sample: Tensor, timestep: Tensor, encoder_hidden_states: Tensor,
-                 temporal_attention_mask: Tensor, depth_sample: Optional[Tensor], kv_cache: List[Tensor],
-                 pe_idx: Tensor, update_idx: Tensor) -> Tensor:
+                 temporal_attention_mask: Optional[Tensor], depth_sample: Optional[Tensor], kv_cache: List[Tensor],
+                 pe_idx: Optional[Tensor], update_idx: Optional[Tensor], temporal=None) -> Tensor:
     """UNet3DConditionStreamingModel.forward (unet_depth_streaming.py:429-627).
 
     sample/depth_sample [N,4,1,h,w] or [N,4,h,w]; returns the same rank.  `kv_cache` (40 tensors
@@ -310,6 +370,9 @@ def unet_forward(sd: SD, d: UNetDims, sample: Tensor, timestep: Tensor, encoder_
     ctx = encoder_hidden_states
     mask = temporal_attention_mask
     nlev = len(d.block_out_channels)
+    if temporal is None:                       # streaming motion module; the warm-up pass swaps in the bidirectional one
+        def temporal(p, x, caches):
+            return temporal_transformer(sd, p, x, caches, mask, pe_idx, update_idx, d)
 
     # time (unet_depth_streaming.py:497-505): sinusoid in fp32 -> model dtype -> MLP
     t_emb = timestep_sinusoid(timestep.expand(sample.shape[0]), d.block_out_channels[0]).to(dt)
@@ -329,8 +392,7 @@ def unet_forward(sd: SD, d: UNetDims, sample: Tensor, timestep: Tensor, encoder_
             x = resnet_block(sd, f"{bp}.resnets.{li}", x, emb, d)
             if d.down_has_attn[bi]:
                 x = spatial_transformer(sd, f"{bp}.attentions.{li}", x, ctx, d)
-            x = temporal_transformer(sd, f"{bp}.motion_modules.{li}.temporal_transformer", x, cur.take2(kv_cache),
-                                     mask, pe_idx, update_idx, d)
+            x = temporal(f"{bp}.motion_modules.{li}.temporal_transformer", x, cur.take2(kv_cache))
             skips.append(x)
         if bi != nlev - 1:
             x = downsample(sd, f"{bp}.downsamplers.0", x)
@@ -349,8 +411,7 @@ def unet_forward(sd: SD, d: UNetDims, sample: Tensor, timestep: Tensor, encoder_
             x = resnet_block(sd, f"{bp}.resnets.{li}", x, emb, d)
             if d.up_has_attn[bi]:
                 x = spatial_transformer(sd, f"{bp}.attentions.{li}", x, ctx, d)
-            x = temporal_transformer(sd, f"{bp}.motion_modules.{li}.temporal_transformer", x, cur.take2(kv_cache),
-                                     mask, pe_idx, update_idx, d)
+            x = temporal(f"{bp}.motion_modules.{li}.temporal_transformer", x, cur.take2(kv_cache))
         if bi != nlev - 1:
             x = upsample(sd, f"{bp}.upsamplers.0", x)
     assert not skips and cur.i == len(kv_cache)

@@ -36,6 +36,6 @@ def import_reference_models():
 
     mods = {}
     for m in ("resnet", "positional_encoding", "attention", "stream_motion_module", "motion_module",
-              "unet_blocks_streaming", "unet_depth_streaming"):
+              "unet_blocks_streaming", "unet_depth_streaming", "unet_blocks_warmup", "unet_depth_warmup"):
         mods[m] = importlib.import_module(f"live2diff.animatediff.models.{m}")
     return mods

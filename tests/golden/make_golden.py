@@ -281,6 +281,89 @@ def gen_unet_tiny(frames=11, seed=3, h=16, w=16, n_rows=2):
     print("unet_tiny_stream.pt", float(torch.stack(ys).abs().mean()), float(torch.stack(ys).abs().max()))
 
 
+def build_ref_warmup_unet(d: UNetDims):
+    """UNet3DConditionWarmupModel configured like its from_pretrained_2d (unet_depth_warmup.py:611-614): motion
+    module type "Vanilla", attention class "versatile", no attention kwargs."""
+    U = M["unet_depth_warmup"].UNet3DConditionWarmupModel
+    kw = mm_kwargs(d)
+    kw["attention_class_name"] = "versatile"
+    kw["attention_kwargs"] = {}
+    return U(block_out_channels=d.block_out_channels, cross_attention_dim=d.cross_attention_dim,
+             attention_head_dim=d.heads, cond_mapping=True, use_inflated_groupnorm=True, use_motion_module=True,
+             motion_module_resolutions=(1, 2, 4, 8), motion_module_type="Vanilla",
+             motion_module_kwargs=kw, norm_eps=d.norm_eps, layers_per_block=d.layers_per_block)
+
+
+def gen_warmup_attention(tag, ch, heads, hw, frames, window, pe_max, seed):
+    """VersatileAttention alone (motion_module.py:438-530): tokens [(b f), d, c] of one clip, cache row [2,hw,L,C]."""
+    d = UNetDims(block_out_channels=(ch,), heads=heads, window_size=window, pe_max_len=pe_max,
+                 down_has_attn=(False,), up_has_attn=(False,))
+    pre = "down_blocks.0.motion_modules.0.temporal_transformer.transformer_blocks.0.attention_blocks.0"
+    w_ = random_tensors(sub_spec(d, pre), seed=seed)
+    A = M["motion_module"].VersatileAttention
+    attn = A(attention_mode="Temporal", cross_attention_dim=None, query_dim=ch, heads=heads, dim_head=ch // heads,
+             dropout=0.0, bias=False, upcast_attention=False, temporal_position_encoding=True,
+             temporal_position_encoding_max_len=pe_max)
+    attn.load_state_dict(w_, strict=True)
+    g = torch.Generator().manual_seed(seed + 1)
+    x = torch.randn(frames, hw, ch, generator=g)
+    kv_row = torch.zeros(2, hw, window, ch)
+    y = attn(x, video_length=frames, kv_cache=kv_row)
+    torch.save({"ch": ch, "heads": heads, "hw": hw, "frames": frames, "window": window, "pe_max": pe_max, "seed": seed,
+                "fingerprint": spec_fingerprint(w_), "x": x, "y": y.clone(), "kv_row": kv_row.clone()},
+               os.path.join(HERE, f"warmup_attention_{tag}.pt"))
+    print("warmup_attention", tag, float(y.abs().mean()))
+
+
+def gen_unet_tiny_warmup(seed=3, h=16, w=16, n_rows=2, stream_frames=3):
+    """Warm-up hand-off (pipeline:315-338 around unet_warmup, then the streaming UNet on the caches it filled):
+    the warm-up model runs once per denoise row idx on `cache[idx]` views, then `stream_frames` streaming steps
+    continue on the same caches.  Same seeded weights for both models (identical state_dict key set)."""
+    d = TINY
+    sd = random_tensors(unet_param_spec(d), seed=seed)
+    uw = build_ref_warmup_unet(d)
+    uw.load_state_dict(sd, strict=True)
+    uw.eval()
+    us = build_ref_unet(d)
+    us.load_state_dict(sd, strict=True)
+    us.eval()
+    us.set_info_for_attn(h, w)
+    uw.set_info_for_attn(h, w)
+    kv = us.prepare_cache(n_rows)
+    f = d.sink_size
+    g = torch.Generator().manual_seed(seed + 7)
+    ctx = torch.randn(1, 77, d.cross_attention_dim, generator=g)
+    ts = torch.tensor([399, 199])
+    xs, ds, ys = [], [], []
+    for idx in range(n_rows):
+        x = torch.randn(1, 4, f, h, w, generator=g)
+        dep = torch.randn(1, 4, f, h, w, generator=g)
+        o = uw(x, ts[idx].view(1), temporal_attention_mask=None, depth_sample=dep, encoder_hidden_states=ctx,
+               kv_cache=[c[idx] for c in kv], return_dict=True)["sample"]
+        xs.append(x)
+        ds.append(dep)
+        ys.append(o.clone())
+    kv_after_warmup = {i: kv[i][:, :, :16].clone() for i in (0, 1, 12, 27, 39)}     # first 16 pixels; sums cover the rest
+    kv_sums = torch.tensor([float(c.double().sum()) for c in kv])
+    kv_abs = torch.tensor([float(c.double().abs().sum()) for c in kv])
+    sx, sdp, sy = [], [], []
+    ctx_s = ctx.repeat(n_rows, 1, 1)
+    for mask, pe_idx, update_idx in run_schedule(n_rows, d.window_size, d.sink_size, stream_frames):
+        x = torch.randn(n_rows, 4, 1, h, w, generator=g)
+        dep = torch.randn(n_rows, 4, 1, h, w, generator=g)
+        o = us(x, ts, encoder_hidden_states=ctx_s, temporal_attention_mask=mask, depth_sample=dep, kv_cache=kv,
+               pe_idx=pe_idx, update_idx=update_idx)
+        sx.append(x)
+        sdp.append(dep)
+        sy.append(o["sample"].clone())
+    torch.save({"dims": d.__dict__, "seed": seed, "h": h, "w": w, "n_rows": n_rows, "frames": f, "timesteps": ts,
+                "ctx": ctx, "fingerprint": spec_fingerprint(sd), "x": torch.stack(xs), "depth": torch.stack(ds),
+                "y": torch.stack(ys), "kv_sums": kv_sums, "kv_abs_sums": kv_abs, "kv_after_warmup": kv_after_warmup,
+                "stream_x": torch.stack(sx), "stream_depth": torch.stack(sdp), "stream_y": torch.stack(sy)},
+               os.path.join(HERE, "unet_tiny_warmup.pt"))
+    print("unet_tiny_warmup.pt", float(torch.stack(ys).abs().mean()), float(torch.stack(sy).abs().mean()))
+
+
 def gen_specs():
     for tag, d in (("tiny", TINY), ("sd15", UNetDims())):
         u = build_ref_unet(d, device="meta")
@@ -289,7 +372,17 @@ def gen_specs():
         print("spec", tag, len(spec), sum(torch.Size(v).numel() for v in spec.values()) / 1e6, "M")
 
 
+def gen_warmup():
+    gen_warmup_attention("c64_f8", 64, 8, 12, 8, 16, 24, seed=41)
+    gen_warmup_attention("c320_f8", 320, 8, 6, 8, 16, 24, seed=42)
+    gen_warmup_attention("c128_f2_L4", 128, 8, 4, 2, 4, 24, seed=43)
+    gen_unet_tiny_warmup()
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "warmup":      # only the warm-up fixtures (the others are unchanged)
+        gen_warmup()
+        sys.exit(0)
     gen_specs()
     gen_schedule()
     gen_scheduler_pointwise()
@@ -301,3 +394,5 @@ if __name__ == "__main__":
     gen_temporal_transformer("c320", 320, 8, 2, 2, 2, 16, 8, 24, 3, seed=32)
     gen_resnet_and_friends()
     gen_unet_tiny()
+    gen_warmup()
+

@@ -99,6 +99,46 @@ def test_unet_tiny_stream_matches_reference():
     torch.testing.assert_close(kv[39][0, :, :64], g["kv_final_39_row0"], **TOL)
 
 
+@pytest.mark.parametrize("tag", ["c64_f8", "c320_f8", "c128_f2_L4"])
+def test_warmup_attention_matches_reference(tag):
+    """VersatileAttention (bidirectional, writes cache slots 0..F-1) -- SURVEY.md §8f-1."""
+    g = load_golden(f"warmup_attention_{tag}.pt")
+    d = UNetDims(block_out_channels=(g["ch"],), heads=g["heads"], window_size=g["window"], pe_max_len=g["pe_max"],
+                 down_has_attn=(False,), up_has_attn=(False,))
+    pre = "down_blocks.0.motion_modules.0.temporal_transformer.transformer_blocks.0.attention_blocks.0"
+    sd = prefixed(regen_weights(sub_spec(d, pre), g["seed"], g["fingerprint"]), "a")
+    kv_row = torch.zeros(2, g["hw"], g["window"], g["ch"])
+    y = O.warmup_temporal_attention(sd, "a", g["x"], kv_row, odims(d))
+    torch.testing.assert_close(y, g["y"], **TOL)
+    torch.testing.assert_close(kv_row, g["kv_row"], **TOL)
+    assert float(kv_row[:, :, g["frames"]:].abs().max()) == 0.0          # slots >= F untouched
+
+
+def test_unet_tiny_warmup_then_stream_matches_reference():
+    """Warm-up UNet once per denoise row on `cache[idx]`, then streaming steps on the caches it filled."""
+    g = load_golden("unet_tiny_warmup.pt")
+    d = dims_from(g["dims"])
+    od = odims(d)
+    sd = regen_weights(unet_param_spec(d), g["seed"], g["fingerprint"])
+    n = g["n_rows"]
+    kv = O.alloc_kv_cache(od, n, g["h"], g["w"])
+    for idx in range(n):
+        y = O.unet_forward_warmup(sd, od, g["x"][idx], g["timesteps"][idx].view(1), g["ctx"], g["depth"][idx],
+                                  [c[idx] for c in kv])
+        torch.testing.assert_close(y, g["y"][idx], rtol=2e-4, atol=5e-5)
+    torch.testing.assert_close(torch.tensor([float(c.double().sum()) for c in kv]), g["kv_sums"], rtol=1e-4, atol=1e-2)
+    torch.testing.assert_close(torch.tensor([float(c.double().abs().sum()) for c in kv]), g["kv_abs_sums"], rtol=1e-4,
+                               atol=1e-2)
+    for i, ref in g["kv_after_warmup"].items():
+        torch.testing.assert_close(kv[i][:, :, :16], ref, **TOL)
+    ctx = g["ctx"].repeat(n, 1, 1)
+    frames = g["stream_x"].shape[0]
+    for f, (mask, pe_idx, update_idx) in enumerate(schedule_frames(n, d.window_size, d.sink_size, frames)):
+        y = O.unet_forward(sd, od, g["stream_x"][f], g["timesteps"], ctx, mask, g["stream_depth"][f], kv, pe_idx,
+                           update_idx)
+        torch.testing.assert_close(y, g["stream_y"][f], rtol=2e-4, atol=5e-5)
+
+
 @pytest.mark.parametrize("tag", ["tiny", "sd15"])
 def test_param_spec_matches_reference_state_dict(tag):
     ref = json.load(open(os.path.join(GOLDEN, f"state_dict_spec_{tag}.json")))
