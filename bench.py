@@ -210,6 +210,7 @@ def run_native(args):
     import torch.distributed as dist
 
     from live2diff_b200 import _lib
+    from live2diff_b200.device_stream import B200DeviceStream
     from live2diff_b200.stream_pipeline import B200StreamPipeline, broadcast_prompt
     from live2diff_b200.unet_step import B200UNetStep
     from live2diff_b200.weights import UNetDims, random_state_dict
@@ -238,9 +239,13 @@ def run_native(args):
         c.normal_(generator=torch.Generator(device=dev).manual_seed(7 + rank))
     prompt = torch.randn(1, 77, d.cross_attention_dim, generator=torch.Generator().manual_seed(42)) if rank == 0 else None
     prompt = broadcast_prompt(prompt, (1, 77, d.cross_attention_dim), dev, src=0)
-    pipe.prepare(prompt, kv)
+    pipe.prepare(prompt, kv)                       # host-scheduled pipeline: only used for the per-family profile below
     for _ in range(3 * WINDOW):                    # run the ring schedule into steady state (all L slots valid)
         pipe.schedule.advance()
+    # the measured path: device-resident stream state, one CUDA graph per frame
+    stream = B200DeviceStream(unet, T_INDEX, seed=2 + rank) if args.pipeline == "device" else pipe
+    if stream is not pipe:
+        stream.prepare(prompt, kv)
 
     n_frames_pool = 16
     host_x = [torch.randn(1, 4, 1, LAT_H, LAT_W, generator=gen).half().pin_memory() for _ in range(n_frames_pool)]
@@ -261,16 +266,19 @@ def run_native(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
+    if stream is not pipe:                         # real frames until every ring slot is valid (steady state)
+        for i in range(3 * WINDOW):
+            stream(dev_x[i % n_frames_pool], dev_d[i % n_frames_pool])
     # ---------------- device-resident throughput ----------------
     for i in range(max(args.warmup, 3)):
-        pipe(dev_x[i % n_frames_pool], dev_d[i % n_frames_pool])
+        stream(dev_x[i % n_frames_pool], dev_d[i % n_frames_pool])
     barrier()
     l0 = lib.l2d_launch_count()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     with ClockSampler(local) as clk:
         ev0.record()
         for i in range(args.steps):
-            pipe(dev_x[i % n_frames_pool], dev_d[i % n_frames_pool])
+            stream(dev_x[i % n_frames_pool], dev_d[i % n_frames_pool])
         ev1.record()
         barrier()
     launches = lib.l2d_launch_count() - l0
@@ -282,10 +290,13 @@ def run_native(args):
     barrier()
     ev0.record()
     for i in range(args.steps):
-        x = host_x[i % n_frames_pool].to(dev, non_blocking=True)
-        dd = host_d[i % n_frames_pool].to(dev, non_blocking=True)
-        out = pipe(x, dd)
-        host_out.copy_(out, non_blocking=True)
+        if stream is not pipe:                               # pinned host in -> H2D, frame graph, D2H -> pinned host out
+            stream(host_x[i % n_frames_pool], host_d[i % n_frames_pool], out=host_out)
+        else:
+            x = host_x[i % n_frames_pool].to(dev, non_blocking=True)
+            dd = host_d[i % n_frames_pool].to(dev, non_blocking=True)
+            out = pipe(x, dd)
+            host_out.copy_(out, non_blocking=True)
         torch.cuda.current_stream().synchronize()            # the caller consumes frame i before sending frame i+1
     ev1.record()
     barrier()
@@ -337,7 +348,10 @@ def run_native(args):
                 "clocks": clk.summary(),
                 "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": bytes_in, "d2h_bytes_per_step": bytes_out,
                         "ms_per_step": e2e_ms / args.steps},
-                "gpu_launches": int(launches), "launches_per_step": int(unet.launches_per_step),
+                "gpu_launches": int(launches),
+                "launches_per_step": int(stream.launches_per_frame if stream is not pipe else unet.launches_per_step),
+                "pipeline": "device-resident stream state, whole frame = 1 CUDA graph (l2d_stream_frame)"
+                            if stream is not pipe else "host-scheduled B200StreamPipeline, UNet step = 1 CUDA graph",
                 "roofline": roofline, "roofline_tensor": tensor, "kernel_time_breakdown_ms": breakdown,
                 "engine_device_gib": round(unet.device_bytes / 2 ** 30, 2)}
     if world > 1:
@@ -360,6 +374,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the (~1 min) CPU oracle leg")
+    ap.add_argument("--pipeline", default="device", choices=["device", "host"],
+                    help="device: B200DeviceStream (state in HBM, whole-frame graph); host: B200StreamPipeline")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

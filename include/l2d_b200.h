@@ -17,6 +17,11 @@
  *                                                                        -> l2d_kv_attn
  *   a4  scheduler_step_batch + stream-batch shift  pipeline_stream_animation_depth.py:387-401,589-601
  *                                                                        -> l2d_lcm_step
+ *   f4  predict_x0_batch state machine (a2 + a5 + a4 around B1), device-resident
+ *                                              pipeline_stream_animation_depth.py:403-438, 573-601 -> l2d_stream_*
+ *   f1  stream.unet_warmup(...) (warm-up pass)  pipeline_stream_animation_depth.py:315-338; the bidirectional
+ *       VersatileAttention + cache fill          live2diff/animatediff/models/motion_module.py:469-530
+ *                                                -> l2d_unet_* with cfg.warmup_frames > 0, l2d_warmup_attn
  * The op-level entry points (l2d_gemm, l2d_layernorm, ...) are the kernels those are built from;
  * they are exported so each kernel can be parity-tested through the same ABI.
  */
@@ -29,7 +34,7 @@
 extern "C" {
 #endif
 
-#define L2D_ABI_VERSION 1
+#define L2D_ABI_VERSION 2
 
 #define L2D_OK 0
 #define L2D_ERR_INVALID (-1)     /* bad argument / unsupported shape */
@@ -55,6 +60,15 @@ int l2d_kv_attn(const void* q, const void* k_new, const void* v_new, int64_t qkv
                 const void* q_pe, const void* k_pe, const void* v_pe, const void* mask,
                 const int64_t* pe_idx, const int64_t* update_idx, void* out,
                 int n_rows, int hw, int window, int channels, int heads, void* stream);
+
+/* f1: warm-up temporal attention of ONE clip of `frames` frames (VersatileAttention.forward core, motion_module.py:488-516):
+ *   kv_cache_row[0,p,f,:] = k[f,p,:]; kv_cache_row[1,p,f,:] = v[f,p,:]            (PE-free fill of slots 0..frames-1)
+ *   out[f,p,head] = softmax_j( <q[f]+Qpe[f], k[j]+Kpe[j]> / sqrt(hd) ) . (v[j]+Vpe[j]),  j over the frames, no mask
+ * q/k/v: rows f*hw+p, `qkv_ld` elements between rows.  kv_cache_row = cache[idx] of one denoise row: [2,hw,L,C].
+ * q_pe/k_pe/v_pe: rows 0..frames-1 with pitch pe_ld.  out rows f*hw+p with pitch out_ld.  frames <= min(16, L). */
+int l2d_warmup_attn(const void* q, const void* k, const void* v, int64_t qkv_ld, void* kv_cache_row,
+                    const void* q_pe, const void* k_pe, const void* v_pe, int64_t pe_ld, void* out, int64_t out_ld,
+                    int frames, int hw, int window, int channels, int heads, void* stream);
 
 /* Developer hook: when non-NULL, every CTA of the (L == 16) K1 kernel writes cycles spent waiting for TMA data,
  * appending/staging, computing, storing, and its tile count to timeline[cta*8 ..]; NULL disables. */
@@ -177,6 +191,11 @@ typedef struct l2d_unet_config {
   int32_t up_has_attn[8];           /* 0,1,1,1 */
   float norm_eps;                   /* 1e-5 */
   int32_t use_cuda_graph;           /* capture the step into a CUDA graph on first call and replay it */
+  int32_t warmup_frames;            /* 0: streaming step.  F > 0: warm-up engine (UNet3DConditionWarmupModel): n_rows must
+                                       equal F (the frames of one clip ride on the batch axis), the motion modules run the
+                                       bidirectional attention over the F frames and fill cache slots 0..F-1; step args:
+                                       kv_cache[i] = row `idx` of cache i ([2,hw,L,C]); mask / pe_idx / update_idx unused
+                                       (may be NULL); timestep / encoder_hidden_states repeated per frame by the caller */
 } l2d_unet_config;
 
 typedef struct l2d_unet_step_args {
@@ -208,6 +227,42 @@ int64_t l2d_unet_device_bytes(const l2d_unet* u);
 /* Kernel launches per step (counted on the most recent step). */
 int64_t l2d_unet_launches_per_step(const l2d_unet* u);
 void l2d_unet_destroy(l2d_unet* u);
+
+/* ---------------------------------------------------------------------------------------------
+ * f4: device-resident stream = the state machine of predict_x0_batch (pipeline_stream_animation_depth.py:573-601) with
+ * its state in HBM: latent / depth buffers [(N-1),4,h,w], the KV ring schedule (attn_bias, pe_idx, update_idx: :403-438),
+ * LCM constants (:260-301), prompt embedding, frame counter.  One frame = one CUDA graph (assembly -> UNet step ->
+ * x0 prediction + re-noise + shift -> schedule advance); the re-noise is a counter-based Philox4x32-10 normal keyed by
+ * (seed, frame, row, element) instead of torch's global generator.  The KV caches stay caller-owned tensors (B1).
+ *   timesteps [N] int64 and consts [4,N] fp32 = (sqrt(abar), sqrt(1-abar), c_skip, c_out): HOST arrays (copied).
+ *   x_t_latent / depth_latent / out_x0: [1,4,1,h,w] fp16, device OR pinned-host pointers (copied in/out on the stream).
+ *   noise: NULL (internal generator) or [(N-1),4,1,h,w] fp16 overriding it for this frame (parity tests).
+ * ------------------------------------------------------------------------------------------- */
+typedef struct l2d_stream l2d_stream;
+int l2d_stream_create(l2d_stream** out, l2d_unet* unet, const int64_t* timesteps, const float* consts, int warmup_slots,
+                      uint64_t seed, int do_add_noise, int use_cuda_graph);
+void l2d_stream_destroy(l2d_stream* s);
+/* prepare(): zero buffers, schedule back to its initial state, frame counter 0 (:171-214, 403-414). */
+int l2d_stream_reset(l2d_stream* s, void* stream);
+/* prompt_embeds [rows,ctx_len,cross_attention_dim] fp16, rows = 1 (repeated to N, :231/:376) or N. */
+int l2d_stream_set_prompt(l2d_stream* s, const void* prompt_embeds, int rows, void* stream);
+/* host array of n_kv device pointers ([N,2,hw,L,C] each, motion_module_idx order); re-captures the graph if they change. */
+int l2d_stream_set_cache(l2d_stream* s, void* const* kv_cache, int n_kv);
+int l2d_stream_frame(l2d_stream* s, const void* x_t_latent, const void* depth_latent, const void* noise, void* out_x0,
+                     void* stream);
+int64_t l2d_stream_launches_per_frame(const l2d_stream* s);
+/* Read-back of the schedule (synchronises): valid [N] int32 (unmasked leading slots), pe_idx [N,L], update_idx [N]. */
+int l2d_stream_get_schedule(l2d_stream* s, int32_t* valid, int64_t* pe_idx, int64_t* update_idx, uint64_t* frame);
+/* Stream migration: buffers + schedule + frame counter + seed as one host blob (synchronises; KV caches not included). */
+int64_t l2d_stream_state_bytes(const l2d_stream* s);
+int l2d_stream_save_state(l2d_stream* s, void* host_buf, int64_t bytes);
+int l2d_stream_load_state(l2d_stream* s, const void* host_buf, int64_t bytes);
+/* The schedule transition and the generator evaluated on the HOST by the same code the kernels run (CPU-side tests):
+ * init != 0 writes the initial state first, then `advance_frames` transitions are applied to the host arrays. */
+int l2d_ring_schedule_host(int32_t* valid, int64_t* pe_idx, int64_t* update_idx, int n_rows, int window, int warmup,
+                           int init, int advance_frames);
+int l2d_stream_randn_host(uint64_t seed, uint64_t frame, uint32_t row, float* out, int count);
+void l2d_philox4x32_10_host(const uint32_t* counter4, const uint32_t* key2, uint32_t* out4);
 
 #ifdef __cplusplus
 }

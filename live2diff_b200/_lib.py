@@ -13,7 +13,7 @@ from typing import Optional
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libl2d_b200.so")
 
-vp, i64, i32, f32 = C.c_void_p, C.c_int64, C.c_int, C.c_float
+vp, i64, i32, f32, u64 = C.c_void_p, C.c_int64, C.c_int, C.c_float, C.c_uint64
 
 
 class L2DTensor(C.Structure):
@@ -26,7 +26,7 @@ class L2DUnetConfig(C.Structure):
                 ("groups", C.c_int32), ("window", C.c_int32), ("n_rows", C.c_int32), ("latent_h", C.c_int32),
                 ("latent_w", C.c_int32), ("mapping_channels", C.c_int32 * 8), ("n_mapping", C.c_int32),
                 ("down_has_attn", C.c_int32 * 8), ("up_has_attn", C.c_int32 * 8), ("norm_eps", C.c_float),
-                ("use_cuda_graph", C.c_int32)]
+                ("use_cuda_graph", C.c_int32), ("warmup_frames", C.c_int32)]
 
 
 class L2DUnetStepArgs(C.Structure):
@@ -42,6 +42,7 @@ SIGNATURES = {
     "l2d_launch_count": (i64, []),
     "l2d_kv_attn": (i32, [vp, vp, vp, i64, vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, vp]),
     "l2d_kv_attn_set_debug": (None, [vp]),
+    "l2d_warmup_attn": (i32, [vp, vp, vp, i64, vp, vp, vp, vp, i64, vp, i64, i32, i32, i32, i32, i32, vp]),
     "l2d_layernorm": (i32, [vp, vp, vp, vp, i32, i32, f32, vp]),
     "l2d_groupnorm_workspace_bytes": (i64, [i32, i32]),
     "l2d_groupnorm": (i32, [vp, i32, vp, i32, vp, vp, vp, vp, i32, i32, i32, i32, f32, i32, i32, i32, vp]),
@@ -67,6 +68,20 @@ SIGNATURES = {
     "l2d_unet_device_bytes": (i64, [vp]),
     "l2d_unet_launches_per_step": (i64, [vp]),
     "l2d_unet_destroy": (None, [vp]),
+    "l2d_stream_create": (i32, [C.POINTER(vp), vp, C.POINTER(i64), C.POINTER(f32), i32, u64, i32, i32]),
+    "l2d_stream_destroy": (None, [vp]),
+    "l2d_stream_reset": (i32, [vp, vp]),
+    "l2d_stream_set_prompt": (i32, [vp, vp, i32, vp]),
+    "l2d_stream_set_cache": (i32, [vp, C.POINTER(vp), i32]),
+    "l2d_stream_frame": (i32, [vp, vp, vp, vp, vp, vp]),
+    "l2d_stream_launches_per_frame": (i64, [vp]),
+    "l2d_stream_get_schedule": (i32, [vp, C.POINTER(i32), C.POINTER(i64), C.POINTER(i64), C.POINTER(u64)]),
+    "l2d_stream_state_bytes": (i64, [vp]),
+    "l2d_stream_save_state": (i32, [vp, vp, i64]),
+    "l2d_stream_load_state": (i32, [vp, vp, i64]),
+    "l2d_ring_schedule_host": (i32, [C.POINTER(i32), C.POINTER(i64), C.POINTER(i64), i32, i32, i32, i32, i32]),
+    "l2d_stream_randn_host": (i32, [u64, u64, C.c_uint32, C.POINTER(f32), i32]),
+    "l2d_philox4x32_10_host": (None, [C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]),
 }
 
 _lib: Optional[C.CDLL] = None
@@ -84,7 +99,7 @@ def lib() -> C.CDLL:
             fn = getattr(handle, name)
             fn.restype = res
             fn.argtypes = args
-        if handle.l2d_abi_version() != 1:
+        if handle.l2d_abi_version() != 2:
             raise RuntimeError("libl2d_b200.so ABI version mismatch")
         _lib = handle
     return _lib

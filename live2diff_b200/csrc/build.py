@@ -15,7 +15,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 PKG = os.path.dirname(HERE)
 OUT = os.path.join(PKG, "libl2d_b200.so")
 OBJ = os.path.join(HERE, "_build")
-SOURCES = ["api.cu", "kv_attn.cu", "kv_attn_mma.cu", "norms.cu", "pointwise.cu", "gemm_tcgen05.cu", "flash_attn.cu", "engine.cu"]
+SOURCES = ["api.cu", "kv_attn.cu", "kv_attn_mma.cu", "kv_warmup.cu", "norms.cu", "pointwise.cu", "gemm_tcgen05.cu", "flash_attn.cu", "engine.cu", "stream_state.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC",
          "--expt-relaxed-constexpr"]

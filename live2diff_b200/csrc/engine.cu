@@ -182,6 +182,7 @@ struct Core {
   DevPool pool;
   cudaStream_t st = nullptr;
   int heads = 8, groups = 32, L = 16, n_rows = 2;
+  int warm_frames = 0;   // > 0: warm-up engine, the n_rows batch rows are the frames of one clip
   Scratch s;
   Profiler prof;
 
@@ -361,6 +362,20 @@ struct Core {
     for (int i = 0; i < 2; ++i) {
       RC(layernorm(s.t, t.ln[i], s.ln, m, c));
       RC(gemm(s.ln, c, t.qkv[i], s.qkv, 3 * c, m));
+      if (warm_frames > 0) {   // VersatileAttention over the frames + sink-slot fill (motion_module.py:469-530)
+        WarmupAttnParams wp{};
+        wp.q = s.qkv; wp.k = s.qkv + c; wp.v = s.qkv + 2 * c; wp.ld = 3 * c;
+        wp.cache_row = static_cast<__half*>(caches[i]);
+        wp.q_pe = t.pe_tab[i]; wp.k_pe = t.pe_tab[i] + c; wp.v_pe = t.pe_tab[i] + 2 * c; wp.pe_ld = 3 * c;
+        wp.out = s.att; wp.ldo = c;
+        wp.frames = warm_frames; wp.hw = hw; wp.L = L; wp.C = c; wp.heads = heads;
+        {
+          Scope sc(*this, FAM_KV);
+          RC(warmup_attn_launch(wp, st));
+        }
+        RC(gemm(s.att, c, t.out[i], s.t, c, m, s.t, c));
+        continue;
+      }
       KvAttnParams p{};
       p.q = s.qkv; p.k_new = s.qkv + c; p.v_new = s.qkv + 2 * c; p.ld = 3 * c;
       p.cache = static_cast<__half*>(caches[i]);
@@ -731,6 +746,8 @@ extern "C" int l2d_unet_create(l2d_unet** out, const l2d_unet_config* cfg, const
   L2D_CHECK_ARG(out && cfg && weights && n_weights > 0, "null arguments");
   L2D_CHECK_ARG(cfg->n_levels >= 1 && cfg->n_levels <= 8 && cfg->layers_per_block >= 1, "bad topology");
   L2D_CHECK_ARG(cfg->n_rows >= 1 && cfg->n_rows <= 8, "n_rows must be in 1..8");
+  L2D_CHECK_ARG(cfg->warmup_frames == 0 || (cfg->warmup_frames == cfg->n_rows && cfg->warmup_frames <= cfg->window),
+                "warm-up engine: warmup_frames must equal n_rows and be <= window");
   L2D_CHECK_ARG(cfg->window >= 1 && cfg->window <= 32, "window must be in 1..32");
   L2D_CHECK_ARG(cfg->latent_h % (1 << (cfg->n_levels - 1)) == 0 && cfg->latent_w % (1 << (cfg->n_levels - 1)) == 0,
                 "latent size must be divisible by 2^(levels-1)");
@@ -746,6 +763,7 @@ extern "C" int l2d_unet_create(l2d_unet** out, const l2d_unet_config* cfg, const
   u->cfg = *cfg;
   Core& k = u->core;
   k.heads = cfg->heads; k.groups = cfg->groups; k.L = cfg->window; k.n_rows = cfg->n_rows;
+  k.warm_frames = cfg->warmup_frames;
   const int nlev = cfg->n_levels, n = cfg->n_rows, lpb = cfg->layers_per_block;
   for (int i = 0; i < nlev; ++i) {
     Level l{cfg->block_out_channels[i], cfg->latent_h >> i, cfg->latent_w >> i, 0};
@@ -962,9 +980,10 @@ extern "C" int l2d_unet_create(l2d_unet** out, const l2d_unet_config* cfg, const
 
 extern "C" int l2d_unet_step(l2d_unet* u, const l2d_unet_step_args* a, void* stream) {
   L2D_CHECK_ARG(u && a, "null arguments");
-  L2D_CHECK_ARG(a->sample && a->timestep && a->encoder_hidden_states && a->temporal_attention_mask && a->depth_sample &&
-                    a->kv_cache && a->pe_idx && a->update_idx && a->out_sample,
+  L2D_CHECK_ARG(a->sample && a->timestep && a->encoder_hidden_states && a->depth_sample && a->kv_cache && a->out_sample,
                 "null tensor pointer in step args");
+  L2D_CHECK_ARG(u->cfg.warmup_frames > 0 || (a->temporal_attention_mask && a->pe_idx && a->update_idx),
+                "null schedule tensor (mask / pe_idx / update_idx) in step args");
   L2D_CHECK_ARG(a->n_kv == u->n_kv, "expected " + std::to_string(u->n_kv) + " kv-cache tensors");
   for (int i = 0; i < a->n_kv; ++i) L2D_CHECK_ARG(a->kv_cache[i] != nullptr, "null kv-cache pointer");
   Core& k = u->core;
@@ -1028,6 +1047,18 @@ extern "C" int l2d_unet_step(l2d_unet* u, const l2d_unet_step_args* a, void* str
   ++u->steps_done;
   return L2D_OK;
 }
+
+namespace l2d {
+int unet_run_eager(::l2d_unet* u, const l2d_unet_step_args* a, cudaStream_t st) {
+  u->core.st = st;
+  return run_step(u, a);
+}
+void unet_geometry(const ::l2d_unet* u, int* n_rows, int* h, int* w, int* window, int* n_kv, int* ctx_len, int* ctx_dim,
+                   int* warmup_frames) {
+  *n_rows = u->cfg.n_rows; *h = u->cfg.latent_h; *w = u->cfg.latent_w; *window = u->cfg.window; *n_kv = u->n_kv;
+  *ctx_len = u->cfg.ctx_len; *ctx_dim = u->cfg.cross_attention_dim; *warmup_frames = u->cfg.warmup_frames;
+}
+}  // namespace l2d
 
 extern "C" int l2d_unet_profile_step(l2d_unet* u, const l2d_unet_step_args* a, void* stream, float* ms_by_family,
                                      int32_t* launches_by_family) {

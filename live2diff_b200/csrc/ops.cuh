@@ -28,6 +28,24 @@ int kv_attn_launch(const KvAttnParams& p, cudaStream_t stream);
 bool kv_attn_mma_supported(const KvAttnParams& p);
 int kv_attn_mma_launch(const KvAttnParams& p, cudaStream_t stream);
 
+// warm-up (bidirectional) temporal attention of one clip + fill of cache slots 0..frames-1 (kv_warmup.cu)
+struct WarmupAttnParams {
+  const __half* q;
+  const __half* k;
+  const __half* v;
+  int64_t ld;          // rows f*hw + pixel
+  __half* cache_row;   // [2, hw, L, C]: one denoise row of the module's cache
+  const __half* q_pe;
+  const __half* k_pe;
+  const __half* v_pe;
+  int64_t pe_ld;
+  __half* out;
+  int64_t ldo;
+  int frames, hw, L, C, heads;
+  float scale;
+};
+int warmup_attn_launch(const WarmupAttnParams& p, cudaStream_t stream);
+
 int groupnorm_launch(const __half* x1, int c1, const __half* x2, int c2, const __half* gamma, const __half* beta,
                      __half* y, float* ws, int n_img, int h, int w, int G, float eps, int silu, int mode, int stride,
                      cudaStream_t st);
@@ -44,5 +62,10 @@ int conv3x3_launch(const __half* x, int n_img, int h, int w, int cin, const __ha
 
 int attention_launch(const __half* q, int64_t ldq, const __half* k, int64_t ldk, const __half* v, int64_t ldv, __half* o,
                      int64_t ldo, int batch, int heads, int sq, int skv, int hd, cudaStream_t st);
+
+// engine.cu internals used by the device-resident stream (stream_state.cu)
+int unet_run_eager(::l2d_unet* u, const l2d_unet_step_args* a, cudaStream_t st);   // enqueue one step on st (capturable)
+void unet_geometry(const ::l2d_unet* u, int* n_rows, int* h, int* w, int* window, int* n_kv, int* ctx_len, int* ctx_dim,
+                   int* warmup_frames);
 
 }  // namespace l2d

@@ -37,6 +37,22 @@ def kv_attn(q, k_new, v_new, kv_cache, q_pe, k_pe, v_pe, mask, pe_idx, update_id
     return out
 
 
+def warmup_attn(q, k, v, kv_cache_row, q_pe, k_pe, v_pe, heads, qkv_ld=None, pe_ld=None, out=None):
+    """Warm-up (bidirectional) temporal attention of one clip + fill of cache slots 0..F-1 (csrc/kv_warmup.cu).
+    q/k/v [F,hw,C] (or views into a fused buffer with row pitch qkv_ld); kv_cache_row [2,hw,L,C] = cache[idx];
+    q_pe/k_pe/v_pe rows 0..F-1 (pitch pe_ld).  Returns out [F,hw,C]."""
+    f, hw, c = q.shape
+    _chk(kv_cache_row, "kv_cache_row")
+    if tuple(kv_cache_row.shape[:2]) != (2, hw) or kv_cache_row.shape[3] != c:
+        raise ValueError(f"kv_cache_row {tuple(kv_cache_row.shape)}: expected [2,{hw},L,{c}]")
+    if out is None:
+        out = torch.empty(f, hw, c, dtype=torch.float16, device=q.device)
+    check(lib().l2d_warmup_attn(ptr(q), ptr(k), ptr(v), qkv_ld if qkv_ld is not None else c, ptr(kv_cache_row), ptr(q_pe),
+                                ptr(k_pe), ptr(v_pe), pe_ld if pe_ld is not None else c, ptr(out), c, f, hw,
+                                kv_cache_row.shape[2], c, heads, current_stream()))
+    return out
+
+
 def layernorm(x, gamma, beta, eps=1e-5):
     _chk(x, "x")
     y = torch.empty_like(x)

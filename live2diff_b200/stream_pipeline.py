@@ -93,6 +93,35 @@ class B200StreamPipeline:
             pe = pe[None]
         self.prompt_embeds = (pe if pe.shape[0] == self.n else pe[:1].repeat(self.n, 1, 1)).contiguous()   # :231
 
+    @torch.no_grad()
+    def warmup(self, unet_warmup, x_t_latent: torch.Tensor, depth_latent: torch.Tensor,
+               noise: Optional[Sequence[torch.Tensor]] = None) -> torch.Tensor:
+        """The denoising loop of the reference's warm-up (pipeline:315-338) after `prepare()`: one pass of the
+        warm-up UNet per denoise row idx over the clip x_t_latent / depth_latent [1,4,F,h,w], each filling sink
+        slots 0..F-1 of row idx of every cache; between passes x_t = sqrt(abar)[idx+1] x0 + sqrt(1-abar)[idx+1] randn.
+        Returns x_0_pred as [F,4,h,w] (what the reference hands to the VAE decoder, :341-342).  `noise[idx]`
+        overrides the generator for the re-noise after pass idx (parity tests)."""
+        c = self.consts_host
+        x_t = x_t_latent.to(device=self.device, dtype=torch.float16).contiguous()
+        dep = depth_latent.to(device=self.device, dtype=torch.float16).contiguous()
+        if x_t.shape[2] != self.warmup:
+            raise ValueError(f"warm-up clip has {x_t.shape[2]} frames, the schedule expects {self.warmup} sink slots")
+        x0 = None
+        for idx, t in enumerate(c.timesteps):
+            out = unet_warmup(x_t, torch.tensor([t], dtype=torch.int64, device=self.device), temporal_attention_mask=None,
+                              depth_sample=dep, encoder_hidden_states=self.prompt_embeds[0:1],
+                              kv_cache=[cache[idx] for cache in self.kv_cache_list], return_dict=True)
+            consts = torch.tensor([[c.sqrt_abar[idx]], [c.sqrt_1m_abar[idx]], [c.c_skip[idx]], [c.c_out[idx]]],
+                                  dtype=torch.float32, device=self.device)
+            x0, _, _ = ops.lcm_step(x_t, out["sample"], consts)          # scheduler_step_batch(..., idx)  :330
+            if idx < self.n - 1:                                          # :331-337
+                eps = noise[idx].to(x0) if noise is not None else torch.randn(
+                    x0.shape, dtype=torch.float16, device=self.device, generator=self.generator)
+                a = torch.tensor(c.sqrt_abar[idx + 1], dtype=torch.float16, device=self.device)
+                b = torch.tensor(c.sqrt_1m_abar[idx + 1], dtype=torch.float16, device=self.device)
+                x_t = a * x0 + b * eps
+        return x0[0].transpose(0, 1).contiguous()                         # "b c f h w -> b f c h w"[0]  :341
+
     def _upload_schedule(self):
         s = self.schedule
         self._h_mask.copy_(torch.tensor(s.mask_rows(), dtype=torch.float16))

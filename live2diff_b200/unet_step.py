@@ -34,6 +34,44 @@ class UNetStepOutput(dict):
             raise AttributeError(k) from e
 
 
+def create_engine(state_dict: Dict[str, torch.Tensor], dims: UNetDims, n_rows: int, latent_h: int, latent_w: int,
+                  ctx_len: int, use_cuda_graph: bool, warmup_frames: int, device: torch.device) -> C.c_void_p:
+    """l2d_unet_create over the reference's state_dict (validated against `unet_param_spec`); the engine keeps
+    repacked copies, the caller keeps its tensors.  warmup_frames > 0 builds the warm-up engine (unet_warmup.py)."""
+    spec = unet_param_spec(dims)
+    missing = [k for k in spec if k not in state_dict]
+    if missing:
+        raise KeyError(f"state_dict is missing {len(missing)} tensors, e.g. {missing[:3]}")
+    named = {}
+    for k, shape in spec.items():
+        t = state_dict[k]
+        if tuple(t.shape) != tuple(shape):
+            raise ValueError(f"{k}: shape {tuple(t.shape)} != expected {tuple(shape)}")
+        named[k] = t.detach().to(device=device, dtype=torch.float16).contiguous()
+    cfg = L2DUnetConfig()
+    nlev = len(dims.block_out_channels)
+    cfg.n_levels = nlev
+    for i, c in enumerate(dims.block_out_channels):
+        cfg.block_out_channels[i] = c
+        cfg.down_has_attn[i] = int(dims.down_has_attn[i])
+        cfg.up_has_attn[i] = int(dims.up_has_attn[i])
+    cfg.layers_per_block, cfg.heads = dims.layers_per_block, dims.heads
+    cfg.cross_attention_dim, cfg.ctx_len, cfg.groups = dims.cross_attention_dim, ctx_len, dims.norm_groups
+    cfg.window, cfg.n_rows, cfg.latent_h, cfg.latent_w = dims.window_size, n_rows, latent_h, latent_w
+    for i, c in enumerate(dims.mapping_channels):
+        cfg.mapping_channels[i] = c
+    cfg.n_mapping = len(dims.mapping_channels)
+    cfg.norm_eps = dims.norm_eps
+    cfg.use_cuda_graph = int(use_cuda_graph)
+    cfg.warmup_frames = int(warmup_frames)
+    arr, keep = make_tensor_table(named)
+    handle = C.c_void_p()
+    with torch.cuda.device(device):
+        check(lib().l2d_unet_create(C.byref(handle), C.byref(cfg), arr, len(named)))
+    del named, arr, keep
+    return handle
+
+
 class B200UNetStep:
     def __init__(self, state_dict: Dict[str, torch.Tensor], dims: UNetDims, n_rows: int, latent_h: int, latent_w: int,
                  ctx_len: int = 77, use_cuda_graph: bool = True, device: Optional[torch.device] = None):
@@ -41,37 +79,7 @@ class B200UNetStep:
             raise RuntimeError("B200UNetStep needs a CUDA device; live2diff_b200 has no CPU fallback")
         self.dims, self.n_rows, self.h, self.w, self.ctx_len = dims, n_rows, latent_h, latent_w, ctx_len
         self.device = torch.device(device or "cuda")
-        spec = unet_param_spec(dims)
-        missing = [k for k in spec if k not in state_dict]
-        if missing:
-            raise KeyError(f"state_dict is missing {len(missing)} tensors, e.g. {missing[:3]}")
-        named = {}
-        for k, shape in spec.items():
-            t = state_dict[k]
-            if tuple(t.shape) != tuple(shape):
-                raise ValueError(f"{k}: shape {tuple(t.shape)} != expected {tuple(shape)}")
-            named[k] = t.detach().to(device=self.device, dtype=torch.float16).contiguous()
-        cfg = L2DUnetConfig()
-        nlev = len(dims.block_out_channels)
-        cfg.n_levels = nlev
-        for i, c in enumerate(dims.block_out_channels):
-            cfg.block_out_channels[i] = c
-            cfg.down_has_attn[i] = int(dims.down_has_attn[i])
-            cfg.up_has_attn[i] = int(dims.up_has_attn[i])
-        cfg.layers_per_block, cfg.heads = dims.layers_per_block, dims.heads
-        cfg.cross_attention_dim, cfg.ctx_len, cfg.groups = dims.cross_attention_dim, ctx_len, dims.norm_groups
-        cfg.window, cfg.n_rows, cfg.latent_h, cfg.latent_w = dims.window_size, n_rows, latent_h, latent_w
-        for i, c in enumerate(dims.mapping_channels):
-            cfg.mapping_channels[i] = c
-        cfg.n_mapping = len(dims.mapping_channels)
-        cfg.norm_eps = dims.norm_eps
-        cfg.use_cuda_graph = int(use_cuda_graph)
-        arr, keep = make_tensor_table(named)
-        handle = C.c_void_p()
-        with torch.cuda.device(self.device):
-            check(lib().l2d_unet_create(C.byref(handle), C.byref(cfg), arr, len(named)))
-        self._handle = handle
-        del named, arr, keep                      # the engine owns repacked copies
+        self._handle = create_engine(state_dict, dims, n_rows, latent_h, latent_w, ctx_len, use_cuda_graph, 0, self.device)
         self.dtype = torch.float16
         self.use_cuda_graph = use_cuda_graph
         dev = self.device

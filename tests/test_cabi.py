@@ -31,7 +31,7 @@ def test_library_exports_every_symbol():
     for name in header_functions():
         assert hasattr(handle, name), f"libl2d_b200.so does not export {name}"
     lib = _lib.lib()
-    assert lib.l2d_abi_version() == 1
+    assert lib.l2d_abi_version() == 2
     assert lib.l2d_launch_count() >= 0
 
 
