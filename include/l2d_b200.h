@@ -222,6 +222,10 @@ int l2d_unet_step(l2d_unet* u, const l2d_unet_step_args* args, void* stream);
 #define L2D_N_FAMILIES 6
 int l2d_unet_profile_step(l2d_unet* u, const l2d_unet_step_args* args, void* stream, float* ms_by_family,
                           int32_t* launches_by_family);
+/* Developer hook (profiles/ablate_families.py): skip every launch of the families whose bit (1 << family) is set -- plus
+ * bit 6 = LayerNorm only, bit 7 = GroupNorm only -- so that the drop in frame time measures that family's true cost on
+ * the graph's critical path.  Results are garbage while a mask is set; 0 restores the real step. */
+void l2d_unet_set_ablation(l2d_unet* u, int family_mask);
 /* Bytes of device memory owned by the engine (weights + workspace). */
 int64_t l2d_unet_device_bytes(const l2d_unet* u);
 /* Kernel launches per step (counted on the most recent step). */

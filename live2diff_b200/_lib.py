@@ -65,6 +65,7 @@ SIGNATURES = {
     "l2d_unet_create": (i32, [C.POINTER(vp), C.POINTER(L2DUnetConfig), C.POINTER(L2DTensor), i32]),
     "l2d_unet_step": (i32, [vp, C.POINTER(L2DUnetStepArgs), vp]),
     "l2d_unet_profile_step": (i32, [vp, C.POINTER(L2DUnetStepArgs), vp, C.POINTER(C.c_float), C.POINTER(C.c_int32)]),
+    "l2d_unet_set_ablation": (None, [vp, i32]),
     "l2d_unet_device_bytes": (i64, [vp]),
     "l2d_unet_launches_per_step": (i64, [vp]),
     "l2d_unet_destroy": (None, [vp]),

@@ -1,5 +1,6 @@
 // Error plumbing + misc exports of the C ABI (include/l2d_b200.h).
 #include <atomic>
+#include <cstdlib>
 
 #include "common.cuh"
 
@@ -14,6 +15,21 @@ int fail(int code, const std::string& msg) {
   return code;
 }
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+bool pdl_enabled() {
+  static const bool on = [] {
+    const char* e = getenv("L2D_PDL");
+    return !(e && e[0] == '0');
+  }();
+  return on;
+}
+
+bool pdl_family(int bit) {
+  static const int mask = [] {
+    const char* e = getenv("L2D_PDL_MASK");
+    return e ? atoi(e) : ~0;
+  }();
+  return (mask >> bit) & 1;
+}
 
 }  // namespace l2d
 

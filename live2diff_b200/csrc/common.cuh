@@ -5,6 +5,7 @@
 #include <stdint.h>
 
 #include <string>
+#include <utility>
 
 #include "../../include/l2d_b200.h"
 
@@ -38,6 +39,40 @@ void count_launch(int n = 1);
     }                                                                                           \
   } while (0)
 
+// ---- programmatic dependent launch (PDL) ------------------------------------------------------
+// A frame is ~850 dependent kernels of ~12 us each, so the launch -> CTA-scheduling -> prologue latency between two
+// kernels is a double-digit share of the frame.  Every hot kernel is launched with the programmatic-stream-serialization
+// attribute: it calls pdl_launch() first (lets the NEXT kernel's CTAs be scheduled as soon as all of this kernel's CTAs
+// have started) and pdl_wait() before it touches global memory that the previous kernel may still be reading or writing
+// (griddepcontrol.wait = the previous grid has completed and flushed).  Work that only touches memory no neighbouring
+// kernel writes (barrier init, TMEM allocation, tensor-map prefetch, K1's PE-window / KV-plane loads) runs before the
+// wait and overlaps the previous kernel's tail.  L2D_PDL=0 launches everything fully serialised (the waits are no-ops).
+bool pdl_enabled();
+bool pdl_family(int bit);   // L2D_PDL_MASK (developer): bit 0 gemm, 1 split-K finish, 2 flash, 3 K1, 4 GroupNorm, 5 LayerNorm
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl_if(bool use_pdl, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                                 Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = (use_pdl && pdl_enabled()) ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+}
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  return launch_pdl_if(true, kernel, grid, block, smem, st, std::forward<Args>(args)...);
+}
+#ifdef __CUDACC__
+__device__ __forceinline__ void pdl_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+#endif
+
 inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
 
@@ -54,6 +89,11 @@ __device__ __forceinline__ uint4 ldg_stream(const void* p) {  // read-once data:
   return r;
 }
 __device__ __forceinline__ uint4 ldg_cached(const void* p) { return __ldg(reinterpret_cast<const uint4*>(p)); }
+// Activations written by a neighbouring kernel: under PDL this kernel's lifetime overlaps its producer's, so the data
+// is NOT read-only for the kernel's lifetime and the non-coherent path (ld.global.nc / __ldg) may return stale L1 lines.
+// ld.global.cg reads at L2, the coherence point that griddepcontrol.wait orders against.  (Parameters -- weights, biases,
+// PE tables -- are constant for the whole step and keep the .nc path.)
+__device__ __forceinline__ uint4 ldg_act(const void* p) { return __ldcg(reinterpret_cast<const uint4*>(p)); }
 
 __device__ __forceinline__ __half2 u32_as_h2(uint32_t u) { return *reinterpret_cast<__half2*>(&u); }
 __device__ __forceinline__ uint32_t h2_as_u32(__half2 h) { return *reinterpret_cast<uint32_t*>(&h); }

@@ -182,6 +182,7 @@ struct Core {
   DevPool pool;
   cudaStream_t st = nullptr;
   int heads = 8, groups = 32, L = 16, n_rows = 2;
+  int skip_mask = 0;     // developer ablation (l2d_unet_set_ablation): families whose launches are skipped
   int warm_frames = 0;   // > 0: warm-up engine, the n_rows batch rows are the frames of one clip
   Scratch s;
   Profiler prof;
@@ -208,25 +209,30 @@ struct Core {
   int gemm_raw(const __half* a, int64_t lda, const __half* w, int64_t ldw, __half* out, int64_t ldo, int m, int n, int k,
                const __half* bias, const __half* rg, int64_t rg_ld, int rpg, const __half* residual, int64_t ldr, int act,
                int force_bn) {
+    if (skip_mask & (1 << FAM_GEMM)) return L2D_OK;
     Scope sc(*this, FAM_GEMM);
     return gemm_launch(a, lda, w, ldw, out, ldo, m, n, k, bias, rg, rg_ld, rpg, residual, ldr, act, force_bn, st);
   }
   // conv3x3 (pad 1, stride 1) over a channels-last tensor as an implicit GEMM (no im2col matrix)
   int conv3x3(const __half* x, int n_img, int h, int w, int cin, const __half* wt, __half* out, int64_t ldo, int cout,
               const __half* bias, const __half* rg, int64_t rg_ld, int rpg, const __half* residual, int64_t ldr, int act) {
+    if (skip_mask & (1 << FAM_GEMM)) return L2D_OK;
     Scope sc(*this, FAM_GEMM);
     return conv3x3_launch(x, n_img, h, w, cin, wt, out, ldo, cout, bias, rg, rg_ld, rpg, residual, ldr, act, st);
   }
   int kv(const KvAttnParams& p) {
+    if (skip_mask & (1 << FAM_KV)) return L2D_OK;
     Scope sc(*this, FAM_KV);
     return kv_attn_launch(p, st);
   }
   int attn(const __half* q, int64_t ldq, const __half* k, int64_t ldk, const __half* v, int64_t ldv, __half* o, int64_t ldo,
            int batch, int sq, int skv, int hd) {
+    if (skip_mask & (1 << FAM_ATTN)) return L2D_OK;
     Scope sc(*this, FAM_ATTN);
     return attention_launch(q, ldq, k, ldk, v, ldv, o, ldo, batch, heads, sq, skv, hd, st);
   }
   int im2col(const __half* x, __half* y, int n_img, int h, int w, int c, int stride, int up) {
+    if (skip_mask & (1 << FAM_IM2COL)) return L2D_OK;
     Scope sc(*this, FAM_IM2COL);
     return l2d_im2col3x3(x, y, n_img, h, w, c, stride, up, 0, st);
   }
@@ -313,11 +319,13 @@ struct Core {
     return gemm_raw(a, lda, l.w, l.k, out, ldo, m, l.n, l.k, l.b, nullptr, 0, 1, residual, ldr, act, force_bn);
   }
   int layernorm(const __half* x, const Norm& n, __half* y, int rows, int c) {
+    if (skip_mask & ((1 << FAM_NORM) | 64)) return L2D_OK;    // bit 6: LayerNorm only
     Scope sc(*this, FAM_NORM);
     return l2d_layernorm(x, n.g, n.b, y, rows, c, 1e-5f, st);
   }
   int gn(const __half* x1, int c1, const __half* x2, int c2, const Norm& n, __half* y, int n_img, int h, int w, float eps,
          int silu, int mode, int stride = 1) {
+    if (skip_mask & ((1 << (mode == 1 ? FAM_IM2COL : FAM_NORM)) | 128)) return L2D_OK;   // bit 7: GroupNorm only
     Scope sc(*this, mode == 1 ? FAM_IM2COL : FAM_NORM);   // the im2col variant is dominated by its 9x write
     return groupnorm_launch(x1, c1, x2, c2, n.g, n.b, y, s.gn_ws, n_img, h, w, groups, eps, silu, mode, stride, st);
   }
@@ -382,6 +390,7 @@ struct Core {
       p.q_pe = t.pe_tab[i]; p.k_pe = t.pe_tab[i] + c; p.v_pe = t.pe_tab[i] + 2 * c; p.pe_ld = 3 * c;
       p.mask = mask; p.pe_idx = pe_idx; p.update_idx = update_idx; p.out = s.att;
       p.n_rows = n_rows; p.hw = hw; p.L = L; p.C = c; p.heads = heads;
+      p.pdl = 1;   // behind the QKV GEMM: the kernel's cache / PE prefetch overlaps that GEMM's tail
       RC(kv(p));
       RC(gemm(s.att, c, t.out[i], s.t, c, m, s.t, c));
     }
@@ -1094,6 +1103,14 @@ extern "C" int l2d_unet_profile_step(l2d_unet* u, const l2d_unet_step_args* a, v
   return L2D_OK;
 }
 
+extern "C" void l2d_unet_set_ablation(l2d_unet* u, int family_mask) {
+  if (!u) return;
+  u->core.skip_mask = family_mask;
+  if (u->graph_exec) {   // the captured graph still holds the skipped launches
+    cudaGraphExecDestroy(u->graph_exec);
+    u->graph_exec = nullptr;
+  }
+}
 extern "C" int64_t l2d_unet_device_bytes(const l2d_unet* u) { return u ? u->core.pool.bytes : 0; }
 extern "C" int64_t l2d_unet_launches_per_step(const l2d_unet* u) { return u ? u->launches_per_step : 0; }
 extern "C" void l2d_unet_destroy(l2d_unet* u) { delete u; }

@@ -76,6 +76,8 @@ __global__ void __launch_bounds__(128) flash_attn_kernel(const FlashParams p) {
   __half* sK = sQ + FA_BM * HDP;
   __half* sV = sK + 2 * FA_BN * HDP;
 
+  pdl_launch();
+  pdl_wait();
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int b = blockIdx.z, h = blockIdx.y, m0 = blockIdx.x * FA_BM;
   const __half* gq = p.q + (size_t)b * p.sq * p.ldq + (size_t)h * p.hd;
@@ -232,7 +234,7 @@ static int launch_flash(const FlashParams& p, int batch, cudaStream_t st) {
     configured = true;
   }
   dim3 grid(ceil_div(p.sq, FA_BM), p.heads, batch);
-  flash_attn_kernel<HD><<<grid, 128, smem, st>>>(p);
+  launch_pdl_if(pdl_family(2), flash_attn_kernel<HD>, grid, dim3(128), smem, st, p);
   L2D_LAUNCH_CHECK();
   return L2D_OK;
 }

@@ -225,7 +225,7 @@ gemm_f16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid
   };
 
   long long* dbg = epi.dbg ? epi.dbg + (size_t)blockIdx.x * 8 : nullptr;   // timeline of this CTA's first tile
-  if (dbg && threadIdx.x == 0) dbg[0] = clock64();
+  pdl_launch();   // the setup below touches no global memory: it overlaps the previous kernel's tail (common.cuh)
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmap_a);
     prefetch_tmap(&tmap_b);
@@ -244,7 +244,10 @@ gemm_f16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
-  if (dbg && threadIdx.x == 0) dbg[1] = clock64();   // setup (barrier init, TMEM alloc) done
+  pdl_wait();     // operands, residual and the output buffer belong to the previous kernels until here
+  if (dbg && threadIdx.x == 0) {
+    dbg[0] = dbg[1] = clock64();   // (setup now precedes the wait and is not part of the timeline)
+  }
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -394,12 +397,12 @@ gemm_f16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid
           if (rg_ptr) {
             float b[8];
             if (lo_ok) {
-              unpack8(ldg_cached(rg_ptr + c0), b);
+              unpack8(ldg_act(rg_ptr + c0), b);
 #pragma unroll
               for (int e = 0; e < 8; ++e) v[e] += b[e];
             }
             if (hi_ok) {
-              unpack8(ldg_cached(rg_ptr + c0 + 8), b);
+              unpack8(ldg_act(rg_ptr + c0 + 8), b);
 #pragma unroll
               for (int e = 0; e < 8; ++e) v[8 + e] += b[e];
             }
@@ -493,6 +496,8 @@ gemm_f16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid
 
 // Second pass of a split-K GEMM: out[m, n0..n0+7] = epilogue(sum_z ws[z][m][n0..]) -- one thread per 8 columns
 __global__ void __launch_bounds__(256) splitk_finish_kernel(const GemmEpilogue epi, int M, int N, int splits) {
+  pdl_launch();
+  pdl_wait();
   const int n8 = N >> 3;
   const size_t total = (size_t)M * n8;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
@@ -512,7 +517,7 @@ __global__ void __launch_bounds__(256) splitk_finish_kernel(const GemmEpilogue e
     }
     if (epi.rowgroup_bias) {
       float b[8];
-      unpack8(ldg_cached(epi.rowgroup_bias + (size_t)(row / epi.rows_per_group) * epi.rg_ld + col), b);
+      unpack8(ldg_act(epi.rowgroup_bias + (size_t)(row / epi.rows_per_group) * epi.rg_ld + col), b);
 #pragma unroll
       for (int e = 0; e < 8; ++e) v[e] += b[e];
     }
@@ -705,7 +710,8 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmE
   const int tiles_n = ceil_div(N, BN);
   const int total = tiles_n * tiles_m * splits;
   const int grid = total < kNumSms ? total : kNumSms;
-  gemm_f16_tcgen05_kernel<BN, STAGES><<<grid, 320, smem, st>>>(ta, tb, e, cg, M, N, K, tiles_n, tiles_m, splits);
+  launch_pdl_if(pdl_family(0), gemm_f16_tcgen05_kernel<BN, STAGES>, dim3(grid), dim3(320), smem, st, ta, tb, e, cg, M, N, K, tiles_n, tiles_m,
+             splits);
   L2D_LAUNCH_CHECK();
   return L2D_OK;
 }
@@ -737,7 +743,7 @@ static int gemm_dispatch(const CUtensorMap& ta, const __half* w, int64_t ldw, co
   if (rc != L2D_OK || plan.splits == 1) return rc;
   const size_t work = (size_t)m * (n / 8);
   const int blocks = (int)std::min<size_t>((work + 255) / 256, (size_t)kNumSms * 8);
-  splitk_finish_kernel<<<blocks, 256, 0, st>>>(e, m, n, plan.splits);
+  launch_pdl_if(pdl_family(1), splitk_finish_kernel, dim3(blocks), dim3(256), 0, st, e, m, n, plan.splits);
   L2D_LAUNCH_CHECK();
   return L2D_OK;
 }

@@ -75,6 +75,8 @@ kv_attn_kernel(const KvAttnParams p, const int n_slots, const int slot_bytes, co
   uint64_t* bars = reinterpret_cast<uint64_t*>((reinterpret_cast<uintptr_t>(s_pi + KV_MAX_L) + 7) & ~uintptr_t(7));
   __shared__ int s_u;
 
+  pdl_launch();
+  pdl_wait();
   const int tid = threadIdx.x;
   const int total_tiles = tiles_per_row * p.n_rows;
   const int my_tiles = (total_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;  // tiles b, b+G, ...
@@ -150,9 +152,9 @@ kv_attn_kernel(const KvAttnParams p, const int n_slots, const int slot_bytes, co
     size_t row = 0;
     if (active) {
       row = (size_t)n * p.hw + pixel;
-      knew = ldg_cached(p.k_new + row * p.ld + (size_t)c * 8);
-      vnew = ldg_cached(p.v_new + row * p.ld + (size_t)c * 8);
-      uint4 qv4 = ldg_cached(p.q + row * p.ld + (size_t)c * 8);
+      knew = ldg_act(p.k_new + row * p.ld + (size_t)c * 8);
+      vnew = ldg_act(p.v_new + row * p.ld + (size_t)c * 8);
+      uint4 qv4 = ldg_act(p.q + row * p.ld + (size_t)c * 8);
       qv4 = hadd8(qv4, ldg_cached(p.q_pe + (size_t)s_pi[u] * p.pe_ld + (size_t)c * 8));   // q + Q_pe[pi[u]] -> fp16
       unpack8(qv4, qf);
       // PE-free append to HBM (stream_motion_module.py:117-119)
@@ -312,9 +314,9 @@ int kv_attn_launch(const KvAttnParams& p0, cudaStream_t stream) {
   const int total = tiles_per_row * p.n_rows;
   const int grid = total < g_num_sms ? total : g_num_sms;
   if (pe_regs)
-    kv_attn_kernel<true><<<grid, threads, smem, stream>>>(p, n_slots, slot_bytes, tiles_per_row);
+    launch_pdl_if(p.pdl != 0, kv_attn_kernel<true>, dim3(grid), dim3(threads), smem, stream, p, n_slots, slot_bytes, tiles_per_row);
   else
-    kv_attn_kernel<false><<<grid, threads, smem, stream>>>(p, n_slots, slot_bytes, tiles_per_row);
+    launch_pdl_if(p.pdl != 0, kv_attn_kernel<false>, dim3(grid), dim3(threads), smem, stream, p, n_slots, slot_bytes, tiles_per_row);
   L2D_LAUNCH_CHECK();
   return L2D_OK;
 }

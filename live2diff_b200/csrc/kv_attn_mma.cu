@@ -196,6 +196,7 @@ kv_attn_mma_kernel(const __grid_constant__ CUtensorMap tmap, const KvAttnParams 
     e_mask = __half2float(p.mask[(size_t)n0 * KM_L + tid]);
     e_u = static_cast<int>(p.update_idx[n0]);
   }
+  pdl_launch();
   if (tid == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap) : "memory");
     for (int b = 0; b < NB; ++b) {
@@ -284,8 +285,8 @@ kv_attn_mma_kernel(const __grid_constant__ CUtensorMap tmap, const KvAttnParams 
   auto load_kq = [&](int tile2) {
     const long long row = pixel_row(tile2);
     if (has_chunk && row >= 0) {
-      pf_k = ldg_cached(p.k_new + (size_t)row * p.ld + (size_t)cg * 8);
-      pf_q = ldg_cached(p.q + (size_t)row * p.ld + (size_t)cg * 8);
+      pf_k = ldg_act(p.k_new + (size_t)row * p.ld + (size_t)cg * 8);
+      pf_q = ldg_act(p.q + (size_t)row * p.ld + (size_t)cg * 8);
     }
   };
   // v is needed half a tile later than k / q and would pin four more registers for a whole tile: it is staged through
@@ -297,6 +298,10 @@ kv_attn_mma_kernel(const __grid_constant__ CUtensorMap tmap, const KvAttnParams 
     }
     asm volatile("cp.async.commit_group;" ::: "memory");   // one group per tile, also when empty: wait_group 1 below counts them
   };
+  // PDL: everything above -- and the producer warp's KV-plane TMA loads plus the PE-window staging below -- reads only
+  // memory that no neighbouring kernel writes (this module's cache, PE tables, schedule tensors) and overlaps the tail of
+  // the QKV GEMM; the freshly projected q / k / v, the cache slot append and the output row come after this wait.
+  pdl_wait();
   load_kq(t_begin);
   load_v(t_begin, 0);
 
@@ -558,7 +563,8 @@ int km_launch(const CUtensorMap& tm, const KvAttnParams& p, int tiles_per_row, i
     L2D_CUDA(cudaFuncSetAttribute(kv_attn_mma_kernel<CT, PT, NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = smem;
   }
-  kv_attn_mma_kernel<CT, PT, NB><<<grid, KM_THREADS, smem, stream>>>(tm, p, tiles_per_row, g_km_dbg);
+  launch_pdl_if(p.pdl != 0 && pdl_family(3), kv_attn_mma_kernel<CT, PT, NB>, dim3(grid), dim3(KM_THREADS), smem, stream, tm, p, tiles_per_row,
+                g_km_dbg);
   L2D_LAUNCH_CHECK();
   return L2D_OK;
 }

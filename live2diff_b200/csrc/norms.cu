@@ -18,6 +18,8 @@ constexpr int LN_MAXCH = 10;  // 16B chunks per lane -> C <= 2560
 __global__ void __launch_bounds__(256) layernorm_kernel(const __half* __restrict__ x, const __half* __restrict__ gamma,
                                                         const __half* __restrict__ beta, __half* __restrict__ y,
                                                         int rows, int C, float eps) {
+  pdl_launch();
+  pdl_wait();
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (warp >= rows) return;
@@ -29,7 +31,7 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const __half* __restrict
   for (int i = 0; i < LN_MAXCH; ++i) {
     const int ch = lane + i * 32;
     if (ch < nch) {
-      unpack8(ldg_cached(xr + ch * 8), v[i]);
+      unpack8(ldg_act(xr + ch * 8), v[i]);
 #pragma unroll
       for (int e = 0; e < 8; ++e) s += v[i][e];
     }
@@ -77,8 +79,8 @@ struct GnSrc {
 
 __device__ __forceinline__ uint4 gn_load_chunk(const GnSrc& s, size_t pix, int ch8) {
   const int c = ch8 * 8;
-  if (c < s.c1) return ldg_cached(s.x1 + pix * s.c1 + c);
-  return ldg_cached(s.x2 + pix * s.c2 + (c - s.c1));
+  if (c < s.c1) return ldg_act(s.x1 + pix * s.c1 + c);
+  return ldg_act(s.x2 + pix * s.c2 + (c - s.c1));
 }
 
 // workspace layout (floats): partial [N][GN_MAX_SPLIT][G][2] (mean, M2 of each slab) | ab [N][2][GN_MAX_C] (per-channel
@@ -106,8 +108,10 @@ __global__ void __launch_bounds__(512) groupnorm_stats_kernel(GnSrc src, const _
   const int p0 = sp * per, p1 = min(hw, p0 + per);
   float* s_sum = sm;
   float* s_sq = sm + C;
+  pdl_launch();
   for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) sm[i] = 0.f;
   __syncthreads();
+  pdl_wait();
   const int R = blockDim.x / nch;  // pixel lanes
   const int r = threadIdx.x / nch, ch = threadIdx.x - r * nch;
   if (r < R) {
@@ -162,33 +166,62 @@ __global__ void __launch_bounds__(512) groupnorm_stats_kernel(GnSrc src, const _
   __syncthreads();
   if (!s_last) return;
   __threadfence();
+  // Merge (Chan's formula as two weighted sums over the slabs).  Latency-bound: every lane first issues ALL of its
+  // partial loads (<= 8 independent 8-byte loads), so the merge costs one L2 round trip instead of one per slab batch.
+  // A group is handled by `lpg` lanes (16 when there are more groups than warps: two groups per warp, one pass).
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
   float* ab = gn_ab(ws, n_img, G, n);
-  for (int g = warp; g < G; g += nwarps) {   // one warp per group: two weighted sums over the slabs
+  const int lpg = G > nwarps ? 16 : 32, gpw = 32 / lpg;
+  const int sub = lane / lpg, l = lane - sub * lpg;
+  constexpr int MAXI = GN_MAX_SPLIT / 16;
+  for (int gb = warp * gpw; gb < G; gb += nwarps * gpw) {     // warp-uniform trip count
+    const int g = gb + sub;
+    const bool gv = g < G;
+    float cnt_s[MAXI], mu_s[MAXI], m2_s[MAXI];
+#pragma unroll
+    for (int i = 0; i < MAXI; ++i) {
+      const int s2 = l + lpg * i;
+      const bool v = gv && s2 < split;
+      const int q0 = s2 * per, q1 = min(hw, q0 + per);
+      cnt_s[i] = v ? (float)max(q1 - q0, 0) * (float)cpg : 0.f;
+      float2 pm = make_float2(0.f, 0.f);
+      if (v) pm = __ldcg(reinterpret_cast<const float2*>(partial + (((size_t)n * GN_MAX_SPLIT + s2) * G + g) * 2));
+      mu_s[i] = pm.x;
+      m2_s[i] = pm.y;
+    }
     float wsum = 0.f, wmean = 0.f;
-    for (int s2 = lane; s2 < split; s2 += 32) {
-      const int q0 = s2 * per, q1 = min(hw, q0 + per);
-      const float c = (float)max(q1 - q0, 0) * (float)cpg;
-      const float* src2 = partial + (((size_t)n * GN_MAX_SPLIT + s2) * G + g) * 2;
-      wsum += c;
-      wmean += c * __ldcg(src2);
+#pragma unroll
+    for (int i = 0; i < MAXI; ++i) {
+      wsum += cnt_s[i];
+      wmean = fmaf(cnt_s[i], mu_s[i], wmean);
     }
-    wsum = warp_sum(wsum);
-    const float mean = warp_sum(wmean) / wsum;
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1) {     // offsets < 16 stay inside a 16-lane half; the 32-lane case adds offset 16 below
+      wsum += __shfl_xor_sync(0xffffffffu, wsum, o);
+      wmean += __shfl_xor_sync(0xffffffffu, wmean, o);
+    }
+    if (lpg == 32) {
+      wsum += __shfl_xor_sync(0xffffffffu, wsum, 16);
+      wmean += __shfl_xor_sync(0xffffffffu, wmean, 16);
+    }
+    const float mean = wsum > 0.f ? wmean / wsum : 0.f;
     float m2 = 0.f;
-    for (int s2 = lane; s2 < split; s2 += 32) {
-      const int q0 = s2 * per, q1 = min(hw, q0 + per);
-      const float c = (float)max(q1 - q0, 0) * (float)cpg;
-      const float* src2 = partial + (((size_t)n * GN_MAX_SPLIT + s2) * G + g) * 2;
-      const float d = __ldcg(src2) - mean;
-      m2 += __ldcg(src2 + 1) + c * d * d;
+#pragma unroll
+    for (int i = 0; i < MAXI; ++i) {
+      const float d = mu_s[i] - mean;
+      m2 += m2_s[i] + cnt_s[i] * d * d;
     }
-    const float rstd = rsqrtf(warp_sum(m2) / wsum + eps);
-    for (int i = lane; i < cpg; i += 32) {
-      const int c = g * cpg + i;
-      const float ga = __half2float(gamma[c]) * rstd;
-      ab[c] = ga;
-      ab[GN_MAX_C + c] = __half2float(beta[c]) - mean * ga;
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1) m2 += __shfl_xor_sync(0xffffffffu, m2, o);
+    if (lpg == 32) m2 += __shfl_xor_sync(0xffffffffu, m2, 16);
+    if (gv) {
+      const float rstd = rsqrtf(m2 / wsum + eps);
+      for (int i = l; i < cpg; i += lpg) {
+        const int c = g * cpg + i;
+        const float ga = __half2float(gamma[c]) * rstd;
+        ab[c] = ga;
+        ab[GN_MAX_C + c] = __half2float(beta[c]) - mean * ga;
+      }
     }
   }
 }
@@ -204,9 +237,10 @@ struct GnApplyParams {
 };
 
 __device__ __forceinline__ void gn_norm8(float (&v)[8], const float* __restrict__ ab, int c0, int silu) {
-  const float4 a0 = __ldg(reinterpret_cast<const float4*>(ab + c0)), a1 = __ldg(reinterpret_cast<const float4*>(ab + c0 + 4));
-  const float4 b0 = __ldg(reinterpret_cast<const float4*>(ab + GN_MAX_C + c0));
-  const float4 b1 = __ldg(reinterpret_cast<const float4*>(ab + GN_MAX_C + c0 + 4));
+  // (written by the statistics kernel right before this one: coherent L2 reads, see ldg_act)
+  const float4 a0 = __ldcg(reinterpret_cast<const float4*>(ab + c0)), a1 = __ldcg(reinterpret_cast<const float4*>(ab + c0 + 4));
+  const float4 b0 = __ldcg(reinterpret_cast<const float4*>(ab + GN_MAX_C + c0));
+  const float4 b1 = __ldcg(reinterpret_cast<const float4*>(ab + GN_MAX_C + c0 + 4));
   const float A[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
   const float B[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
 #pragma unroll
@@ -217,6 +251,8 @@ __device__ __forceinline__ void gn_norm8(float (&v)[8], const float* __restrict_
 }
 
 __global__ void __launch_bounds__(256) groupnorm_apply_kernel(const GnApplyParams p) {
+  pdl_launch();
+  pdl_wait();
   const int C = p.src.c1 + p.src.c2;
   const int hw = p.h * p.w;
   const int n = blockIdx.y;
@@ -278,7 +314,7 @@ __global__ void __launch_bounds__(256) im2col3x3_kernel(const __half* __restrict
         iy >>= 1;
         ix >>= 1;
       }
-      o = ldg_cached(x + (((size_t)n * h + iy) * w + ix) * C + ch * 8);
+      o = ldg_act(x + (((size_t)n * h + iy) * w + ix) * C + ch * 8);
       if (silu) {
         float v[8];
         unpack8(o, v);
@@ -346,8 +382,12 @@ __global__ void __launch_bounds__(256) transpose_kernel(const __half* __restrict
 // ---------------------------------------------------------------------------------------------
 // launchers
 // ---------------------------------------------------------------------------------------------
-static int pick_split(int hw) {
-  int s = hw / 32;   // ~32 pixels per block: the per-thread pixel loop stays short (it is latency-bound)
+// The statistics pass is latency-bound (a launch moves <= 10 MB): pick the slab so that every thread issues ONE batch
+// of <= 4 independent 16-byte loads -- pixels per block = 4 x (pixel lanes per block) -- instead of looping.
+static int pick_split(int hw, int nch, int threads) {
+  const int lanes = threads / nch > 0 ? threads / nch : 1;
+  const int per_block = 4 * lanes;
+  int s = (hw + per_block - 1) / per_block;
   if (s < 1) s = 1;
   if (s > GN_MAX_SPLIT) s = GN_MAX_SPLIT;
   return s;
@@ -357,9 +397,9 @@ int groupnorm_launch(const __half* x1, int c1, const __half* x2, int c2, const _
                      __half* y, float* ws, int n_img, int h, int w, int G, float eps, int silu, int mode, int stride,
                      cudaStream_t st) {
   const int C = c1 + c2, hw = h * w, nch = C / 8;
-  const int split = pick_split(hw);
-  GnSrc src{x1, x2, c1, c2};
   const int threads = 512;
+  const int split = pick_split(hw, nch > 0 ? nch : 1, threads);
+  GnSrc src{x1, x2, c1, c2};
   if (nch > threads || C > GN_MAX_C) return fail(L2D_ERR_INVALID, "groupnorm: C > 4096");
   static size_t cfg_stats = 0;
   const size_t smem = (size_t)2 * C * sizeof(float);
@@ -367,13 +407,13 @@ int groupnorm_launch(const __half* x1, int c1, const __half* x2, int c2, const _
     L2D_CUDA(cudaFuncSetAttribute(groupnorm_stats_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     cfg_stats = smem;
   }
-  groupnorm_stats_kernel<<<dim3(split, n_img), threads, smem, st>>>(src, gamma, beta, ws, hw, G, split, eps);
+  launch_pdl_if(pdl_family(4), groupnorm_stats_kernel, dim3(split, n_img), dim3(threads), smem, st, src, gamma, beta, ws, hw, G, split, eps);
   L2D_LAUNCH_CHECK();
   GnApplyParams p{src, ws + (size_t)n_img * GN_MAX_SPLIT * G * 2, y, h, w, silu, mode, stride};
   size_t work = mode == 0 ? (size_t)hw * nch : (size_t)(h / stride) * (w / stride) * 9 * nch;
   int blocks = (int)std::min<size_t>((work + 255) / 256, 148 * 8);
   if (blocks < 1) blocks = 1;
-  groupnorm_apply_kernel<<<dim3(blocks, n_img), 256, 0, st>>>(p);
+  launch_pdl_if(pdl_family(4), groupnorm_apply_kernel, dim3(blocks, n_img), dim3(256), 0, st, p);
   L2D_LAUNCH_CHECK();
   return L2D_OK;
 }
@@ -388,8 +428,8 @@ extern "C" int l2d_layernorm(const void* x, const void* gamma, const void* beta,
   L2D_CHECK_ARG(channels % 8 == 0 && channels <= 8 * 32 * LN_MAXCH, "need C % 8 == 0 and C <= 2560");
   if (rows <= 0) return L2D_OK;
   const int blocks = ceil_div(rows, 8);
-  layernorm_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>((const __half*)x, (const __half*)gamma,
-                                                             (const __half*)beta, (__half*)y, rows, channels, eps);
+  launch_pdl_if(pdl_family(5), layernorm_kernel, dim3(blocks), dim3(256), 0, (cudaStream_t)stream, (const __half*)x, (const __half*)gamma,
+             (const __half*)beta, (__half*)y, rows, channels, eps);
   L2D_LAUNCH_CHECK();
   return L2D_OK;
 }

@@ -23,6 +23,8 @@ struct KvAttnParams {
   int P;    // pixels per block
   int hd8;  // chunks per head
   float scale;
+  int pdl;  // 1: launched behind the QKV GEMM inside the engine (reads of the cache / PE tables may precede the PDL wait);
+            // 0 (stand-alone l2d_kv_attn): fully serialised launch, the caller may have just written the cache
 };
 int kv_attn_launch(const KvAttnParams& p, cudaStream_t stream);
 bool kv_attn_mma_supported(const KvAttnParams& p);

@@ -94,7 +94,7 @@ class B200StreamPipeline:
         self.prompt_embeds = (pe if pe.shape[0] == self.n else pe[:1].repeat(self.n, 1, 1)).contiguous()   # :231
 
     @torch.no_grad()
-    def warmup(self, unet_warmup, x_t_latent: torch.Tensor, depth_latent: torch.Tensor,
+    def warmup_denoise(self, unet_warmup, x_t_latent: torch.Tensor, depth_latent: torch.Tensor,
                noise: Optional[Sequence[torch.Tensor]] = None) -> torch.Tensor:
         """The denoising loop of the reference's warm-up (pipeline:315-338) after `prepare()`: one pass of the
         warm-up UNet per denoise row idx over the clip x_t_latent / depth_latent [1,4,F,h,w], each filling sink

@@ -107,9 +107,9 @@ def test_device_stream_internal_noise_is_seeded_and_state_round_trips():
               for _ in range(9)]
     for f in range(5):
         oa, ob, oc = (s(*frames[f]).clone() for s in (a, b, c))
-        close(ob, oa, f"same seed frame {f}", tol=2e-3)
+        close(ob, oa, f"same seed frame {f}")                        # (GroupNorm's shared-memory atomics reorder sums run to run)
         if f >= 1:                                                    # frame 0 has no re-noised row yet
-            assert float((oc.float() - oa.float()).abs().max()) > 1e-3, "a different seed must change the stream"
+            assert float((oc.float() - oa.float()).abs().max()) > 5e-2, "a different seed must change the stream"
     blob = a.save_state()
     assert len(blob) > 2 * (N - 1) * 4 * H * W * 2
     # migrate stream a onto a fresh stream object d (different construction seed: the blob carries the seed)
@@ -120,7 +120,7 @@ def test_device_stream_internal_noise_is_seeded_and_state_round_trips():
     assert d.schedule() == a.schedule()
     for f in range(5, 9):
         oa, od = a(*frames[f]).clone(), d(*frames[f]).clone()
-        close(od, oa, f"migrated stream frame {f}", tol=2e-3)
+        close(od, oa, f"migrated stream frame {f}")
     assert d.schedule() == a.schedule() and a.schedule()["frame"] == 9
     # the re-noised buffer row is a[1] * x0 + b[1] * noise with noise ~ N(0,1): not degenerate
     buf = torch.frombuffer(bytearray(a.save_state()[-2 * (N - 1) * 4 * H * W * 2:-(N - 1) * 4 * H * W * 2]), dtype=torch.float16)

@@ -122,7 +122,7 @@ def test_unet_sd15_warmup_vs_oracle():
 
 
 def test_pipeline_warmup_loop_vs_oracle():
-    """B200StreamPipeline.warmup (pipeline:315-338): N passes with LCM x0 prediction and injected re-noise, against the
+    """B200StreamPipeline.warmup_denoise (pipeline:315-338): N passes with LCM x0 prediction and injected re-noise, against the
     same loop over the CPU oracle; then one streaming frame on the warmed caches."""
     from live2diff_b200.stream_pipeline import B200StreamPipeline
     from live2diff_b200.unet_step import B200UNetStep
@@ -140,7 +140,7 @@ def test_pipeline_warmup_loop_vs_oracle():
     x = torch.randn(1, 4, f, h, w, generator=gen).half()
     dep = torch.randn(1, 4, f, h, w, generator=gen).half()
     noise = [torch.randn(1, 4, f, h, w, generator=gen).half()]
-    x0 = pipe.warmup(warm, x.to(DEV), dep.to(DEV), noise=[z.to(DEV) for z in noise])
+    x0 = pipe.warmup_denoise(warm, x.to(DEV), dep.to(DEV), noise=[z.to(DEV) for z in noise])
     # oracle loop (fp32, fp16-rounded constants like the reference's prepare())
     od = odims(d)
     sub, c_skip, c_out, a, b = [v.half().float() if v.is_floating_point() else v for v in S.stream_constants([30, 40])]
