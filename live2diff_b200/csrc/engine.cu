@@ -211,6 +211,7 @@ struct Core {
                int force_bn) {
     if (skip_mask & (1 << FAM_GEMM)) return L2D_OK;
     Scope sc(*this, FAM_GEMM);
+    GemmConstWeights cw;
     return gemm_launch(a, lda, w, ldw, out, ldo, m, n, k, bias, rg, rg_ld, rpg, residual, ldr, act, force_bn, st);
   }
   // conv3x3 (pad 1, stride 1) over a channels-last tensor as an implicit GEMM (no im2col matrix)
@@ -218,6 +219,7 @@ struct Core {
               const __half* bias, const __half* rg, int64_t rg_ld, int rpg, const __half* residual, int64_t ldr, int act) {
     if (skip_mask & (1 << FAM_GEMM)) return L2D_OK;
     Scope sc(*this, FAM_GEMM);
+    GemmConstWeights cw;
     return conv3x3_launch(x, n_img, h, w, cin, wt, out, ldo, cout, bias, rg, rg_ld, rpg, residual, ldr, act, st);
   }
   int kv(const KvAttnParams& p) {

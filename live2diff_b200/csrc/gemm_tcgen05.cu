@@ -244,23 +244,37 @@ gemm_f16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
-  pdl_wait();     // operands, residual and the output buffer belong to the previous kernels until here
   if (dbg && threadIdx.x == 0) {
-    dbg[0] = dbg[1] = clock64();   // (setup now precedes the wait and is not part of the timeline)
+    dbg[0] = dbg[1] = clock64();   // (setup precedes the PDL wait and is not part of the timeline)
   }
 
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
+      // PDL: the B operand is a weight matrix (constant for the whole step), so the weight tiles of the first ring slots
+      // are requested while the previous kernel is still draining; the A tiles (activations written by that kernel)
+      // follow after the wait.  One expect_tx per slot covers both operands.
+      int pre = 0;
+      if (my_tiles > 0) {
+        const Tile t0 = decode(0);
+        pre = t0.num_kb < STAGES ? t0.num_kb : STAGES;
+        for (int kb = 0; kb < pre; ++kb) {
+          const uint32_t fb = smem_u32(&full_bar[kb]);
+          mbar_expect_tx(fb, S::STAGE_BYTES);
+          tma_load_2d(smem_u32(smem_b + kb * S::B_BYTES), &tmap_b, fb, (t0.kb_begin + kb) * BK, t0.n0);
+        }
+      }
+      pdl_wait();
       int it = 0;   // running k-block counter: the operand ring never drains between tiles
       for (int i = 0; i < my_tiles; ++i) {
         const Tile tl = decode(i);
         for (int kb = 0; kb < tl.num_kb; ++kb, ++it) {
           const int s = it % STAGES;
           const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
-          mbar_wait(smem_u32(&empty_bar[s]), ph ^ 1u);
+          const bool prefetched = it < pre;               // slot `it` of tile 0: expect_tx + B already issued above
+          if (!prefetched) mbar_wait(smem_u32(&empty_bar[s]), ph ^ 1u);
           const uint32_t fb = smem_u32(&full_bar[s]);
-          mbar_expect_tx(fb, S::STAGE_BYTES);
+          if (!prefetched) mbar_expect_tx(fb, S::STAGE_BYTES);
           const int kk = tl.kb_begin + kb;
           if (cg.enabled) {
             const int tap = kk / cg.cin_blocks, cb = kk - tap * cg.cin_blocks;
@@ -269,7 +283,7 @@ gemm_f16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid
           } else {
             tma_load_2d(smem_u32(smem_a + s * S::A_BYTES), &tmap_a, fb, kk * BK, tl.m0);
           }
-          tma_load_2d(smem_u32(smem_b + s * S::B_BYTES), &tmap_b, fb, kk * BK, tl.n0);
+          if (!prefetched) tma_load_2d(smem_u32(smem_b + s * S::B_BYTES), &tmap_b, fb, kk * BK, tl.n0);
         }
       }
     }
@@ -308,6 +322,7 @@ gemm_f16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid
     // ===================== epilogue (warps 2..9) =====================
     // 8 warps: warp w may touch TMEM lanes 32*(w%4)..+31 only, so two warps share each lane quarter and split the
     // tile's columns (h = 0: first half, h = 1: second half).
+    pdl_wait();                         // bias rows / residual / output belong to the previous kernels until here
     const int q = warp & 3;             // TMEM lane quarter
     const int h = (warp - 2) >> 2;      // column half handled by this warp
     constexpr int NCH = BN / 16;        // 16-column chunks of the tile
@@ -690,6 +705,11 @@ bool conv3x3_implicit_supported(int n_img, int h, int w, int cin) {
 
 static float* g_ws = nullptr;
 static long long* g_dbg = nullptr;
+// Set by the engine around its GEMM launches: the weight operand is engine-owned and constant, so the kernel may be
+// launched with PDL and fetch weight tiles before the PDL wait.  Stand-alone l2d_gemm / l2d_conv3x3 calls (the caller may
+// have just written `w`) launch fully serialised.
+static thread_local bool t_weights_constant = false;
+void gemm_weights_constant(bool on) { t_weights_constant = on; }
 
 static int ensure_splitk_workspace() {
   if (g_ws) return L2D_OK;
@@ -710,7 +730,7 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmE
   const int tiles_n = ceil_div(N, BN);
   const int total = tiles_n * tiles_m * splits;
   const int grid = total < kNumSms ? total : kNumSms;
-  launch_pdl_if(pdl_family(0), gemm_f16_tcgen05_kernel<BN, STAGES>, dim3(grid), dim3(320), smem, st, ta, tb, e, cg, M, N, K, tiles_n, tiles_m,
+  launch_pdl_if(pdl_family(0) && t_weights_constant, gemm_f16_tcgen05_kernel<BN, STAGES>, dim3(grid), dim3(320), smem, st, ta, tb, e, cg, M, N, K, tiles_n, tiles_m,
              splits);
   L2D_LAUNCH_CHECK();
   return L2D_OK;

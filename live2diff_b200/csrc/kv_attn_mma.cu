@@ -301,6 +301,42 @@ kv_attn_mma_kernel(const __grid_constant__ CUtensorMap tmap, const KvAttnParams 
   // PDL: everything above -- and the producer warp's KV-plane TMA loads plus the PE-window staging below -- reads only
   // memory that no neighbouring kernel writes (this module's cache, PE tables, schedule tensors) and overlaps the tail of
   // the QKV GEMM; the freshly projected q / k / v, the cache slot append and the output row come after this wait.
+  // per-row schedule + PE windows (block-uniform; all 8 math warps): Q_pe row and the K_pe / V_pe windows by cp.async
+  int cur_n = -1;
+  bool pe_pending = false;
+  auto stage_row = [&](int n) {
+    if (cur_n >= 0) km_bar(15, 256);                         // every group is done with the previous row's windows
+    if (tid < KM_L) {
+      if (cur_n >= 0) {
+        e_pi = static_cast<int>(p.pe_idx[(size_t)n * KM_L + tid]);
+        e_mask = __half2float(p.mask[(size_t)n * KM_L + tid]);
+        e_u = static_cast<int>(p.update_idx[n]);
+      }
+      s_pi[tid] = e_pi;
+      s_mask[tid] = e_mask;
+      if (tid == 0) s_misc[0] = e_u;
+    }
+    km_bar(15, 256);
+    // window slot j <- table row pe_idx[n][j], copied asynchronously (no registers, no wait here): the copies are
+    // queued ahead of the producer's first burst and land while the first K plane is in flight
+    const int u0 = s_misc[0];
+    for (int idx = tid; idx < KM_L * T; idx += 256) {
+      const int j = idx / T, c = idx - j * T;
+      const uint32_t off = km_off(j, c, KM_L);
+      km_cp_async16(km_smem_u32(pek + off), p.k_pe + (size_t)s_pi[j] * p.pe_ld + (size_t)c * 8);
+      km_cp_async16(km_smem_u32(pev + off), p.v_pe + (size_t)s_pi[j] * p.pe_ld + (size_t)c * 8);
+    }
+    for (int c = tid; c < T; c += 256)
+      km_cp_async16(km_smem_u32(s_qpe + (size_t)c * 8), p.q_pe + (size_t)s_pi[u0] * p.pe_ld + (size_t)c * 8);
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    if (cur_n < 0) {
+      __syncwarp();
+      if (lane == 0) km_mbar_arrive(go_bar);
+    }
+    pe_pending = true;
+    cur_n = n;
+  };
+  stage_row(t_begin / tiles_per_row);   // first row: queued before the PDL wait (and ahead of the producer's first burst)
   pdl_wait();
   load_kq(t_begin);
   load_v(t_begin, 0);
@@ -317,8 +353,6 @@ kv_attn_mma_kernel(const __grid_constant__ CUtensorMap tmap, const KvAttnParams 
       g_hi[m] = km_off(row + 1, ch, R) + hb;
     }
   }
-  int cur_n = -1;
-  bool pe_pending = false;
   const bool tl = dbg != nullptr && tid == 0;
   long long d_wait = 0, d_patch = 0, d_qk = 0, d_mid = 0, d_pv = 0, d_store = 0, d_t = 0, d_wv = 0, d_bar2 = 0, d_gather = 0;   // developer timeline
   auto stamp = [&](long long& acc) {
@@ -334,38 +368,7 @@ kv_attn_mma_kernel(const __grid_constant__ CUtensorMap tmap, const KvAttnParams 
     const int tile = t_begin + i;
     const int n = tile / tiles_per_row, p0 = (tile - n * tiles_per_row) * P;
     const bool active = p0 + pl < p.hw;
-    if (n != cur_n) {   // block-uniform: per-row schedule; PE windows and Q_pe row by cp.async (all 8 math warps)
-      if (cur_n >= 0) km_bar(15, 256);                         // every group is done with the previous row's windows
-      if (tid < KM_L) {
-        if (cur_n >= 0) {
-          e_pi = static_cast<int>(p.pe_idx[(size_t)n * KM_L + tid]);
-          e_mask = __half2float(p.mask[(size_t)n * KM_L + tid]);
-          e_u = static_cast<int>(p.update_idx[n]);
-        }
-        s_pi[tid] = e_pi;
-        s_mask[tid] = e_mask;
-        if (tid == 0) s_misc[0] = e_u;
-      }
-      km_bar(15, 256);
-      // window slot j <- table row pe_idx[n][j], copied asynchronously (no registers, no wait here): the copies are
-      // queued ahead of the producer's first burst and land while the first K plane is in flight
-      const int u0 = s_misc[0];
-      for (int idx = tid; idx < KM_L * T; idx += 256) {
-        const int j = idx / T, c = idx - j * T;
-        const uint32_t off = km_off(j, c, KM_L);
-        km_cp_async16(km_smem_u32(pek + off), p.k_pe + (size_t)s_pi[j] * p.pe_ld + (size_t)c * 8);
-        km_cp_async16(km_smem_u32(pev + off), p.v_pe + (size_t)s_pi[j] * p.pe_ld + (size_t)c * 8);
-      }
-      for (int c = tid; c < T; c += 256)
-        km_cp_async16(km_smem_u32(s_qpe + (size_t)c * 8), p.q_pe + (size_t)s_pi[u0] * p.pe_ld + (size_t)c * 8);
-      asm volatile("cp.async.commit_group;" ::: "memory");
-      if (cur_n < 0) {
-        __syncwarp();
-        if (lane == 0) km_mbar_arrive(go_bar);
-      }
-      pe_pending = true;
-      cur_n = n;
-    }
+    if (n != cur_n) stage_row(n);
     const int u = s_misc[0];
     const int sK = 2 * i, sV = 2 * i + 1;
     const int bK = sK % NB, bV = sV % NB;

@@ -53,6 +53,11 @@ int groupnorm_launch(const __half* x1, int c1, const __half* x2, int c2, const _
                      cudaStream_t st);
 
 int gemm_pick_tile_n(int m, int n, int k);
+void gemm_weights_constant(bool on);   // thread-local: the following GEMM launches read engine-owned (constant) weights
+struct GemmConstWeights {
+  GemmConstWeights() { gemm_weights_constant(true); }
+  ~GemmConstWeights() { gemm_weights_constant(false); }
+};
 int gemm_launch(const __half* a, int64_t lda, const __half* w, int64_t ldw, __half* out, int64_t ldo, int m, int n, int k,
                 const __half* bias, const __half* rowgroup_bias, int64_t rg_ld, int rows_per_group,
                 const __half* residual, int64_t ldr, int act, int force_bn, cudaStream_t st);
