@@ -3,16 +3,18 @@
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
 
 A "step" = one frame of the stream = one `predict_x0_batch`: stream-batch assembly, the whole UNet
-step (N=2 rows, 64x64 latent, L=16 KV window, SD1.5 widths, fp16), the LCM x0 prediction and the
-buffer shift.  VAE/MiDaS are outside the hot path.  Synthetic latents, seeded random
+step (N=2 rows, 64x64 latent, L=16 KV window, SD1.5 widths, fp16), the LCM x0 prediction with re-noise, the
+buffer shift and the ring-schedule advance -- by default through `B200DeviceStream` (state resident in HBM,
+one CUDA graph per frame; `--pipeline host` selects the host-scheduled `B200StreamPipeline`).  VAE/MiDaS are outside the hot path.  Synthetic latents, seeded random
 weights with the real shapes (no checkpoints can be downloaded here).
 
 Printed JSON (one line, rank 0):
   value        frames/s with inputs resident in HBM, CUDA-event timed, max over ranks, all ranks' frames
-  e2e          frames/s through the public API from pinned HOST buffers (H2D of x_t + depth latent, step,
-               D2H of x0, sync) -- the number to compare with the reference arm
+  e2e          frames/s through the public API from pinned HOST buffers (H2D of x_t + depth latent, frame graph,
+               D2H of x0 into pinned memory, stream sync per frame) -- the number to compare with the reference arm
   roofline     the temporal KV-cache attention kernel (K1): algorithmic bytes / CUDA-event time of its 40
-               launches inside a real step, against the measured HBM peak (MEASURED_PEAKS.json)
+               launches inside a real (eager, event-bracketed) step, against the measured HBM peak
+               (MEASURED_PEAKS.json); `traffic` = ncu DRAM bytes per launch (profiles/k1_traffic.json)
   cpu_baseline the oracle (CPU restatement of the reference UNet step, torch fp32) on the host cores
 With --impl reference the same workload runs on the CPU oracle port only (rank 0), same JSON shape.
 Multi-GPU: one independent stream per rank (weak scaling); the only collective is the
