@@ -47,8 +47,8 @@ def test_host_schedule_matches_python_ring_schedule():
     for n, L, w0 in ((2, 16, 8), (4, 32, 8), (1, 4, 2), (3, 8, 7)):
         rs = RingSchedule(n, L, w0)
         for valid, pe, up in run_schedule(n, L, w0, 3 * L):
-            if n > 1:                                   # N == 1: the reference has no defined initial state (SURVEY A-1)
-                assert (valid, pe, up) == (rs.valid, rs.pe_idx, rs.update_idx)
+            # (N == 1: the reference's initialiser raises, SURVEY A-1; both implementations guard it the same way)
+            assert (valid, pe, up) == (rs.valid, rs.pe_idx, rs.update_idx)
             rs.advance()
 
 
@@ -81,3 +81,42 @@ def test_stream_randn_is_standard_normal_and_keyed():
     assert np.array_equal(a, draw(2, 0, 0))                                              # deterministic
     for other in (draw(3, 0, 0), draw(2, 1, 0), draw(2, 0, 1)):                          # seed / frame / row all key it
         assert abs(np.corrcoef(a, other)[0, 1]) < 0.02
+
+
+def test_config1_plumbing_stream_on_the_oracle():
+    """BASELINE configs[0] geometry -- 1 denoise step, KV window 4 with 2 sink slots, CPU fp32 -- through the stream
+    oracle (tiny channel widths keep it to seconds): fill phase, first wrap and steady state of a single-row stream;
+    the oracle's tensor schedule, the Python RingSchedule and the device schedule code agree frame by frame."""
+    import torch
+
+    from live2diff_b200.schedule import RingSchedule
+    from live2diff_b200.weights import UNetDims, random_state_dict
+    from oracle import schedule_oracle as S
+    from oracle import unet_oracle as O
+
+    d = UNetDims(block_out_channels=(32, 64, 64, 64), cross_attention_dim=64, window_size=4, sink_size=2, pe_max_len=24)
+    od = O.UNetDims(**d.__dict__)
+    sd = random_state_dict(d, seed=3)
+    n, h, w = 1, 8, 8
+    gen = torch.Generator().manual_seed(0)
+    kv = O.alloc_kv_cache(od, n, h, w)
+    for c in kv:
+        c[:, :, :, :2] = torch.randn(c[:, :, :, :2].shape, generator=gen)
+    prompt = torch.randn(n, 77, 64, generator=gen)
+    orc = S.StreamOracle(lambda s_, t, **kw: O.unet_forward(sd, od, s_, t, kw["encoder_hidden_states"],
+                                                            kw["temporal_attention_mask"], kw["depth_sample"],
+                                                            kw["kv_cache"], kw["pe_idx"], kw["update_idx"]),
+                         kv, prompt, [40], (h, w), window=4, warmup=2)
+    rs = RingSchedule(n, 4, 2)
+    dev_sched = run_schedule(n, 4, 2, 8)
+    outs = []
+    for f in range(8):
+        valid, pe, up = next(dev_sched)
+        assert (valid, pe, up) == (rs.valid, rs.pe_idx, rs.update_idx) == (
+            (orc.attn_bias == 0).sum(1).tolist(), orc.pe_idx.tolist(), orc.update_idx.tolist()), f
+        x0 = orc.step(torch.randn(1, 4, 1, h, w, generator=gen), torch.randn(1, 4, 1, h, w, generator=gen), None)
+        assert x0.shape == (1, 4, 1, h, w) and torch.isfinite(x0).all()
+        outs.append(x0)
+        rs.advance()
+    assert rs.valid == [4] and sorted(rs.pe_idx[0]) == [0, 1, 2, 3]
+    assert float((outs[-1] - outs[-2]).abs().max()) > 0                      # a live stream, not a constant
