@@ -333,7 +333,7 @@ def run_native(args):
         tp = os.path.join(ROOT, "profiles", "k1_traffic.json")
         if os.path.exists(tp):
             traffic = json.load(open(tp)).get("dram_bytes_per_launch_avg")     # ncu dram read+write, per launch
-        roofline = {"kernel": "kv_attn_kernel (K1, 40 launches/step)", "bound": "hbm", "achieved": achieved,
+        roofline = {"kernel": "kv_attn_mma_kernel (K1, 40 launches/step)", "bound": "hbm", "achieved": achieved,
                     "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak, "peak_source": which,
                     "algorithmic_bytes_per_step": k1_bytes, "algorithmic_bytes_per_launch": k1_bytes / fam_cnt["kv_attn"],
                     "ms_per_step_in_kernel": k1_ms, "us_per_launch": k1_ms * 1e3 / fam_cnt["kv_attn"], "traffic": traffic}
