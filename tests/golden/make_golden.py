@@ -364,6 +364,43 @@ def gen_unet_tiny_warmup(seed=3, h=16, w=16, n_rows=2, stream_frames=3):
     print("unet_tiny_warmup.pt", float(torch.stack(ys).abs().mean()), float(torch.stack(sy).abs().mean()))
 
 
+def gen_unet_sd15_widths(frames=3, seed=0, h=16, w=16, n_rows=2):
+    """The reference's streaming UNet at the REAL SD1.5 widths (320/640/1280/1280, head dims 40/80/160, 1.28 G
+    parameters) on a small 16x16 latent: pins the oracle at the channel geometry the GPU engine runs (the tiny fixture
+    covers the topology, this one the widths).  Weights = live2diff_b200.weights.random_state_dict(seed) -- the same
+    ones the GPU parity tests and bench.py use; only inputs, outputs and cache checksums are stored."""
+    from live2diff_b200.weights import random_state_dict
+
+    d = UNetDims()
+    sd = random_state_dict(d, seed=seed)
+    u = build_ref_unet(d)
+    u.load_state_dict(sd, strict=True)
+    u.eval()
+    u.set_info_for_attn(h, w)
+    kv = u.prepare_cache(n_rows)
+    g = torch.Generator().manual_seed(seed + 101)
+    for c in kv:
+        c[:, :, :, : d.sink_size] = torch.randn(c[:, :, :, : d.sink_size].shape, generator=g)
+    ctx = torch.randn(n_rows, 77, d.cross_attention_dim, generator=g)
+    t = torch.tensor([399, 199])
+    xs, ds, ys = [], [], []
+    for mask, pe_idx, update_idx in run_schedule(n_rows, d.window_size, d.sink_size, frames):
+        x = torch.randn(n_rows, 4, 1, h, w, generator=g)
+        dep = torch.randn(n_rows, 4, 1, h, w, generator=g)
+        o = u(x, t, encoder_hidden_states=ctx, temporal_attention_mask=mask, depth_sample=dep, kv_cache=kv,
+              pe_idx=pe_idx, update_idx=update_idx)
+        xs.append(x)
+        ds.append(dep)
+        ys.append(o["sample"].clone())
+    probe = {i: kv[i][:, :, :4, d.sink_size:d.sink_size + frames + 1].clone() for i in (0, 13, 26, 39)}
+    torch.save({"seed": seed, "h": h, "w": w, "n_rows": n_rows, "timesteps": t, "ctx": ctx,
+                "fingerprint": spec_fingerprint({k: sd[k] for k in list(sd)[:40]}),
+                "x": torch.stack(xs), "depth": torch.stack(ds), "y": torch.stack(ys),
+                "kv_abs_sums": torch.tensor([float(c.double().abs().sum()) for c in kv]), "kv_probe": probe},
+               os.path.join(HERE, "unet_sd15_widths.pt"))
+    print("unet_sd15_widths.pt", float(torch.stack(ys).abs().mean()), float(torch.stack(ys).abs().max()))
+
+
 def gen_specs():
     for tag, d in (("tiny", TINY), ("sd15", UNetDims())):
         u = build_ref_unet(d, device="meta")
@@ -380,6 +417,9 @@ def gen_warmup():
 
 
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "sd15":        # only the SD1.5-width fixture (needs ~15 GB of host memory)
+        gen_unet_sd15_widths()
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "warmup":      # only the warm-up fixtures (the others are unchanged)
         gen_warmup()
         sys.exit(0)

@@ -99,6 +99,36 @@ def test_unet_tiny_stream_matches_reference():
     torch.testing.assert_close(kv[39][0, :, :64], g["kv_final_39_row0"], **TOL)
 
 
+def test_unet_sd15_widths_matches_reference():
+    """The oracle at the real SD1.5 widths (1.28 G parameters, head dims 40/80/160) on a 16x16 latent, against the
+    fixture from the reference's UNet3DConditionStreamingModel loaded with the very weights the GPU parity tests and
+    bench.py use (`random_state_dict(UNetDims(), seed=0)`): reference <-> oracle here, oracle <-> CUDA engine at the same
+    widths in tests/test_modules_gpu.py."""
+    from live2diff_b200.weights import random_state_dict, spec_fingerprint
+
+    g = load_golden("unet_sd15_widths.pt")
+    d = UNetDims()
+    od = odims(d)
+    sd = random_state_dict(d, seed=g["seed"])
+    fp = spec_fingerprint({k: sd[k] for k in list(sd)[:40]})
+    assert abs(fp - g["fingerprint"]) <= 1e-9 * abs(g["fingerprint"]), "seeded weights differ from the fixture's"
+    n, h, w = g["n_rows"], g["h"], g["w"]
+    kv = O.alloc_kv_cache(od, n, h, w)
+    gen = torch.Generator().manual_seed(g["seed"] + 101)
+    for c in kv:
+        c[:, :, :, : d.sink_size] = torch.randn(c[:, :, :, : d.sink_size].shape, generator=gen)
+    ctx = torch.randn(n, 77, d.cross_attention_dim, generator=gen)
+    torch.testing.assert_close(ctx, g["ctx"])
+    frames = g["x"].shape[0]
+    for f, (mask, pe_idx, update_idx) in enumerate(schedule_frames(n, d.window_size, d.sink_size, frames)):
+        y = O.unet_forward(sd, od, g["x"][f], g["timesteps"], ctx, mask, g["depth"][f], kv, pe_idx, update_idx)
+        torch.testing.assert_close(y, g["y"][f], rtol=5e-4, atol=1e-4)
+    torch.testing.assert_close(torch.tensor([float(c.double().abs().sum()) for c in kv]), g["kv_abs_sums"], rtol=1e-4,
+                               atol=1e-2)
+    for i, ref in g["kv_probe"].items():
+        torch.testing.assert_close(kv[i][:, :, :4, d.sink_size:d.sink_size + frames + 1], ref, rtol=5e-4, atol=1e-4)
+
+
 @pytest.mark.parametrize("tag", ["c64_f8", "c320_f8", "c128_f2_L4"])
 def test_warmup_attention_matches_reference(tag):
     """VersatileAttention (bidirectional, writes cache slots 0..F-1) -- SURVEY.md §8f-1."""
