@@ -93,6 +93,41 @@ def test_unet_tiny_stream_vs_reference_golden():
     referee(sums, g["kv_sums"], sums16, "unet_tiny kv sums", slack=3.0, floor=2e-3)
 
 
+def test_unet_sd15_widths_vs_reference_golden():
+    """The engine at the real SD1.5 widths against OUTPUTS OF THE REFERENCE ITSELF (fixture unet_sd15_widths.pt: the
+    reference's UNet3DConditionStreamingModel with `random_state_dict(UNetDims(), seed=0)` on a 16x16 latent, 3 frames of
+    the fill phase).  The small latent also exercises the degenerate geometries: 2x2 pixels at the last level."""
+    from live2diff_b200.unet_step import B200UNetStep
+
+    g = load_golden("unet_sd15_widths.pt")
+    d = UNetDims()
+    n, h, w = g["n_rows"], g["h"], g["w"]
+    sd = random_state_dict(d, seed=g["seed"])
+    unet = B200UNetStep(sd, d, n, h, w, use_cuda_graph=False)
+    sd16 = {k: v.to(DEV).half() for k, v in sd.items()}
+    del sd
+    kv = unet.prepare_cache(n)
+    kv16 = [torch.zeros_like(c) for c in kv]
+    gen = torch.Generator().manual_seed(g["seed"] + 101)
+    for c, c16 in zip(kv, kv16):
+        r = torch.randn(c[:, :, :, : d.sink_size].shape, generator=gen).half().to(DEV)
+        c[:, :, :, : d.sink_size] = r
+        c16[:, :, :, : d.sink_size] = r
+    ctx = g["ctx"].half().to(DEV)
+    t = g["timesteps"].to(DEV)
+    for f, (mask, pe_idx, update_idx) in enumerate(frames(n, d.window_size, d.sink_size, g["x"].shape[0])):
+        x, dep = g["x"][f].half().to(DEV), g["depth"][f].half().to(DEV)
+        m16, pi, ui = mask.half().to(DEV), pe_idx.to(DEV), update_idx.to(DEV)
+        out = unet(x, t, depth_sample=dep, encoder_hidden_states=ctx, temporal_attention_mask=m16, kv_cache=kv,
+                   pe_idx=pi, update_idx=ui)["sample"]
+        y16 = O.unet_forward(sd16, odims(d), x, t, ctx, m16, dep, kv16, pi, ui)
+        referee(out, g["y"][f], y16, f"unet_sd15_widths frame {f}", slack=2.5)
+    fr = g["x"].shape[0]
+    for i, ref in g["kv_probe"].items():
+        referee(kv[i][:, :, :4, d.sink_size:d.sink_size + fr + 1], ref, kv16[i][:, :, :4, d.sink_size:d.sink_size + fr + 1],
+                f"unet_sd15_widths kv[{i}]", slack=2.5)
+
+
 def _unet_case(d, n, h, w, graph, steps, tag, t_list, kv_probe=(0, 13, 39)):
     from live2diff_b200.unet_step import B200UNetStep
 
