@@ -401,6 +401,33 @@ def gen_unet_sd15_widths(frames=3, seed=0, h=16, w=16, n_rows=2):
     print("unet_sd15_widths.pt", float(torch.stack(ys).abs().mean()), float(torch.stack(ys).abs().max()))
 
 
+def gen_unet_sd15_widths_warmup(seed=0, h=16, w=16):
+    """The reference's WARM-UP UNet at the real SD1.5 widths: one pass over an 8-frame clip on row 0 of zero caches."""
+    from live2diff_b200.weights import random_state_dict
+
+    d = UNetDims()
+    sd = random_state_dict(d, seed=seed)
+    uw = build_ref_warmup_unet(d)
+    uw.load_state_dict(sd, strict=True)
+    uw.eval()
+    uw.set_info_for_attn(h, w)
+    f = d.sink_size
+    rows = [torch.zeros(s_[1:]) for s_ in d.kv_cache_shapes(1, h, w)]
+    g = torch.Generator().manual_seed(seed + 202)
+    x = torch.randn(1, 4, f, h, w, generator=g)
+    dep = torch.randn(1, 4, f, h, w, generator=g)
+    ctx = torch.randn(1, 77, d.cross_attention_dim, generator=g)
+    t = torch.tensor([399])
+    y = uw(x, t, temporal_attention_mask=None, depth_sample=dep, encoder_hidden_states=ctx, kv_cache=rows,
+           return_dict=True)["sample"]
+    probe = {i: rows[i][:, :4, :f].clone() for i in (0, 13, 26, 39)}
+    torch.save({"seed": seed, "h": h, "w": w, "frames": f, "timestep": t, "ctx": ctx, "x": x, "depth": dep, "y": y.clone(),
+                "fingerprint": spec_fingerprint({k: sd[k] for k in list(sd)[:40]}),
+                "kv_abs_sums": torch.tensor([float(c.double().abs().sum()) for c in rows]), "kv_probe": probe},
+               os.path.join(HERE, "unet_sd15_widths_warmup.pt"))
+    print("unet_sd15_widths_warmup.pt", float(y.abs().mean()), float(y.abs().max()))
+
+
 def gen_specs():
     for tag, d in (("tiny", TINY), ("sd15", UNetDims())):
         u = build_ref_unet(d, device="meta")
@@ -419,6 +446,7 @@ def gen_warmup():
 if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "sd15":        # only the SD1.5-width fixture (needs ~15 GB of host memory)
         gen_unet_sd15_widths()
+        gen_unet_sd15_widths_warmup()
         sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "warmup":      # only the warm-up fixtures (the others are unchanged)
         gen_warmup()

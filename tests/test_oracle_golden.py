@@ -99,19 +99,46 @@ def test_unet_tiny_stream_matches_reference():
     torch.testing.assert_close(kv[39][0, :, :64], g["kv_final_39_row0"], **TOL)
 
 
+_SD15 = {}
+
+
+def sd15_weights(seed, fingerprint):
+    """`random_state_dict(UNetDims(), seed)` (1.28 G parameters, ~15 s to generate) shared by the SD1.5-width tests."""
+    from live2diff_b200.weights import random_state_dict, spec_fingerprint
+
+    if seed not in _SD15:
+        _SD15.clear()
+        _SD15[seed] = random_state_dict(UNetDims(), seed=seed)
+    sd = _SD15[seed]
+    fp = spec_fingerprint({k: sd[k] for k in list(sd)[:40]})
+    assert abs(fp - fingerprint) <= 1e-9 * abs(fingerprint), "seeded weights differ from the fixture's"
+    return sd
+
+
+def test_unet_sd15_widths_warmup_matches_reference():
+    """The warm-up pass of the oracle at the real SD1.5 widths against the reference's UNet3DConditionWarmupModel."""
+    g = load_golden("unet_sd15_widths_warmup.pt")
+    d = UNetDims()
+    od = odims(d)
+    sd = sd15_weights(g["seed"], g["fingerprint"])
+    rows = [torch.zeros(s_[1:]) for s_ in d.kv_cache_shapes(1, g["h"], g["w"])]
+    y = O.unet_forward_warmup(sd, od, g["x"], g["timestep"], g["ctx"], g["depth"], rows)
+    torch.testing.assert_close(y, g["y"], rtol=5e-4, atol=1e-4)
+    torch.testing.assert_close(torch.tensor([float(c.double().abs().sum()) for c in rows]), g["kv_abs_sums"], rtol=1e-4,
+                               atol=1e-2)
+    for i, ref in g["kv_probe"].items():
+        torch.testing.assert_close(rows[i][:, :4, : g["frames"]], ref, rtol=5e-4, atol=1e-4)
+
+
 def test_unet_sd15_widths_matches_reference():
     """The oracle at the real SD1.5 widths (1.28 G parameters, head dims 40/80/160) on a 16x16 latent, against the
     fixture from the reference's UNet3DConditionStreamingModel loaded with the very weights the GPU parity tests and
     bench.py use (`random_state_dict(UNetDims(), seed=0)`): reference <-> oracle here, oracle <-> CUDA engine at the same
     widths in tests/test_modules_gpu.py."""
-    from live2diff_b200.weights import random_state_dict, spec_fingerprint
-
     g = load_golden("unet_sd15_widths.pt")
     d = UNetDims()
     od = odims(d)
-    sd = random_state_dict(d, seed=g["seed"])
-    fp = spec_fingerprint({k: sd[k] for k in list(sd)[:40]})
-    assert abs(fp - g["fingerprint"]) <= 1e-9 * abs(g["fingerprint"]), "seeded weights differ from the fixture's"
+    sd = sd15_weights(g["seed"], g["fingerprint"])
     n, h, w = g["n_rows"], g["h"], g["w"]
     kv = O.alloc_kv_cache(od, n, h, w)
     gen = torch.Generator().manual_seed(g["seed"] + 101)

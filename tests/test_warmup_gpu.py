@@ -121,6 +121,30 @@ def test_unet_sd15_warmup_vs_oracle():
     print(f"[info] warm-up engine bytes={warm.device_bytes / 2**30:.2f} GiB")
 
 
+def test_unet_sd15_widths_warmup_vs_reference_golden():
+    """The warm-up engine at the real SD1.5 widths against OUTPUTS OF THE REFERENCE's UNet3DConditionWarmupModel
+    (fixture unet_sd15_widths_warmup.pt: 8-frame clip, 16x16 latent, row 0 of zero caches)."""
+    from helpers import load_golden
+    from live2diff_b200.unet_warmup import B200UNetWarmup
+
+    g = load_golden("unet_sd15_widths_warmup.pt")
+    d = UNetDims()
+    f, h, w = g["frames"], g["h"], g["w"]
+    sd = random_state_dict(d, seed=g["seed"])
+    warm = B200UNetWarmup(sd, d, f, h, w)
+    sd16 = {k: v.to(DEV).half() for k, v in sd.items()}
+    del sd
+    rows = [torch.zeros(s_[1:], dtype=torch.float16, device=DEV) for s_ in d.kv_cache_shapes(1, h, w)]
+    rows16 = [r.clone() for r in rows]
+    x, dep, ctx = g["x"].half().to(DEV), g["depth"].half().to(DEV), g["ctx"].half().to(DEV)
+    t = g["timestep"].to(DEV)
+    out = warm(x, t, depth_sample=dep, encoder_hidden_states=ctx, kv_cache=rows)["sample"]
+    y16 = O.unet_forward_warmup(sd16, odims(d), x, t, ctx, dep, rows16)
+    referee(out, g["y"], y16, "unet_sd15_widths warmup", slack=2.5)
+    for i, ref in g["kv_probe"].items():
+        referee(rows[i][:, :4, :f], ref, rows16[i][:, :4, :f], f"unet_sd15_widths warmup kv row[{i}]", slack=2.5)
+
+
 def test_pipeline_warmup_loop_vs_oracle():
     """B200StreamPipeline.warmup_denoise (pipeline:315-338): N passes with LCM x0 prediction and injected re-noise, against the
     same loop over the CPU oracle; then one streaming frame on the warmed caches."""
