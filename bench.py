@@ -1,24 +1,34 @@
-"""Benchmark of the hot path: streaming frames/s at 512x512, 2 denoise steps (BASELINE.json configs[1]).
+"""Benchmark of the hot path: streaming frames/s (BASELINE.json configs; default = configs[1], the headline).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--config 2|3|4] [--impl native|reference|torch-fp16]
 
-A "step" = one frame of the stream = one `predict_x0_batch`: stream-batch assembly, the whole UNet
-step (N=2 rows, 64x64 latent, L=16 KV window, SD1.5 widths, fp16), the LCM x0 prediction with re-noise, the
-buffer shift and the ring-schedule advance -- by default through `B200DeviceStream` (state resident in HBM,
-one CUDA graph per frame; `--pipeline host` selects the host-scheduled `B200StreamPipeline`).  VAE/MiDaS are outside the hot path.  Synthetic latents, seeded random
-weights with the real shapes (no checkpoints can be downloaded here).
+A "step" = one frame of the stream = one `predict_x0_batch`: stream-batch assembly, the whole UNet step (SD1.5 widths,
+fp16), the LCM x0 prediction with re-noise, the buffer shift and the ring-schedule advance -- by default through
+`B200DeviceStream` (state resident in HBM, one CUDA graph per frame; `--pipeline host` selects the host-scheduled
+`B200StreamPipeline`).  Synthetic latents, seeded random weights with the real shapes (no checkpoints can be downloaded).
+  --config 2   512x512 (64x64 latent), 2 denoise rows, KV window 16      (BASELINE configs[1], the metric's config)
+  --config 3   768x512 (64x96 latent), 2 denoise rows, KV window 16      (configs[2]; the depth latent is synthetic)
+  --config 4   512x512, 4 denoise rows, KV window 32 (long-cache stress) (configs[3])
 
 Printed JSON (one line, rank 0):
   value        frames/s with inputs resident in HBM, CUDA-event timed, max over ranks, all ranks' frames
   e2e          frames/s through the public API from pinned HOST buffers (H2D of x_t + depth latent, frame graph,
                D2H of x0 into pinned memory, stream sync per frame) -- the number to compare with the reference arm
-  roofline     the temporal KV-cache attention kernel (K1): algorithmic bytes / CUDA-event time of its 40
-               launches inside a real (eager, event-bracketed) step, against the measured HBM peak
-               (MEASURED_PEAKS.json); `traffic` = ncu DRAM bytes per launch (profiles/k1_traffic.json)
+  roofline     the temporal KV-cache attention kernel (K1): algorithmic bytes / CUDA-event time of its 40 launches
+               inside a real (eager, event-bracketed) step, against the measured HBM peak (MEASURED_PEAKS.json);
+               `frac_in_graph` = the same bytes / the kernel's marginal cost inside the whole-frame graph replay (frame
+               time with and without its launches, `l2d_unet_set_ablation`), where PDL overlaps its prologue with the
+               QKV GEMM's tail; `traffic` = ncu DRAM bytes per launch (profiles/k1_traffic.json, regenerated per round)
   cpu_baseline the oracle (CPU restatement of the reference UNet step, torch fp32) on the host cores
-With --impl reference the same workload runs on the CPU oracle port only (rank 0), same JSON shape.
-Multi-GPU: one independent stream per rank (weak scaling); the only collective is the
-NCCL broadcast of the prompt embedding before the timed region.
+  torch_fp16_eager / vs_torch_fp16_eager (N=1): the reference's evaluation order restated with torch ops, run EAGERLY
+               in fp16 on the same GPU (cuDNN / cuBLAS / SDPA kernels, host-synchronising ring schedule like the
+               reference's update_attn_bias) = the stand-in for "the reference, TensorRT off, fp16, on this box"
+               (the reference package itself cannot travel to the GPU box); BASELINE's target is >= 2x this.
+With --impl reference the same workload runs on the CPU oracle port only (rank 0: ONE CPU stream; the line says so in
+`streams`, so a multi-GPU ratio against it is N GPU streams vs 1 CPU stream); --impl torch-fp16 prints the eager-torch
+GPU arm alone, same JSON shape.
+Multi-GPU: one independent stream per rank (weak scaling); the only collective is the NCCL broadcast of the
+prompt embedding before the timed region.
 """
 import argparse
 import json
@@ -33,19 +43,84 @@ sys.path.insert(0, ROOT)
 
 import torch  # noqa: E402
 
-METRIC = "stream_fps_512x512_2step"
 UNIT = "frames/s"
-T_INDEX = [30, 40]
-LAT_H = LAT_W = 64
-WINDOW, WARMUP_SLOTS = 16, 8
+CONFIGS = {
+    2: dict(metric="stream_fps_512x512_2step", h=64, w=64, t_index=[30, 40], window=16, sink=8, pe_max=24,
+            name="BASELINE configs[1]: 512x512 stream (64x64 latent), 2 denoise steps (t_index [30,40] of 50), KV window 16 "
+                 "(8 sink + 8 rolling), SD1.5 UNet widths (320,640,1280,1280), fp16, steady state"),
+    3: dict(metric="stream_fps_768x512_2step", h=64, w=96, t_index=[30, 40], window=16, sink=8, pe_max=24,
+            name="BASELINE configs[2]: 768x512 stream (64x96 latent), 2 denoise steps, KV window 16, fp16, steady state; "
+                 "the depth latent is synthetic (the MiDaS prior is outside the UNet step)"),
+    4: dict(metric="stream_fps_512x512_4step_L32", h=64, w=64, t_index=[25, 31, 37, 43], window=32, sink=8, pe_max=32,
+            name="BASELINE configs[3]: 512x512 stream, 4 denoise steps (t_index [25,31,37,43]), KV window 32 "
+                 "(8 sink + 24 rolling; long-cache stress), fp16, steady state"),
+}
+CFG = CONFIGS[2]
 
 
-def workload_config(n_gpus):
-    return {"workload": "BASELINE configs[1]: 512x512 stream (64x64 latent), 2 denoise steps (t_index [30,40] of 50), "
-                        "KV window 16 (8 sink + 8 rolling), SD1.5 UNet widths (320,640,1280,1280), fp16, steady state",
-            "streams": n_gpus, "stream_batch_rows": 2, "latent": [LAT_H, LAT_W], "window": WINDOW,
-            "l2": "per-step working set (2.83 GiB KV cache + 2.56 GB weights) exceeds the 126 MB L2; no flush needed",
-            "parallelism": f"{n_gpus} independent stream replicas, 1 per GPU; prompt embedding broadcast once (NCCL)"}
+def unet_dims():
+    from live2diff_b200.weights import UNetDims
+
+    return UNetDims(window_size=CFG["window"], sink_size=CFG["sink"], pe_max_len=CFG["pe_max"])
+
+
+def workload_config(n_gpus, cpu_streams=None):
+    from live2diff_b200.weights import UNetDims  # noqa: F401
+
+    d = unet_dims()
+    n = len(CFG["t_index"])
+    kv_gib = sum(s[0] * s[1] * s[2] * s[3] * s[4] for s in d.kv_cache_shapes(n, CFG["h"], CFG["w"])) * 2 / 2 ** 30
+    return {"workload": CFG["name"],
+            "streams": n_gpus if cpu_streams is None else cpu_streams, "stream_batch_rows": n,
+            "latent": [CFG["h"], CFG["w"]], "window": CFG["window"],
+            "l2": f"per-step working set ({kv_gib:.2f} GiB KV cache + 2.56 GB weights) exceeds the 126 MB L2; no flush needed",
+            "parallelism": f"{n_gpus} independent stream replicas, 1 per GPU; prompt embedding broadcast once (NCCL)"
+                           if cpu_streams is None else f"{cpu_streams} CPU stream on rank 0 (N GPUs requested: {n_gpus})"}
+
+
+def unet_gemm_flops(d, n, h, w):
+    """Dense-contraction flops of one UNet step that run on the tcgen05 GEMM kernel (every Linear, 1x1 and 3x3 conv;
+    attention matmuls and the once-per-prompt projections excluded), counted from the layer shapes."""
+    c = d.block_out_channels
+    nlev = len(c)
+
+    def lin(m, k, nn):
+        return 2.0 * m * k * nn
+
+    def resnet(m, cin, cout):
+        return lin(m, 9 * cin, cout) + lin(m, 9 * cout, cout) + (lin(m, cin, cout) if cin != cout else 0.0)
+
+    m0 = n * h * w
+    mc = d.mapping_channels
+    fl = lin(m0, 64, c[0]) + lin(m0, 64, mc[0]) + lin(m0, 9 * mc[-1], c[0]) + lin(m0, 9 * c[0], 8)
+    for i in range(len(mc) - 1):
+        fl += lin(m0, 9 * mc[i], mc[i]) + lin(m0, 9 * mc[i], mc[i + 1])
+    out_ch = c[0]
+    for bi in range(nlev):
+        in_ch, out_ch = out_ch, c[bi]
+        m = n * (h >> bi) * (w >> bi)
+        for li in range(d.layers_per_block):
+            fl += resnet(m, in_ch if li == 0 else out_ch, out_ch) + 22 * lin(m, out_ch, out_ch)   # + temporal transformer
+            if d.down_has_attn[bi]:
+                fl += 20 * lin(m, out_ch, out_ch)                                                # spatial transformer
+        if bi != nlev - 1:
+            fl += lin(m // 4, 9 * out_ch, out_ch)
+    m = n * (h >> (nlev - 1)) * (w >> (nlev - 1))
+    fl += 2 * resnet(m, c[-1], c[-1]) + 20 * lin(m, c[-1], c[-1])
+    out_ch = c[-1]
+    for bi in range(nlev):
+        prev_out, out_ch = out_ch, c[nlev - 1 - bi]
+        in_ch = c[max(nlev - 2 - bi, 0)]
+        lvl = nlev - 1 - bi
+        m = n * (h >> lvl) * (w >> lvl)
+        for li in range(d.layers_per_block + 1):
+            fl += resnet(m, (prev_out if li == 0 else out_ch) + (in_ch if li == d.layers_per_block else out_ch), out_ch)
+            fl += 22 * lin(m, out_ch, out_ch)
+            if d.up_has_attn[bi]:
+                fl += 20 * lin(m, out_ch, out_ch)
+        if bi != nlev - 1:
+            fl += lin(m * 4, 9 * out_ch, out_ch)
+    return fl
 
 
 # --------------------------------------------------------------------------------------------------
@@ -142,41 +217,49 @@ def pick_cpu_threads():
     return best
 
 
+def _oracle_inputs(n, gen, device="cpu", dtype=torch.float32):
+    d = unet_dims()
+    x = torch.randn(n, 4, 1, CFG["h"], CFG["w"], generator=gen)
+    dep = torch.randn(n, 4, 1, CFG["h"], CFG["w"], generator=gen)
+    ctx = torch.randn(n, 77, d.cross_attention_dim, generator=gen)
+    return x.to(device=device, dtype=dtype), dep.to(device=device, dtype=dtype), ctx.to(device=device, dtype=dtype)
+
+
 def cpu_oracle_fps(steps, warmup, budget_s):
-    from live2diff_b200.weights import UNetDims, random_state_dict
+    from live2diff_b200.weights import random_state_dict
     from oracle import schedule_oracle as S
     from oracle import unet_oracle as O
 
     cores = pick_cpu_threads()
     torch.set_num_threads(cores)
-    d = UNetDims()
+    d = unet_dims()
     od = O.UNetDims(**d.__dict__)
     sd = random_state_dict(d, seed=0)
-    n = len(T_INDEX)
+    n = len(CFG["t_index"])
+    L, W0 = CFG["window"], CFG["sink"]
     gen = torch.Generator().manual_seed(1)
-    kv = O.alloc_kv_cache(od, n, LAT_H, LAT_W)
+    kv = O.alloc_kv_cache(od, n, CFG["h"], CFG["w"])
     for c in kv:
         c.normal_(generator=gen)
-    ab, pe, up = S.init_schedule(n, WINDOW, WARMUP_SLOTS)
-    for _ in range(3 * WINDOW):
-        S.update_schedule(ab, pe, up, WINDOW, WARMUP_SLOTS)
-    ctx = torch.randn(n, 77, d.cross_attention_dim, generator=gen)
-    sub, c_skip, c_out, a, b = S.stream_constants(T_INDEX)
-    x = torch.randn(n, 4, 1, LAT_H, LAT_W, generator=gen)
-    dep = torch.randn(n, 4, 1, LAT_H, LAT_W, generator=gen)
+    ab, pe, up = S.init_schedule(n, L, W0)
+    for _ in range(3 * L):
+        S.update_schedule(ab, pe, up, L, W0)
+    x, dep, ctx = _oracle_inputs(n, gen)
+    sub, c_skip, c_out, a, b = S.stream_constants(CFG["t_index"])
 
     def one():
         with torch.no_grad():
             eps = O.unet_forward(sd, od, x, sub, ctx, ab, dep, kv, pe, up)
             S.scheduler_step_batch(eps, x, c_skip, c_out, a, b)
-        S.update_schedule(ab, pe, up, WINDOW, WARMUP_SLOTS)
+        S.update_schedule(ab, pe, up, L, W0)
 
+    what = f"full UNet steps (N={n}, {CFG['h']}x{CFG['w']} latent, L={L}) of the CPU oracle, torch fp32, {cores} threads"
     t0 = time.perf_counter()
     one()                                           # first call (allocator / thread-pool warm-up), normally discarded
     first = time.perf_counter() - t0
     if first > budget_s:                            # bounded sample: do not spend minutes of box time on the CPU leg
-        sample = (f"1 full UNet step (N=2, 64x64 latent, L=16) of the CPU oracle, torch fp32, {cores} threads, first call "
-                  f"(no warm-up: it alone exceeded the {budget_s:.0f} s budget); {first:.2f} s/step")
+        sample = (f"1 of the {what}, first call (no warm-up: it alone exceeded the {budget_s:.0f} s budget); "
+                  f"{first:.2f} s/step")
         return 1.0 / first, first, cores, 1, sample
     w_eff = max(0, min(warmup - 1, int(budget_s * 0.2 / max(first, 1e-3))))
     for _ in range(w_eff):
@@ -186,8 +269,7 @@ def cpu_oracle_fps(steps, warmup, budget_s):
     for _ in range(k_eff):
         one()
     dt = (time.perf_counter() - t0) / k_eff
-    sample = (f"{k_eff} timed + {w_eff + 1} discarded full UNet steps (N=2, 64x64 latent, L=16) of the CPU oracle, "
-              f"torch fp32, {cores} threads; {dt:.2f} s/step")
+    sample = f"{k_eff} timed + {w_eff + 1} discarded {what}; {dt:.2f} s/step"
     return 1.0 / dt, dt, cores, k_eff, sample
 
 
@@ -196,14 +278,75 @@ def run_reference(args):
     if rank != 0:
         return
     fps, dt, cores, k_eff, sample = cpu_oracle_fps(args.steps, args.warmup, budget_s=150.0)
-    line = {"impl": "reference", "metric": METRIC, "value": fps, "unit": UNIT, "n_gpus": args.gpus, "steps": k_eff,
+    line = {"impl": "reference", "metric": CFG["metric"], "value": fps, "unit": UNIT, "n_gpus": args.gpus, "steps": k_eff,
             "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(args.gpus),
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(args.gpus, cpu_streams=1),
             "cpu_baseline": {"value": fps, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": fps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-            "gpu_launches": 0,
+            "gpu_launches": 0, "streams_measured": 1, "value_per_stream": fps,
             "note": "reference arm = the reference's UNet step restated for CPU (oracle/, torch fp32): the reference "
-                    "package itself hard-codes CUDA in its pipeline and is absent from the GPU box"}
+                    "package itself hard-codes CUDA in its pipeline and is absent from the GPU box.  ONE CPU stream on "
+                    "all usable host cores whatever --gpus says (the cores are shared, N CPU streams would each run 1/N "
+                    "as fast): at N > 1 compare this value with the native arm's value / n_gpus (per-stream)"}
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------------------------------
+# torch fp16 eager arm on the GPU (the measured stand-in for "reference, TensorRT off, fp16, same box")
+# --------------------------------------------------------------------------------------------------
+def torch_fp16_eager_fps(dev, steps, warmup):
+    """The reference's own evaluation order (oracle/unet_oracle.py restates live2diff's modules op by op with torch
+    calls) run eagerly in fp16 on `dev`: conv2d -> cuDNN, Linear -> cuBLAS, attention -> F.scaled_dot_product_attention,
+    the ring schedule advanced on the host with `.any()` syncs exactly like update_attn_bias (pipeline:416-438)."""
+    from live2diff_b200.weights import random_state_dict
+    from oracle import schedule_oracle as S
+    from oracle import unet_oracle as O
+
+    d = unet_dims()
+    od = O.UNetDims(**d.__dict__)
+    n = len(CFG["t_index"])
+    L, W0 = CFG["window"], CFG["sink"]
+    sd16 = {k: v.to(device=dev, dtype=torch.float16) for k, v in random_state_dict(d, seed=0).items()}
+    gen = torch.Generator().manual_seed(1)
+    kv = [torch.randn(s, device=dev, dtype=torch.float16) for s in d.kv_cache_shapes(n, CFG["h"], CFG["w"])]
+    x1, d1, ctx = _oracle_inputs(1, gen, dev, torch.float16)
+    noise = torch.randn(max(n - 1, 1), 4, 1, CFG["h"], CFG["w"], generator=gen).to(device=dev, dtype=torch.float16)
+    orc = S.StreamOracle(lambda sm, t, **kw: O.unet_forward(sd16, od, sm, t, kw["encoder_hidden_states"],
+                                                            kw["temporal_attention_mask"], kw["depth_sample"],
+                                                            kw["kv_cache"], kw["pe_idx"], kw["update_idx"]),
+                         kv, ctx.repeat(n, 1, 1), CFG["t_index"], (CFG["h"], CFG["w"]), window=L, warmup=W0,
+                         dtype=torch.float16, device=dev)
+    with torch.no_grad():
+        for _ in range(max(warmup, 3) + 2 * L):      # fill the ring: steady state like the native arm
+            orc.step(x1, d1, noise[: n - 1] if n > 1 else None)
+        torch.cuda.synchronize(dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            out = orc.step(x1, d1, noise[: n - 1] if n > 1 else None)
+        e1.record()
+        torch.cuda.synchronize(dev)
+    assert torch.isfinite(out).all()
+    ms = e0.elapsed_time(e1) / steps
+    del sd16, kv, orc
+    torch.cuda.empty_cache()
+    return 1e3 / ms, ms
+
+
+def run_torch_fp16(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")))
+    torch.cuda.set_device(dev)
+    with ClockSampler(dev.index) as clk:
+        fps, ms = torch_fp16_eager_fps(dev, args.steps, args.warmup)
+    line = {"impl": "torch-fp16", "metric": CFG["metric"], "value": fps, "unit": UNIT, "n_gpus": 1, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f16", "data": "synthetic", "config": workload_config(1), "clocks": clk.summary(),
+            "gpu_launches": 0,
+            "note": "eager torch fp16 restatement of the reference's UNet step + LCM step + host ring schedule on one GPU "
+                    "(library kernels only: cuDNN / cuBLAS / SDPA); none of this repo's kernels run in this arm"}
     print(json.dumps(line), flush=True)
 
 
@@ -215,7 +358,7 @@ def run_native(args):
     from live2diff_b200.device_stream import B200DeviceStream
     from live2diff_b200.stream_pipeline import B200StreamPipeline, broadcast_prompt
     from live2diff_b200.unet_step import B200UNetStep
-    from live2diff_b200.weights import UNetDims, random_state_dict
+    from live2diff_b200.weights import random_state_dict
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -229,7 +372,8 @@ def run_native(args):
         dist.init_process_group("nccl", device_id=dev)
     lib = _lib.lib()
 
-    d = UNetDims()
+    d = unet_dims()
+    T_INDEX, LAT_H, LAT_W, WINDOW = CFG["t_index"], CFG["h"], CFG["w"], CFG["window"]
     n = len(T_INDEX)
     sd = random_state_dict(d, seed=0)
     unet = B200UNetStep(sd, d, n, LAT_H, LAT_W, use_cuda_graph=True, device=dev)
@@ -254,6 +398,7 @@ def run_native(args):
     host_d = [torch.randn(1, 4, 1, LAT_H, LAT_W, generator=gen).half().pin_memory() for _ in range(n_frames_pool)]
     dev_x = [t.to(dev) for t in host_x]
     dev_d = [t.to(dev) for t in host_d]
+    dev_out = torch.empty(1, 4, 1, LAT_H, LAT_W, dtype=torch.float16, device=dev)
     host_out = torch.empty(1, 4, 1, LAT_H, LAT_W, dtype=torch.float16).pin_memory()
 
     def barrier():
@@ -268,19 +413,34 @@ def run_native(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
+    def frame_dev(i):
+        if stream is not pipe:
+            stream(dev_x[i % n_frames_pool], dev_d[i % n_frames_pool], out=dev_out)
+        else:
+            stream(dev_x[i % n_frames_pool], dev_d[i % n_frames_pool])
+
+    def timed_frames(k):
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
+        for i in range(k):
+            frame_dev(i)
+        ev1.record()
+        torch.cuda.synchronize(dev)
+        return ev0.elapsed_time(ev1)
+
     if stream is not pipe:                         # real frames until every ring slot is valid (steady state)
         for i in range(3 * WINDOW):
-            stream(dev_x[i % n_frames_pool], dev_d[i % n_frames_pool])
+            frame_dev(i)
     # ---------------- device-resident throughput ----------------
     for i in range(max(args.warmup, 3)):
-        stream(dev_x[i % n_frames_pool], dev_d[i % n_frames_pool])
+        frame_dev(i)
     barrier()
     l0 = lib.l2d_launch_count()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     with ClockSampler(local) as clk:
         ev0.record()
         for i in range(args.steps):
-            stream(dev_x[i % n_frames_pool], dev_d[i % n_frames_pool])
+            frame_dev(i)
         ev1.record()
         barrier()
     launches = lib.l2d_launch_count() - l0
@@ -329,22 +489,44 @@ def run_native(args):
         k1_bytes = k1_algorithmic_bytes(d, n, LAT_H, LAT_W)
         k1_ms = fam_ms["kv_attn"]
         achieved = k1_bytes / (k1_ms * 1e-3) / 1e9
+        # marginal cost of K1 / the GEMM family inside the whole-frame graph replay (what they cost in the measured frame)
+        in_graph = {}
+        if stream is not pipe and not args.no_ablation:
+            k_abl = max(10, min(args.steps, 40))
+            timed_frames(3)
+            base_ms = timed_frames(k_abl) / k_abl
+            for fam, bit in (("kv_attn", 0), ("gemm", 1), ("spatial_attn", 2), ("norm", 3)):
+                lib.l2d_unet_set_ablation(unet._handle, 1 << bit)
+                stream.invalidate_graph()
+                timed_frames(3)
+                in_graph[fam] = base_ms - timed_frames(k_abl) / k_abl
+            lib.l2d_unet_set_ablation(unet._handle, 0)
+            stream.invalidate_graph()
+            timed_frames(3)
         traffic = None
         tp = os.path.join(ROOT, "profiles", "k1_traffic.json")
-        if os.path.exists(tp):
+        if os.path.exists(tp) and args.config == 2:
             traffic = json.load(open(tp)).get("dram_bytes_per_launch_avg")     # ncu dram read+write, per launch
-        roofline = {"kernel": "kv_attn_mma_kernel (K1, 40 launches/step)", "bound": "hbm", "achieved": achieved,
-                    "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak, "peak_source": which,
+        roofline = {"kernel": "kv_attn_mma_kernel (K1, %d launches/step)" % fam_cnt["kv_attn"], "bound": "hbm",
+                    "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak, "peak_source": which,
                     "algorithmic_bytes_per_step": k1_bytes, "algorithmic_bytes_per_launch": k1_bytes / fam_cnt["kv_attn"],
                     "ms_per_step_in_kernel": k1_ms, "us_per_launch": k1_ms * 1e3 / fam_cnt["kv_attn"], "traffic": traffic}
-        gemm_flops = 2.227e12 * 0.93                        # all dense contractions except the 3 attention families
+        if in_graph.get("kv_attn", 0) > 0:
+            roofline["ms_per_step_in_graph"] = in_graph["kv_attn"]
+            roofline["frac_in_graph"] = k1_bytes / (in_graph["kv_attn"] * 1e-3) / 1e9 / hbm_peak
+        gemm_flops = unet_gemm_flops(d, n, LAT_H, LAT_W)
         breakdown = {f: {"ms": round(fam_ms[f], 4), "launches": fam_cnt[f]} for f in fam_ms}
+        for f, v in in_graph.items():
+            breakdown[f]["ms_in_graph"] = round(v, 4)
         tensor = {"kernel": "gemm_f16_tcgen05_kernel (all linears + convs)", "bound": "tensor",
                   "achieved": gemm_flops / (fam_ms["gemm"] * 1e-3) / 1e12, "peak": tf_peak, "unit": "TFLOP/s",
                   "frac": gemm_flops / (fam_ms["gemm"] * 1e-3) / 1e12 / tf_peak if tf_peak else None,
-                  "note": "flops = 0.93 x 2.227 TFLOP/step (SURVEY §6 split), time = CUDA events around the GEMM launches "
-                          "of an eager step; peak = measured cuBLAS bf16 sustained"}
-        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                  "flops_per_step": gemm_flops,
+                  "note": "flops counted from the layer shapes (bench.unet_gemm_flops), time = CUDA events around the GEMM "
+                          "launches of an eager step; peak = measured cuBLAS bf16 sustained"}
+        if in_graph.get("gemm", 0) > 0 and tf_peak:
+            tensor["frac_in_graph"] = gemm_flops / (in_graph["gemm"] * 1e-3) / 1e12 / tf_peak
+        line = {"metric": CFG["metric"], "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "f16", "data": "synthetic", "config": workload_config(world),
                 "clocks": clk.summary(),
@@ -355,10 +537,18 @@ def run_native(args):
                 "pipeline": "device-resident stream state, whole frame = 1 CUDA graph (l2d_stream_frame)"
                             if stream is not pipe else "host-scheduled B200StreamPipeline, UNet step = 1 CUDA graph",
                 "roofline": roofline, "roofline_tensor": tensor, "kernel_time_breakdown_ms": breakdown,
-                "engine_device_gib": round(unet.device_bytes / 2 ** 30, 2)}
+                "engine_device_gib": round(unet.device_bytes / 2 ** 30, 2), "value_per_stream": value / world}
     if world > 1:
         dist.barrier()
     if rank == 0:
+        if world == 1 and not args.no_torch_baseline:
+            del stream, pipe, unet, kv
+            torch.cuda.empty_cache()
+            t_fps, t_ms = torch_fp16_eager_fps(dev, max(5, min(args.steps, 30)), 3)
+            line["torch_fp16_eager"] = {"value": t_fps, "unit": UNIT, "ms_per_step": t_ms,
+                                        "what": "eager torch fp16 restatement of the reference step on the same GPU "
+                                                "(cuDNN/cuBLAS/SDPA), same config; see --impl torch-fp16"}
+            line["vs_torch_fp16_eager"] = e2e / t_fps
         if world == 1 and not args.no_cpu_baseline:
             fps, dt, cores, k_eff, sample = cpu_oracle_fps(2, 1, budget_s=25.0)
             line["cpu_baseline"] = {"value": fps, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample}
@@ -370,17 +560,25 @@ def run_native(args):
 
 
 def main():
+    global CFG
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=10)
-    ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--impl", default="native", choices=["native", "reference", "torch-fp16"])
+    ap.add_argument("--config", type=int, default=2, choices=sorted(CONFIGS),
+                    help="BASELINE.json configuration (2 = the metric's own, default)")
     ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the (~1 min) CPU oracle leg")
+    ap.add_argument("--no-torch-baseline", action="store_true", help="skip the eager torch fp16 GPU leg")
+    ap.add_argument("--no-ablation", action="store_true", help="skip the in-graph marginal-cost passes")
     ap.add_argument("--pipeline", default="device", choices=["device", "host"],
                     help="device: B200DeviceStream (state in HBM, whole-frame graph); host: B200StreamPipeline")
     args = ap.parse_args()
+    CFG = CONFIGS[args.config]
     if args.impl == "reference":
         run_reference(args)
+    elif args.impl == "torch-fp16":
+        run_torch_fp16(args)
     else:
         run_native(args)
 

@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define L2D_ABI_VERSION 2
+#define L2D_ABI_VERSION 3
 
 #define L2D_OK 0
 #define L2D_ERR_INVALID (-1)     /* bad argument / unsupported shape */
@@ -42,6 +42,8 @@ extern "C" {
 #define L2D_ERR_MISSING (-3)     /* a required weight tensor was not supplied */
 
 int l2d_abi_version(void);
+/* sha1 of the CUDA sources the library was compiled from (live2diff_b200/csrc/build.py compares it with the tree). */
+const char* l2d_build_hash(void);
 const char* l2d_last_error(void);
 /* Number of kernels this library has launched in the calling process (monotonic counter). */
 int64_t l2d_launch_count(void);
@@ -69,10 +71,6 @@ int l2d_kv_attn(const void* q, const void* k_new, const void* v_new, int64_t qkv
 int l2d_warmup_attn(const void* q, const void* k, const void* v, int64_t qkv_ld, void* kv_cache_row,
                     const void* q_pe, const void* k_pe, const void* v_pe, int64_t pe_ld, void* out, int64_t out_ld,
                     int frames, int hw, int window, int channels, int heads, void* stream);
-
-/* Developer hook: when non-NULL, every CTA of the (L == 16) K1 kernel writes cycles spent waiting for TMA data,
- * appending/staging, computing, storing, and its tile count to timeline[cta*8 ..]; NULL disables. */
-void l2d_kv_attn_set_debug(void* timeline);
 
 /* ---------------------------------------------------------------------------------------------
  * Op-level kernels (row-major fp16 activations, "tokens x channels" = NHWC).
@@ -116,9 +114,6 @@ int l2d_nhwc_to_nchw(const void* x, const void* residual_nchw, void* y, int n_im
 int l2d_gemm(const void* a, int64_t lda, const void* w, void* out, int64_t ldo, int m, int n, int k,
              const void* bias, const void* rowgroup_bias, int rows_per_group, const void* residual,
              int64_t ldr, int act, void* stream);
-/* Developer hook: when non-NULL, every GEMM CTA writes 8 clock64() stamps (start, setup done, first stage landed,
- * last MMA issued, accumulator ready, epilogue done, all warps joined, unused) to timeline[cta*8 ..]; NULL disables. */
-void l2d_gemm_set_debug(void* timeline);
 /* Implicit-GEMM 3x3 convolution, pad 1, stride 1 (no im2col matrix): x [N,h,w,Cin] channels-last contiguous,
  * weight [Cout, 9*Cin] with columns ordered (tap = ky*3+kx, cin), out rows = pixels (n*h*w + y*w + x), `ldo` elements
  * per row.  Epilogue as l2d_gemm (rowgroup_bias [N, Cout] is per image).  Needs Cin % 64 == 0 and h, w whose
@@ -209,6 +204,11 @@ typedef struct l2d_unet_step_args {
   const int64_t* pe_idx;            /* [N,L] int64 (device) */
   const int64_t* update_idx;        /* [N] int64 (device) */
   void* out_sample;                 /* [N,4,1,h,w] fp16 */
+  int32_t reuse_constants;          /* 0: timestep / encoder_hidden_states may have changed -- their projections (time MLP,
+                                       22 x time_emb_proj, 16 x cross-attention K|V) are recomputed before the step.
+                                       1: both are unchanged since this engine's previous step: the projections are reused
+                                       (the reference recomputes them every frame although both are constant per prompt,
+                                       pipeline_stream_animation_depth.py:231-246).  They are never part of the CUDA graph. */
 } l2d_unet_step_args;
 
 int l2d_unet_create(l2d_unet** out, const l2d_unet_config* cfg, const l2d_tensor* weights, int n_weights);
@@ -222,10 +222,10 @@ int l2d_unet_step(l2d_unet* u, const l2d_unet_step_args* args, void* stream);
 #define L2D_N_FAMILIES 6
 int l2d_unet_profile_step(l2d_unet* u, const l2d_unet_step_args* args, void* stream, float* ms_by_family,
                           int32_t* launches_by_family);
-/* Developer hook (profiles/ablate_families.py): skip every launch of the families whose bit (1 << family) is set -- plus
- * bit 6 = LayerNorm only, bit 7 = GroupNorm only -- so that the drop in frame time measures that family's true cost on
- * the graph's critical path.  Results are garbage while a mask is set; 0 restores the real step. */
-void l2d_unet_set_ablation(l2d_unet* u, int family_mask);
+/* Counter bumped every time the engine recomputed its (timestep, prompt) projections: a caller that passes
+ * reuse_constants = 1 while sharing the engine with another caller (e.g. a device-resident stream) compares it with the
+ * value it saw after its own last step and passes 0 when someone else has recomputed them in between. */
+int64_t l2d_unet_constants_epoch(const l2d_unet* u);
 /* Bytes of device memory owned by the engine (weights + workspace). */
 int64_t l2d_unet_device_bytes(const l2d_unet* u);
 /* Kernel launches per step (counted on the most recent step). */

@@ -32,16 +32,16 @@ class L2DUnetConfig(C.Structure):
 class L2DUnetStepArgs(C.Structure):
     _fields_ = [("sample", vp), ("timestep", vp), ("encoder_hidden_states", vp), ("temporal_attention_mask", vp),
                 ("depth_sample", vp), ("kv_cache", C.POINTER(vp)), ("n_kv", C.c_int32), ("pe_idx", vp),
-                ("update_idx", vp), ("out_sample", vp)]
+                ("update_idx", vp), ("out_sample", vp), ("reuse_constants", C.c_int32)]
 
 
 # name -> (restype, argtypes); the symbol list is also what tests/test_cabi.py checks against the header
 SIGNATURES = {
     "l2d_abi_version": (i32, []),
+    "l2d_build_hash": (C.c_char_p, []),
     "l2d_last_error": (C.c_char_p, []),
     "l2d_launch_count": (i64, []),
     "l2d_kv_attn": (i32, [vp, vp, vp, i64, vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, vp]),
-    "l2d_kv_attn_set_debug": (None, [vp]),
     "l2d_warmup_attn": (i32, [vp, vp, vp, i64, vp, vp, vp, vp, i64, vp, i64, i32, i32, i32, i32, i32, vp]),
     "l2d_layernorm": (i32, [vp, vp, vp, vp, i32, i32, f32, vp]),
     "l2d_groupnorm_workspace_bytes": (i64, [i32, i32]),
@@ -53,7 +53,6 @@ SIGNATURES = {
     "l2d_gemm": (i32, [vp, i64, vp, vp, i64, i32, i32, i32, vp, vp, i32, vp, i64, i32, vp]),
     "l2d_conv3x3": (i32, [vp, i32, i32, i32, i32, vp, vp, i64, i32, vp, vp, vp, i64, i32, vp]),
     "l2d_gemm_tile_n": (i32, [i32, i32, i32]),
-    "l2d_gemm_set_debug": (None, [vp]),
     "l2d_geglu_interleave": (i32, [vp, vp, vp, vp, i32, i32, i32, vp]),
     "l2d_small_linear": (i32, [vp, vp, vp, vp, i32, i32, i32, i32, i32, vp]),
     "l2d_timestep_embedding": (i32, [vp, vp, i32, i32, vp]),
@@ -65,7 +64,7 @@ SIGNATURES = {
     "l2d_unet_create": (i32, [C.POINTER(vp), C.POINTER(L2DUnetConfig), C.POINTER(L2DTensor), i32]),
     "l2d_unet_step": (i32, [vp, C.POINTER(L2DUnetStepArgs), vp]),
     "l2d_unet_profile_step": (i32, [vp, C.POINTER(L2DUnetStepArgs), vp, C.POINTER(C.c_float), C.POINTER(C.c_int32)]),
-    "l2d_unet_set_ablation": (None, [vp, i32]),
+    "l2d_unet_constants_epoch": (i64, [vp]),
     "l2d_unet_device_bytes": (i64, [vp]),
     "l2d_unet_launches_per_step": (i64, [vp]),
     "l2d_unet_destroy": (None, [vp]),
@@ -85,6 +84,15 @@ SIGNATURES = {
     "l2d_philox4x32_10_host": (None, [C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]),
 }
 
+# developer hooks (include/l2d_b200_debug.h): used by profiles/*.py only, not part of the drop-in ABI
+DEBUG_SIGNATURES = {
+    "l2d_kv_attn_set_debug": (None, [vp]),
+    "l2d_gemm_set_debug": (None, [vp]),
+    "l2d_unet_set_ablation": (None, [vp, i32]),
+    "l2d_stream_invalidate_graph": (None, [vp]),
+}
+
+ABI_VERSION = 3
 _lib: Optional[C.CDLL] = None
 
 
@@ -96,12 +104,24 @@ def lib() -> C.CDLL:
                 f"{LIB_PATH} is missing: build the CUDA library first (python live2diff_b200/csrc/build.py). "
                 "live2diff_b200 has no CPU or PyTorch fallback.")
         handle = C.CDLL(LIB_PATH)
-        for name, (res, args) in SIGNATURES.items():
+        for name, (res, args) in {**SIGNATURES, **DEBUG_SIGNATURES}.items():
             fn = getattr(handle, name)
             fn.restype = res
             fn.argtypes = args
-        if handle.l2d_abi_version() != 2:
-            raise RuntimeError("libl2d_b200.so ABI version mismatch")
+        if handle.l2d_abi_version() != ABI_VERSION:
+            raise RuntimeError("libl2d_b200.so ABI version mismatch: rebuild (python live2diff_b200/csrc/build.py)")
+        # a library compiled from other sources than the ones lying next to it is refused (stale kernels would make
+        # every parity / bench number meaningless); installs that ship no sources skip the check
+        try:
+            from .csrc import build as _build
+
+            want = _build.source_hash()
+        except Exception:
+            want = None
+        got = handle.l2d_build_hash().decode()
+        if want is not None and got != want:
+            raise RuntimeError(f"libl2d_b200.so was built from other sources (hash {got[:12]} != tree {want[:12]}): "
+                               "rebuild with python live2diff_b200/csrc/build.py")
         _lib = handle
     return _lib
 

@@ -33,6 +33,13 @@ bool pdl_family(int bit) {
 
 }  // namespace l2d
 
+#ifndef L2D_BUILD_HASH_STR
+#define L2D_BUILD_HASH_STR "unstamped"
+#endif
+// sha1 of the sources this library was compiled from (csrc/build.py); build() compares it with the tree
+// and _lib.py refuses a library whose hash differs from the sources lying next to it
+extern "C" const char l2d_build_hash_marker[] = "L2D_BUILD_HASH=" L2D_BUILD_HASH_STR;
+extern "C" const char* l2d_build_hash(void) { return l2d_build_hash_marker + 15; }
 extern "C" int l2d_abi_version(void) { return L2D_ABI_VERSION; }
 extern "C" const char* l2d_last_error(void) { return l2d::g_last_error.c_str(); }
 extern "C" int64_t l2d_launch_count(void) { return l2d::g_launches.load(std::memory_order_relaxed); }

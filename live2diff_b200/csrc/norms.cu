@@ -1,6 +1,6 @@
 // K5/K6 -- GroupNorm(+SiLU)(+3x3 im2col) and LayerNorm on channels-last fp16 activations, plus the
 // raw im2col / layout kernels.  All HBM/L2-bandwidth kernels: 128-bit accesses, fp32 statistics,
-// warp-shuffle reductions.
+// warp-shuffle / fixed-order shared-memory reductions (no atomics on data: results are bit-reproducible).
 //
 // Reference semantics: nn.GroupNorm / InflatedGroupNorm per frame (resnet.py:68-76; eps 1e-5 in
 // resnets/conv_norm_out, 1e-6 at transformer entries -- SURVEY A-9), nn.LayerNorm(eps 1e-5),
@@ -99,20 +99,18 @@ __device__ __forceinline__ int* gn_counters(float* ws, int n_img, int G) {
 __global__ void __launch_bounds__(512) groupnorm_stats_kernel(GnSrc src, const __half* __restrict__ gamma,
                                                                const __half* __restrict__ beta, float* __restrict__ ws,
                                                                int hw, int G, int split, float eps) {
-  extern __shared__ float sm[];  // [2][C] per-channel sum, sumsq
+  extern __shared__ float sm[];  // [2][R][C]: per pixel-lane, per channel (sum | sumsq); lane 0's rows end up holding the totals
   __shared__ int s_last;
   const int C = src.c1 + src.c2;
   const int nch = C >> 3;
   const int n = blockIdx.y, sp = blockIdx.x, n_img = gridDim.y;
   const int per = (hw + split - 1) / split;
   const int p0 = sp * per, p1 = min(hw, p0 + per);
-  float* s_sum = sm;
-  float* s_sq = sm + C;
-  pdl_launch();
-  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) sm[i] = 0.f;
-  __syncthreads();
-  pdl_wait();
   const int R = blockDim.x / nch;  // pixel lanes
+  float* s_sum = sm;
+  float* s_sq = sm + (size_t)R * C;
+  pdl_launch();
+  pdl_wait();
   const int r = threadIdx.x / nch, ch = threadIdx.x - r * nch;
   if (r < R) {
     float a[8] = {0, 0, 0, 0, 0, 0, 0, 0}, b[8] = {0, 0, 0, 0, 0, 0, 0, 0};
@@ -132,11 +130,24 @@ __global__ void __launch_bounds__(512) groupnorm_stats_kernel(GnSrc src, const _
         }
       }
     }
-#pragma unroll
-    for (int e = 0; e < 8; ++e) {
-      atomicAdd(&s_sum[ch * 8 + e], a[e]);
-      atomicAdd(&s_sq[ch * 8 + e], b[e]);
+    // fixed-order reduction (no atomics): every pixel lane parks its partials, then one thread per channel adds the
+    // lanes in lane order -- the same sums bit for bit on every run
+    float* ds = s_sum + (size_t)r * C + ch * 8;
+    float* dq = s_sq + (size_t)r * C + ch * 8;
+    *reinterpret_cast<float4*>(ds) = make_float4(a[0], a[1], a[2], a[3]);
+    *reinterpret_cast<float4*>(ds + 4) = make_float4(a[4], a[5], a[6], a[7]);
+    *reinterpret_cast<float4*>(dq) = make_float4(b[0], b[1], b[2], b[3]);
+    *reinterpret_cast<float4*>(dq + 4) = make_float4(b[4], b[5], b[6], b[7]);
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float ts = s_sum[c], tq = s_sq[c];
+    for (int r2 = 1; r2 < R; ++r2) {
+      ts += s_sum[(size_t)r2 * C + c];
+      tq += s_sq[(size_t)r2 * C + c];
     }
+    s_sum[c] = ts;
+    s_sq[c] = tq;
   }
   __syncthreads();
   const int cpg = C / G;
@@ -402,7 +413,8 @@ int groupnorm_launch(const __half* x1, int c1, const __half* x2, int c2, const _
   GnSrc src{x1, x2, c1, c2};
   if (nch > threads || C > GN_MAX_C) return fail(L2D_ERR_INVALID, "groupnorm: C > 4096");
   static size_t cfg_stats = 0;
-  const size_t smem = (size_t)2 * C * sizeof(float);
+  const int lanes = threads / (nch > 0 ? nch : 1) > 0 ? threads / (nch > 0 ? nch : 1) : 1;
+  const size_t smem = (size_t)2 * lanes * C * sizeof(float);   // <= 32 KB: lanes * C <= 8 * threads
   if (smem > 48 * 1024 && smem > cfg_stats) {
     L2D_CUDA(cudaFuncSetAttribute(groupnorm_stats_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     cfg_stats = smem;

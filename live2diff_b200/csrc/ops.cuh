@@ -72,6 +72,9 @@ int attention_launch(const __half* q, int64_t ldq, const __half* k, int64_t ldk,
 
 // engine.cu internals used by the device-resident stream (stream_state.cu)
 int unet_run_eager(::l2d_unet* u, const l2d_unet_step_args* a, cudaStream_t st);   // enqueue one step on st (capturable)
+// time-embedding MLP + stacked time_emb_proj + stacked cross-attention K|V projection: once per (timestep, prompt)
+int64_t unet_consts_epoch(const ::l2d_unet* u);
+int unet_prepare_constants(::l2d_unet* u, const int64_t* timestep, const void* encoder_hidden_states, cudaStream_t st);
 void unet_geometry(const ::l2d_unet* u, int* n_rows, int* h, int* w, int* window, int* n_kv, int* ctx_len, int* ctx_dim,
                    int* warmup_frames);
 

@@ -7,6 +7,7 @@
 #include <memory>
 #include <vector>
 
+#include "../../include/l2d_b200_debug.h"
 #include "ops.cuh"
 #include "stream_state.cuh"
 
@@ -118,6 +119,8 @@ struct l2d_stream {
   uint64_t* frame = nullptr;
   std::vector<void*> kv;
   bool have_prompt = false;
+  int64_t consts_epoch = -1;
+  bool consts_dirty = true;   // prompt changed since the engine's (timestep, prompt) projections were computed
   // whole-frame graph on an owned stream (the caller's stream may be the legacy default stream: not capturable)
   cudaStream_t own_st = nullptr;
   cudaEvent_t ev_in = nullptr, ev_out = nullptr;
@@ -251,6 +254,7 @@ extern "C" int l2d_stream_set_prompt(l2d_stream* s, const void* prompt_embeds, i
                              static_cast<const uint8_t*>(prompt_embeds) + (rows == 1 ? 0 : r) * row_b, row_b,
                              cudaMemcpyDefault, (cudaStream_t)stream));
   s->have_prompt = true;
+  s->consts_dirty = true;
   return L2D_OK;
 }
 
@@ -289,6 +293,12 @@ extern "C" int l2d_stream_frame(l2d_stream* s, const void* x_t_latent, const voi
     L2D_CUDA(cudaMemsetAsync(s->noise_mode, 0, sizeof(int), st));
     if (mode) L2D_CUDA(cudaMemsetAsync(s->noise_mode, 1, 1, st));   // little endian: int 1
   }
+  if (s->consts_dirty || unet_consts_epoch(s->unet) != s->consts_epoch) {   // once per prompt: time-embedding / cross-attention K|V projections, outside the frame graph
+    const int rc = unet_prepare_constants(s->unet, s->timesteps, s->ctx, st);
+    if (rc != L2D_OK) return rc;
+    s->consts_dirty = false;
+    s->consts_epoch = unet_consts_epoch(s->unet);
+  }
   if (!s->use_graph || s->frames_done == 0) {
     // the first frame is always eager: it sizes shared-memory attributes and fills the tensor-map cache
     const int rc = enqueue_frame(s, st);
@@ -319,6 +329,15 @@ extern "C" int l2d_stream_frame(l2d_stream* s, const void* x_t_latent, const voi
   L2D_CUDA(cudaStreamWaitEvent(caller, s->ev_out, 0));
   ++s->frames_done;
   return L2D_OK;
+}
+
+// developer hook (include/l2d_b200_debug.h): drop the captured frame graph so the next frame re-captures it
+extern "C" void l2d_stream_invalidate_graph(l2d_stream* s) {
+  if (s && s->graph_exec) {
+    cudaStreamSynchronize(s->own_st);
+    cudaGraphExecDestroy(s->graph_exec);
+    s->graph_exec = nullptr;
+  }
 }
 
 extern "C" int64_t l2d_stream_launches_per_frame(const l2d_stream* s) { return s ? s->launches_per_frame : 0; }

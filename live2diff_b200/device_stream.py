@@ -84,11 +84,13 @@ class B200DeviceStream:
     @torch.no_grad()
     def predict_x0_batch(self, x_t_latent: torch.Tensor, depth_latent: torch.Tensor,
                          noise: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
-        """x_t_latent, depth_latent: [1,4,1,h,w] fp16, CUDA or pinned host.  Returns x0 [1,4,1,h,w] (`out` if given --
-        CUDA or pinned host; for a host `out` the caller synchronises the stream before reading it)."""
+        """x_t_latent, depth_latent: [1,4,1,h,w] fp16, CUDA or pinned host.  Returns x0 [1,4,1,h,w]: a fresh CUDA tensor
+        per frame like the reference (safe to queue), or `out` if given (CUDA or pinned host; for a host `out` the caller
+        synchronises the stream before reading it).  Pinned-host inputs are read asynchronously by the frame's H2D copies:
+        do not rewrite them before the stream has been synchronised (or an event recorded after this call has fired)."""
         per = self._out.numel()
         if out is None:
-            out = self._out
+            out = torch.empty_like(self._out)
         n_ptr = None if noise is None else self._addr(noise, "noise", (self.n - 1) * per)
         check(lib().l2d_stream_frame(self._handle, self._addr(x_t_latent, "x_t_latent", per),
                                      self._addr(depth_latent, "depth_latent", per), n_ptr, self._addr(out, "out", per),
@@ -101,6 +103,10 @@ class B200DeviceStream:
     @property
     def launches_per_frame(self) -> int:
         return lib().l2d_stream_launches_per_frame(self._handle)
+
+    def invalidate_graph(self) -> None:
+        """Developer hook (profiles/, bench.py's ablation passes): re-capture the frame graph on the next frame."""
+        lib().l2d_stream_invalidate_graph(self._handle)
 
     def schedule(self) -> Dict[str, list]:
         """Read the ring schedule back from the device (synchronises): valid [N], pe_idx [N][L], update_idx [N], frame."""

@@ -75,10 +75,14 @@ class B200StreamPipeline:
         self.sub_timesteps_tensor = torch.tensor(c.timesteps, dtype=torch.int64, device=dev)
         self.consts = torch.tensor(c.table(), dtype=torch.float32, device=dev).contiguous()
         self.kv_cache_list = kv_cache_list if kv_cache_list is not None else self.unet.prepare_cache(n)
-        # pinned staging for the three tiny schedule tensors
-        self._h_mask = torch.empty(n, self.window, dtype=torch.float16).pin_memory()
-        self._h_pe = torch.empty(n, self.window, dtype=torch.int64).pin_memory()
-        self._h_up = torch.empty(n, dtype=torch.int64).pin_memory()
+        # pinned staging for the three tiny schedule tensors: a ring of slots, each guarded by a CUDA event, because the
+        # host runs ahead of the GPU (graph replay, no sync per frame) and must not rewrite a slot whose H2D copy is queued
+        self._stage_slots = []
+        for _ in range(4):
+            self._stage_slots.append((torch.empty(n, self.window, dtype=torch.float16).pin_memory(),
+                                      torch.empty(n, self.window, dtype=torch.int64).pin_memory(),
+                                      torch.empty(n, dtype=torch.int64).pin_memory(), torch.cuda.Event()))
+        self._stage_i = 0
         self.attn_bias = torch.empty(n, self.window, dtype=torch.float16, device=dev)
         self.pe_idx = torch.empty(n, self.window, dtype=torch.int64, device=dev)
         self.update_idx = torch.empty(n, dtype=torch.int64, device=dev)
@@ -124,12 +128,17 @@ class B200StreamPipeline:
 
     def _upload_schedule(self):
         s = self.schedule
-        self._h_mask.copy_(torch.tensor(s.mask_rows(), dtype=torch.float16))
-        self._h_pe.copy_(torch.tensor(s.pe_idx, dtype=torch.int64))
-        self._h_up.copy_(torch.tensor(s.update_idx, dtype=torch.int64))
-        self.attn_bias.copy_(self._h_mask, non_blocking=True)
-        self.pe_idx.copy_(self._h_pe, non_blocking=True)
-        self.update_idx.copy_(self._h_up, non_blocking=True)
+        h_mask, h_pe, h_up, ev = self._stage_slots[self._stage_i % len(self._stage_slots)]
+        if self._stage_i >= len(self._stage_slots):
+            ev.synchronize()                       # the copies issued from this slot 4 frames ago have run
+        self._stage_i += 1
+        h_mask.copy_(torch.tensor(s.mask_rows(), dtype=torch.float16))
+        h_pe.copy_(torch.tensor(s.pe_idx, dtype=torch.int64))
+        h_up.copy_(torch.tensor(s.update_idx, dtype=torch.int64))
+        self.attn_bias.copy_(h_mask, non_blocking=True)
+        self.pe_idx.copy_(h_pe, non_blocking=True)
+        self.update_idx.copy_(h_up, non_blocking=True)
+        ev.record()
 
     # ------------------------------------------------------------------------------------------
     @torch.no_grad()

@@ -94,6 +94,8 @@ class B200UNetStep:
         self._upd = torch.empty(n_rows, dtype=torch.int64, device=dev)
         self._kv_ids = None
         self._kv_arr = None
+        self._const_epoch = -1
+        self._const_key = None        # identity + version of the (timestep, prompt) pair whose projections the engine holds
         self._kv_shapes = dims.kv_cache_shapes(n_rows, latent_h, latent_w)
 
     # -- reference-compatible helpers --------------------------------------------------------
@@ -141,8 +143,16 @@ class B200UNetStep:
         """Copy the call's inputs into the fixed staging buffers (stable addresses for the CUDA graph)."""
         self._sample.copy_(sample.reshape(self._sample.shape), non_blocking=True)
         self._depth.copy_(depth_sample.reshape(self._depth.shape), non_blocking=True)
-        self._t.copy_(timestep.reshape(-1).expand(self.n_rows), non_blocking=True)   # int64 like the pipeline (:246)
-        self._ctx.copy_(encoder_hidden_states, non_blocking=True)
+        # timestep / prompt are constant per stream and prompt (pipeline:231-246): their projections are recomputed only
+        # when either tensor is a different object or was modified in place (torch bumps `_version` on every in-place op)
+        key = (timestep.data_ptr(), timestep._version, tuple(timestep.shape), encoder_hidden_states.data_ptr(),
+               encoder_hidden_states._version, tuple(encoder_hidden_states.shape))
+        reuse = key == self._const_key and lib().l2d_unet_constants_epoch(self._handle) == self._const_epoch
+        if not reuse:
+            self._t.copy_(timestep.reshape(-1).expand(self.n_rows), non_blocking=True)   # int64 like the pipeline (:246)
+            self._ctx.copy_(encoder_hidden_states, non_blocking=True)
+            self._const_key = key
+            self._const_refs = (timestep, encoder_hidden_states)   # keep them alive: a freed tensor's address could be reused
         self._mask.copy_(temporal_attention_mask, non_blocking=True)
         self._pe_idx.copy_(pe_idx, non_blocking=True)
         self._upd.copy_(update_idx, non_blocking=True)
@@ -153,6 +163,7 @@ class B200UNetStep:
         args.kv_cache = C.cast(self._kv_table(kv_cache), C.POINTER(C.c_void_p))
         args.n_kv = len(kv_cache)
         args.pe_idx, args.update_idx, args.out_sample = self._pe_idx.data_ptr(), self._upd.data_ptr(), self._out.data_ptr()
+        args.reuse_constants = int(reuse)
         return args
 
     @torch.no_grad()
@@ -164,6 +175,7 @@ class B200UNetStep:
         ms = (C.c_float * 6)()
         cnt = (C.c_int32 * 6)()
         check(lib().l2d_unet_profile_step(self._handle, C.byref(args), current_stream(), ms, cnt))
+        self._const_epoch = lib().l2d_unet_constants_epoch(self._handle)
         return {f: (float(ms[i]), int(cnt[i])) for i, f in enumerate(self.FAMILIES)}
 
     @torch.no_grad()
@@ -176,6 +188,7 @@ class B200UNetStep:
         args = self._stage(sample, timestep, encoder_hidden_states, temporal_attention_mask, depth_sample, kv_cache,
                            pe_idx, update_idx)
         check(lib().l2d_unet_step(self._handle, C.byref(args), current_stream()))
+        self._const_epoch = lib().l2d_unet_constants_epoch(self._handle)
         out = self._out.clone()
         if not return_dict:
             return (out, kv_cache)

@@ -31,3 +31,19 @@ def pytest_collection_modifyitems(config, items):
 @pytest.fixture(scope="session")
 def golden_dir():
     return GOLDEN
+
+
+def pytest_sessionfinish(session, exitstatus):
+    """Parity figures of every referee() comparison of the session -> gpurun_out/parity_report.json (copied to profiles/)."""
+    try:
+        import json
+
+        import parity
+
+        if parity.REPORT:
+            out = os.path.join(ROOT, "gpurun_out")
+            os.makedirs(out, exist_ok=True)
+            with open(os.path.join(out, "parity_report.json"), "w") as f:
+                json.dump(parity.REPORT, f, indent=1)
+    except Exception:
+        pass

@@ -15,6 +15,13 @@ REFEREE -- chains of ops (attention with fp16-rounded P / K+pe, whole modules, t
 import torch
 
 RTOL, ATOL = 1e-3, 1e-4
+REPORT = []   # one record per referee() call; tests/conftest.py writes it to gpurun_out/parity_report.json at session end
+# Floor on the fraction of elements that agree with the torch-fp16 evaluation of the reference's own order within
+# BASELINE's rtol 1e-3 / atol 1e-4.  Two correct fp16 chains differ by roughly one fp16 ulp (9.8e-4 relative) per
+# rounding point, so element-wise agreement at 1e-3 is a property of short chains only; the floor below is what every
+# chain in the suite clears with margin on B200 (profiles/r2/parity_report.json holds the measured fractions) and
+# catches the failure mode a rel-rms bound can miss: a small fraction of badly wrong elements.
+MIN_WITHIN_DEFAULT = 0.30
 
 
 def strict(ours: torch.Tensor, ref32: torch.Tensor, name="", rtol=RTOL, atol=ATOL):
@@ -36,7 +43,8 @@ def rel_rms(a: torch.Tensor, ref: torch.Tensor) -> float:
     return float(((a - ref) ** 2).mean().sqrt() / (ref ** 2).mean().sqrt().clamp_min(1e-30))
 
 
-def referee(ours: torch.Tensor, ref32: torch.Tensor, ref16: torch.Tensor, name="", slack=2.0, floor=6e-4):
+def referee(ours: torch.Tensor, ref32: torch.Tensor, ref16: torch.Tensor, name="", slack=2.0, floor=6e-4,
+            min_within=MIN_WITHIN_DEFAULT):
     ours, ref32, ref16 = ours.float().cpu(), ref32.float().cpu(), ref16.float().cpu()
     assert ours.shape == ref32.shape, (name, ours.shape, ref32.shape)
     assert torch.isfinite(ours).all(), f"{name}: non-finite values in the CUDA result"
@@ -47,5 +55,17 @@ def referee(ours: torch.Tensor, ref32: torch.Tensor, ref16: torch.Tensor, name="
     within = float(((ours - ref16).abs() <= ATOL + RTOL * ref16.abs()).float().mean())
     print(f"[parity] {name}: rel-rms ours={e_ours:.2e} torch-fp16={e_ref:.2e} | max-abs ours={m_ours:.2e} "
           f"torch-fp16={m_ref:.2e} (scale {scale:.2e}) | within rtol1e-3/atol1e-4 of torch-fp16: {within:.4f}")
+    # the same fraction for the torch-fp16 chain against the fp32 oracle bounds what any fp16 chain can reach here
+    within_ref = float(((ref16 - ref32).abs() <= ATOL + RTOL * ref32.abs()).float().mean())
+    within_ours32 = float(((ours - ref32).abs() <= ATOL + RTOL * ref32.abs()).float().mean())
+    REPORT.append({"name": name, "rel_rms_ours": e_ours, "rel_rms_torch_fp16": e_ref, "max_abs_ours": m_ours,
+                   "max_abs_torch_fp16": m_ref, "scale": scale, "within_vs_torch_fp16": within,
+                   "within_vs_fp32_ours": within_ours32, "within_vs_fp32_torch_fp16": within_ref})
     assert e_ours <= max(slack * e_ref, floor), f"{name}: rel-rms error {e_ours:.3e} vs fp16 reference {e_ref:.3e}"
     assert m_ours <= max(slack * 2 * m_ref, 4 * floor * scale), f"{name}: max-abs error {m_ours:.3e} vs {m_ref:.3e}"
+    # element-wise agreement with the fp32 oracle at BASELINE's tolerance must not be materially worse than what the
+    # reference's own fp16 evaluation order achieves on the same inputs
+    if min_within is not None:
+        assert within_ours32 >= min(min_within, 0.9 * within_ref), (
+            f"{name}: only {within_ours32:.4f} of the elements within rtol1e-3/atol1e-4 of the fp32 oracle "
+            f"(torch fp16 chain: {within_ref:.4f})")

@@ -8,8 +8,8 @@ import pytest
 ROOT = os.path.abspath(os.path.join(os.path.dirname(__file__), ".."))
 
 
-def header_functions():
-    src = open(os.path.join(ROOT, "include", "l2d_b200.h")).read()
+def header_functions(name="l2d_b200.h"):
+    src = open(os.path.join(ROOT, "include", name)).read()
     src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
     return sorted(set(re.findall(r"\b(l2d_[a-z0-9_]+)\s*\(", src)))
 
@@ -18,6 +18,8 @@ def test_header_and_binding_agree():
     from live2diff_b200 import _lib
 
     assert header_functions() == sorted(_lib.SIGNATURES)
+    assert header_functions("l2d_b200_debug.h") == sorted(_lib.DEBUG_SIGNATURES)      # developer hooks: separate header
+    assert not set(_lib.DEBUG_SIGNATURES) & set(header_functions())
 
 
 def test_library_exports_every_symbol():
@@ -28,10 +30,19 @@ def test_library_exports_every_symbol():
 
         __graft_entry__.build()
     handle = ctypes.CDLL(_lib.LIB_PATH)
-    for name in header_functions():
+    for name in header_functions() + header_functions("l2d_b200_debug.h"):
         assert hasattr(handle, name), f"libl2d_b200.so does not export {name}"
     lib = _lib.lib()
-    assert lib.l2d_abi_version() == 2
+    assert lib.l2d_abi_version() == _lib.ABI_VERSION == 3
+
+
+def test_library_carries_the_hash_of_the_sources_next_to_it():
+    """A stale .so (sources changed, library not rebuilt) must be refused, not silently used."""
+    from live2diff_b200 import _lib
+    from live2diff_b200.csrc import build
+
+    lib = _lib.lib()
+    assert lib.l2d_build_hash().decode() == build.source_hash() == build.built_hash()
     assert lib.l2d_launch_count() >= 0
 
 

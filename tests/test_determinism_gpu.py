@@ -1,0 +1,112 @@
+"""Bit-reproducibility of the engine: every reduction runs in a fixed order (warp shuffles, fixed-order
+shared-memory / slice sums, no atomics on data), so the same inputs give the same bits -- run to run, eager vs CUDA-graph
+replay, and with programmatic dependent launch on vs off.  These are the checks that expose ordering / visibility bugs
+(e.g. a stale non-coherent load under PDL) immediately instead of as a small drift inside a tolerance."""
+import hashlib
+import json
+import os
+import subprocess
+import sys
+
+import pytest
+import torch
+
+from live2diff_b200.weights import UNetDims, random_state_dict
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+ROOT = os.path.abspath(os.path.join(os.path.dirname(__file__), ".."))
+TINY = UNetDims(block_out_channels=(64, 128, 128, 128), cross_attention_dim=96)
+
+
+def _inputs(d, n, h, w, seed=3):
+    gen = torch.Generator().manual_seed(seed)
+    x = torch.randn(n, 4, 1, h, w, generator=gen).half().to(DEV)
+    dep = torch.randn(n, 4, 1, h, w, generator=gen).half().to(DEV)
+    ctx = torch.randn(n, 77, d.cross_attention_dim, generator=gen).half().to(DEV)
+    t = torch.tensor([399, 199, 99, 19][:n], dtype=torch.int64, device=DEV)
+    return x, dep, ctx, t
+
+
+def _schedule(d, n, frames):
+    from live2diff_b200.schedule import RingSchedule
+
+    rs = RingSchedule(n, d.window_size, d.sink_size)
+    for _ in range(frames):
+        rs.advance()
+    mask = torch.tensor(rs.mask_rows(), dtype=torch.float16, device=DEV)
+    return mask, torch.tensor(rs.pe_idx, dtype=torch.int64, device=DEV), torch.tensor(rs.update_idx, dtype=torch.int64, device=DEV)
+
+
+def _fresh_cache(unet, n, seed=9, kv=None):
+    """Same cache contents every time; `kv` reuses the tensors (same pointers -> the captured graph is replayed)."""
+    gen = torch.Generator().manual_seed(seed)
+    kv = unet.prepare_cache(n) if kv is None else kv
+    for c in kv:
+        c.copy_(torch.randn(c.shape, generator=gen).half())
+    return kv
+
+
+def _run(unet, d, n, h, w, kv, frames_advanced=20):
+    x, dep, ctx, t = _inputs(d, n, h, w)
+    mask, pe, up = _schedule(d, n, frames_advanced)
+    out = unet(x, t, depth_sample=dep, encoder_hidden_states=ctx, temporal_attention_mask=mask, kv_cache=kv, pe_idx=pe,
+               update_idx=up)
+    return out["sample"].clone()
+
+
+@pytest.mark.parametrize("dims,h,w", [(TINY, 16, 16), (UNetDims(), 32, 32)], ids=["tiny", "sd15_widths_32x32"])
+def test_same_step_twice_and_graph_replay_are_bit_identical(dims, h, w):
+    from live2diff_b200.unet_step import B200UNetStep
+
+    n = 2
+    sd = random_state_dict(dims, seed=4)
+    eager = B200UNetStep(sd, dims, n, h, w, use_cuda_graph=False)
+    graph = B200UNetStep(sd, dims, n, h, w, use_cuda_graph=True)
+    del sd
+    outs, caches = [], []
+    for unet, reps in ((eager, 2), (graph, 3)):              # graph engine: call 0 eager, call 1 captures + replays, call 2 replays
+        kv = None
+        for _ in range(reps):
+            kv = _fresh_cache(unet, n, kv=kv)
+            outs.append(_run(unet, dims, n, h, w, kv))
+            caches.append([kv[i].clone() for i in (0, 7, len(kv) - 1)])
+    assert torch.isfinite(outs[0].float()).all()
+    for i in range(1, len(outs)):
+        assert torch.equal(outs[i], outs[0]), f"run {i} differs from run 0 (max diff {float((outs[i].float() - outs[0].float()).abs().max()):.3e})"
+        for a, b in zip(caches[i], caches[0]):
+            assert torch.equal(a, b)
+
+
+_CHILD = r"""
+import hashlib, json, sys, torch
+sys.path.insert(0, %(root)r); sys.path.insert(0, %(root)r + "/tests")
+from test_determinism_gpu import TINY, _fresh_cache, _run
+from live2diff_b200.unet_step import B200UNetStep
+from live2diff_b200.weights import random_state_dict
+unet = B200UNetStep(random_state_dict(TINY, seed=4), TINY, 2, 16, 16, use_cuda_graph=True)
+hs = []
+kv = None
+for _ in range(3):
+    kv = _fresh_cache(unet, 2, kv=kv)
+    out = _run(unet, TINY, 2, 16, 16, kv)
+    torch.cuda.synchronize()
+    h = hashlib.sha256(out.cpu().numpy().tobytes())
+    for c in kv:
+        h.update(c.cpu().numpy().tobytes())
+    hs.append(h.hexdigest())
+print(json.dumps(hs))
+"""
+
+
+def test_pdl_on_and_off_are_bit_identical():
+    """L2D_PDL is read once per process, so each setting runs in its own interpreter; the digests cover the output and
+    all 40 KV caches of an eager step and two graph replays."""
+    digests = {}
+    for pdl in ("0", "1"):
+        env = dict(os.environ, L2D_PDL=pdl)
+        r = subprocess.run([sys.executable, "-c", _CHILD % {"root": ROOT}], env=env, capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0, r.stderr[-2000:]
+        digests[pdl] = json.loads(r.stdout.strip().splitlines()[-1])
+    assert len(set(digests["0"])) == 1 and len(set(digests["1"])) == 1, digests
+    assert digests["0"] == digests["1"], digests

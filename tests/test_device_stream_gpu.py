@@ -57,12 +57,12 @@ def test_device_stream_matches_host_scheduled_pipeline(graph):
         noise = torch.randn(N - 1, 4, 1, H, W, generator=gen).half().to(DEV)
         ref = pipe(x, dep, noise=noise).clone()
         out = ds(x, dep, noise=noise).clone()
-        close(out, ref, f"frame {f}")
+        close(out, ref, f"frame {f}", tol=0.0)     # same engine, same kernels, deterministic reductions: bit for bit
         s = ds.schedule()
         assert (s["valid"], s["pe_idx"], s["update_idx"], s["frame"]) == (pipe.schedule.valid, pipe.schedule.pe_idx,
                                                                          pipe.schedule.update_idx, f + 1), f"frame {f}"
     for i in (0, 17, 39):
-        close(kv_b[i], kv_a[i], f"kv[{i}]")
+        close(kv_b[i], kv_a[i], f"kv[{i}]", tol=0.0)
     assert ds.launches_per_frame > unet.launches_per_step > 0
 
 
