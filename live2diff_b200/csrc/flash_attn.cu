@@ -241,6 +241,8 @@ static int launch_flash(const FlashParams& p, int batch, cudaStream_t st) {
 
 int attention_launch(const __half* q, int64_t ldq, const __half* k, int64_t ldk, const __half* v, int64_t ldv, __half* o,
                      int64_t ldo, int batch, int heads, int sq, int skv, int hd, cudaStream_t st) {
+  if (attention_tcgen05_supported(q, k, v, o, ldq, ldk, ldv, ldo, sq, skv, hd))
+    return attention_tcgen05_launch(q, ldq, k, ldk, v, ldv, o, ldo, batch, heads, sq, skv, hd, st);
   FlashParams p{q, k, v, o, ldq, ldk, ldv, ldo, heads, sq, skv, hd, 1.4426950408889634f / sqrtf((float)hd)};
   const int hdp = ((hd + 15) / 16) * 16;
   switch (hdp) {

@@ -1,0 +1,441 @@
+// K2/K3 on the 5th-generation tensor cores -- spatial self-attention (S x S) and text cross-attention (S x 77):
+//     O = softmax(Q K^T / sqrt(hd)) V   per (batch, head), no mask.
+// Reference semantics: diffusers 0.25.0 `Attention` + AttnProcessor2_0 (F.scaled_dot_product_attention) as used for
+// attn1 / attn2 of BasicTransformerBlock (live2diff/animatediff/models/attention.py:173-194, 243, 251-253); heads = 8,
+// hd = 40 / 80 at the two levels where S is large (64x64 and 32x32 latents: S = 4096 / 1024).
+//
+// One CTA = one 128-query tile of one (batch, head); it walks the keys in tiles of 128:
+//   warp 0     TMA producer: Q once, then K_j / V_j tiles ([128 rows x 64 columns] boxes, 128B swizzle) into two
+//              independent rings (K is consumed one tile ahead of V)
+//   warp 1     TMEM allocator + single-thread tcgen05.mma issuer:
+//                S_j = Q . K_j^T   (M = 128 queries, N = 128 keys, K = hd padded to 16s; both operands K-major) into one
+//                                  of two S accumulators in TMEM, so that S_{j+1} is computed while S_j is in the softmax
+//                T_j = P_j . V_j   (M = 128, N = hd rounded to 16, K = 128 keys; A = P from shared memory, K-major;
+//                                  B = the V tile exactly as TMA delivered it = MN-major, 128B swizzle)
+//   warps 2-5  softmax + correction + epilogue: thread = one query row (tcgen05.ld 32x32b: TMEM lane = row), so row max /
+//              row sum need no shuffles; P is rounded to fp16 (like the fused SDPA kernels the reference dispatches to)
+//              and written into shared memory in the UMMA K-major swizzled layout; the running output lives in registers
+//              (o = o * corr + T_j, flash-attention's online softmax in fp32), the 1/l normalisation is applied once.
+// hd = 40: the K extent of Q.K^T is padded to 48 by zeroing columns 40..47 of the Q tile in shared memory (the K tile's
+// columns 40..47 then hold the next head's values, finite, times zero); T's columns 40..47 are ignored.
+// Keys beyond skv in the last tile (cross-attention: 77 keys) are masked to -inf before the softmax; their V rows are
+// other rows of the same tensor or TMA zero fill, always finite.
+#include <cuda.h>
+
+#include "ops.cuh"
+
+namespace l2d {
+
+int get_tmap_2d(const void* ptr, int64_t rows, int64_t cols, int64_t ld, int box_rows, CUtensorMap* out);   // gemm_tcgen05.cu
+
+namespace {
+
+__device__ __forceinline__ uint32_t ft_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void ft_mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void ft_mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void ft_mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void ft_mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done = 0, spins = 0;
+  long long t0 = 0;
+  while (true) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (done) break;
+    if ((++spins & 1023u) == 0) {   // never hang the GPU on a protocol bug: trap after ~2 s
+      const long long now = clock64();
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > 4000000000ll) __trap();
+    }
+  }
+}
+__device__ __forceinline__ void ft_tma_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void ft_fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void ft_tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void ft_tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void ft_umma(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void ft_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void ft_tmem_ld32(uint32_t addr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(addr));
+}
+__device__ __forceinline__ void ft_tmem_ld16(uint32_t addr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(addr));
+}
+__device__ __forceinline__ float ft_ex2(float x) {   // arguments <= 0: no overflow; tiny results flush to zero
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ void ft_tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// UMMA shared-memory descriptors (cute::UMMA::SmemDescriptor bit layout, version 1, SWIZZLE_128B):
+//   K-major  (Q, K, P): rows of 128 B (64 fp16 along K), 8-row groups 1024 B apart (SBO); a K step of 16 = +32 B
+//   MN-major (V as loaded: row = key = K index, 64 consecutive head channels = MN): canonical ((8,n),(8,k)):((1,LBO),(8,SBO))
+//            in 16-byte units: 8-key groups 1024 B apart (SBO), 64-channel column blocks `lbo` bytes apart (LBO)
+__device__ __forceinline__ uint64_t ft_desc(uint32_t smem_addr, uint32_t lbo_bytes) {
+  uint64_t d = (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= 1ull << 46;
+  d |= 2ull << 61;
+  return d;
+}
+// cute::UMMA::InstrDescriptor: c_format F32 (1) @4, a/b format F16 (0) @7/@10, a_major @15, b_major @16 (0 = K, 1 = MN),
+// N >> 3 @17, M >> 4 @24
+__host__ __device__ constexpr uint32_t ft_idesc(int n, int b_mn_major) {
+  return (1u << 4) | ((uint32_t)b_mn_major << 16) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+}
+
+struct FtParams {
+  __half* o;
+  int64_t ldo;
+  int sq, skv, heads;
+  float scale_log2;   // log2(e) / sqrt(hd)
+};
+
+constexpr int FT_THREADS = 192;   // TMA warp, MMA warp, 4 softmax warps
+constexpr int FT_TILE = 128 * 128;   // bytes of one [128 rows x 64 fp16] swizzled block
+
+template <int HD>
+struct FtCfg {
+  static constexpr int KSTEPS = (HD + 15) / 16;     // k16 steps of Q.K^T
+  static constexpr int NBLK = (HD + 63) / 64;       // 64-column blocks of a Q / K / V tile
+  static constexpr int ON = KSTEPS * 16;            // columns of T = P.V that are read back (hd rounded up to 16)
+  static constexpr int ON_MMA = NBLK * 64;          // MMA N of P.V: whole 64-channel swizzle atoms of the V tile
+  static constexpr int STAGES = HD <= 64 ? 3 : 2;   // K / V ring depth
+  static constexpr int TILE_BYTES = NBLK * FT_TILE;
+  static constexpr int SMEM = TILE_BYTES * (1 + 2 * STAGES) + 2 * FT_TILE /* P */ + 256 /* barriers */ + 1024 /* align */;
+};
+
+template <int HD>
+__global__ void __launch_bounds__(FT_THREADS, 1)
+flash_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
+                     const __grid_constant__ CUtensorMap tmap_v, const FtParams p) {
+  using Cfg = FtCfg<HD>;
+  constexpr int ST = Cfg::STAGES, NBLK = Cfg::NBLK, KSTEPS = Cfg::KSTEPS, ON = Cfg::ON;
+  extern __shared__ __align__(1024) uint8_t ft_smem_raw[];
+  uint8_t* smem = ft_smem_raw + ((1024u - (ft_smem_u32(ft_smem_raw) & 1023u)) & 1023u);
+  uint8_t* sQ = smem;
+  uint8_t* sK = sQ + Cfg::TILE_BYTES;
+  uint8_t* sV = sK + ST * Cfg::TILE_BYTES;
+  uint8_t* sP = sV + ST * Cfg::TILE_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 2 * FT_TILE);
+  const uint32_t bar0 = ft_smem_u32(bars);
+  // barrier map
+  const uint32_t q_full = bar0, q_ready = bar0 + 8, p_full = bar0 + 16, o_full = bar0 + 24, o_empty = bar0 + 32;
+  auto k_full = [&](int s) { return bar0 + 40 + 8u * s; };
+  auto k_empty = [&](int s) { return bar0 + 40 + 8u * (ST + s); };
+  auto v_full = [&](int s) { return bar0 + 40 + 8u * (2 * ST + s); };
+  auto v_empty = [&](int s) { return bar0 + 40 + 8u * (3 * ST + s); };
+  auto s_full = [&](int b) { return bar0 + 40 + 8u * (4 * ST + b); };
+  auto s_empty = [&](int b) { return bar0 + 40 + 8u * (4 * ST + 2 + b); };
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 5 + 4 * ST + 4);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int b = blockIdx.z, h = blockIdx.y, m0 = blockIdx.x * 128;
+  const int nk = (p.skv + 127) >> 7;
+  const int col0 = h * HD;
+
+  pdl_launch();
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_q) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_k) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_v) : "memory");
+    ft_mbar_init(q_full, 1);
+    ft_mbar_init(q_ready, 4);
+    ft_mbar_init(p_full, 4);
+    ft_mbar_init(o_full, 1);
+    ft_mbar_init(o_empty, 4);
+    for (int s = 0; s < ST; ++s) {
+      ft_mbar_init(k_full(s), 1);
+      ft_mbar_init(k_empty(s), 1);
+      ft_mbar_init(v_full(s), 1);
+      ft_mbar_init(v_empty(s), 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      ft_mbar_init(s_full(a), 1);
+      ft_mbar_init(s_empty(a), 4);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(ft_smem_u32(tmem_ptr_smem)), "r"(512u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  ft_tc_fence_before();
+  __syncthreads();
+  ft_tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+  constexpr uint32_t TM_S = 0, TM_O = 256;   // TMEM columns: S[0] 0..127, S[1] 128..255, T 256..256+ON_MMA
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      pdl_wait();   // q / k / v were written by the projection GEMMs right before this kernel
+      ft_mbar_expect_tx(q_full, Cfg::TILE_BYTES);
+      for (int cb = 0; cb < NBLK; ++cb) ft_tma_2d(ft_smem_u32(sQ + cb * FT_TILE), &tmap_q, q_full, col0 + cb * 64, b * p.sq + m0);
+      for (int j = 0; j < nk; ++j) {
+        const int s = j % ST;
+        const uint32_t ph = (uint32_t)(j / ST) & 1u;
+        const int row = b * p.skv + j * 128;
+        ft_mbar_wait(k_empty(s), ph ^ 1u);
+        ft_mbar_expect_tx(k_full(s), Cfg::TILE_BYTES);
+        for (int cb = 0; cb < NBLK; ++cb)
+          ft_tma_2d(ft_smem_u32(sK + s * Cfg::TILE_BYTES + cb * FT_TILE), &tmap_k, k_full(s), col0 + cb * 64, row);
+        ft_mbar_wait(v_empty(s), ph ^ 1u);
+        ft_mbar_expect_tx(v_full(s), Cfg::TILE_BYTES);
+        for (int cb = 0; cb < NBLK; ++cb)
+          ft_tma_2d(ft_smem_u32(sV + s * Cfg::TILE_BYTES + cb * FT_TILE), &tmap_v, v_full(s), col0 + cb * 64, row);
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      constexpr uint32_t idesc_s = ft_idesc(128, 0);
+      constexpr uint32_t idesc_o = ft_idesc(Cfg::ON_MMA, 1);
+      auto issue_s = [&](int j) {
+        const int s = j % ST, a = j & 1;
+        ft_mbar_wait(k_full(s), (uint32_t)(j / ST) & 1u);
+        ft_mbar_wait(s_empty(a), ((uint32_t)(j >> 1) & 1u) ^ 1u);   // the softmax has drained this S accumulator (tile j-2)
+        ft_tc_fence_after();
+        const uint32_t qa = ft_smem_u32(sQ), ka = ft_smem_u32(sK + s * Cfg::TILE_BYTES);
+#pragma unroll
+        for (int k = 0; k < KSTEPS; ++k) {
+          const uint32_t off = (uint32_t)(k >> 2) * FT_TILE + (uint32_t)(k & 3) * 32;
+          ft_umma(tmem_base + TM_S + (uint32_t)a * 128, ft_desc(qa + off, 0), ft_desc(ka + off, 0), idesc_s, k != 0);
+        }
+        ft_commit(k_empty(s));
+        ft_commit(s_full(a));
+      };
+      auto issue_pv = [&](int j) {
+        const int s = j % ST;
+        ft_mbar_wait(v_full(s), (uint32_t)(j / ST) & 1u);
+        ft_mbar_wait(p_full, (uint32_t)j & 1u);
+        if (j > 0) ft_mbar_wait(o_empty, (uint32_t)(j - 1) & 1u);   // T_{j-1} has been folded into the register accumulator
+        ft_tc_fence_after();
+        const uint32_t pa = ft_smem_u32(sP), va = ft_smem_u32(sV + s * Cfg::TILE_BYTES);
+#pragma unroll
+        for (int kk = 0; kk < 8; ++kk) {   // 128 keys = 8 k16 steps: P block kk/4, +32 B per step; V: 16 key rows = 2 KB per step
+          const uint64_t da = ft_desc(pa + (uint32_t)(kk >> 2) * FT_TILE + (uint32_t)(kk & 3) * 32, 0);
+          const uint64_t db = ft_desc(va + (uint32_t)kk * 2048, FT_TILE);
+          ft_umma(tmem_base + TM_O, da, db, idesc_o, kk != 0);
+        }
+        ft_commit(v_empty(s));
+        ft_commit(o_full);
+      };
+      ft_mbar_wait(q_ready, 0);
+      issue_s(0);
+      for (int j = 0; j < nk; ++j) {
+        if (j + 1 < nk) issue_s(j + 1);
+        issue_pv(j);
+      }
+    }
+  } else {
+    // ===================== softmax / correction / epilogue (warps 2..5) =====================
+    const int q = warp & 3;                    // TMEM lane quarter this warp may touch
+    const int r = q * 32 + lane;               // query row inside the tile
+    const uint32_t t_lane = tmem_base + ((uint32_t)(q * 32) << 16);
+    ft_mbar_wait(q_full, 0);
+    if (HD % 16 != 0) {   // zero columns HD .. KSTEPS*16-1 of this row (hd = 40: chunk 5 of block 0)
+      constexpr int chunk = HD / 8;
+      *reinterpret_cast<uint4*>(sQ + (chunk >> 3) * FT_TILE + r * 128 + (((chunk & 7) ^ (r & 7)) << 4)) = make_uint4(0, 0, 0, 0);
+    }
+    ft_fence_proxy_async();
+    __syncwarp();
+    if (lane == 0) ft_mbar_arrive(q_ready);
+
+    float m_run = -INFINITY, l_run = 0.f, corr_pending = 0.f;
+    float o_acc[ON];
+#pragma unroll
+    for (int i = 0; i < ON; ++i) o_acc[i] = 0.f;
+    const float c = p.scale_log2;
+
+    auto fold_t = [&](float corr) {   // o = o * corr + T   (T = P.V of the previous tile, in TMEM)
+#pragma unroll
+      for (int cc = 0; cc < ON / 16; ++cc) {
+        uint32_t t[16];
+        ft_tmem_ld16(t_lane + TM_O + cc * 16, t);
+        ft_tmem_ld_wait();
+#pragma unroll
+        for (int e = 0; e < 16; ++e) o_acc[cc * 16 + e] = fmaf(o_acc[cc * 16 + e], corr, __uint_as_float(t[e]));
+      }
+    };
+
+    for (int j = 0; j < nk; ++j) {
+      const int a = j & 1;
+      const int nvalid = min(128, p.skv - j * 128);
+      ft_mbar_wait(s_full(a), (uint32_t)(j >> 1) & 1u);
+      ft_tc_fence_after();
+      const uint32_t s_addr = t_lane + TM_S + (uint32_t)a * 128;
+      // ---- pass 1: row max of the raw scores ----
+      float mx = -INFINITY;
+#pragma unroll 1
+      for (int cc = 0; cc < 4; ++cc) {
+        uint32_t v[32];
+        ft_tmem_ld32(s_addr + cc * 32, v);
+        ft_tmem_ld_wait();
+        if (nvalid < 128) {
+#pragma unroll
+          for (int e = 0; e < 32; ++e)
+            if (cc * 32 + e < nvalid) mx = fmaxf(mx, __uint_as_float(v[e]));
+        } else {
+#pragma unroll
+          for (int e = 0; e < 32; ++e) mx = fmaxf(mx, __uint_as_float(v[e]));
+        }
+      }
+      const float m_new = fmaxf(m_run, mx);
+      const float corr = ft_ex2((m_run - m_new) * c);   // 0 for the first tile (m_run = -inf)
+      const float mneg = -m_new * c;
+      m_run = m_new;
+      // ---- fold the previous tile's P.V into the register accumulator (it finished long ago) ----
+      if (j > 0) {
+        ft_mbar_wait(o_full, (uint32_t)(j - 1) & 1u);
+        ft_tc_fence_after();
+        fold_t(corr_pending);
+        ft_tc_fence_before();
+        __syncwarp();
+        if (lane == 0) ft_mbar_arrive(o_empty);
+      }
+      corr_pending = corr;
+      // ---- pass 2: p = 2^(s*c - m*c), row sum in fp32, P -> fp16 in the UMMA K-major swizzled layout ----
+      float rs = 0.f;
+#pragma unroll 1
+      for (int cc = 0; cc < 4; ++cc) {
+        uint32_t v[32];
+        ft_tmem_ld32(s_addr + cc * 32, v);
+        ft_tmem_ld_wait();
+        uint32_t pk[16];
+#pragma unroll
+        for (int e = 0; e < 32; e += 2) {
+          float p0 = ft_ex2(fmaf(__uint_as_float(v[e]), c, mneg));
+          float p1 = ft_ex2(fmaf(__uint_as_float(v[e + 1]), c, mneg));
+          if (nvalid < 128) {
+            if (cc * 32 + e >= nvalid) p0 = 0.f;
+            if (cc * 32 + e + 1 >= nvalid) p1 = 0.f;
+          }
+          rs += p0 + p1;
+          pk[e >> 1] = h2_as_u32(__floats2half2_rn(p0, p1));
+        }
+        // keys cc*32 .. +31 = 16-byte chunks 4cc .. 4cc+3 of this row: block (4cc+i)/8, swizzled chunk ((4cc+i)%8) ^ (r%8)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int ch = cc * 4 + i;
+          *reinterpret_cast<uint4*>(sP + (ch >> 3) * FT_TILE + r * 128 + (((ch & 7) ^ (r & 7)) << 4)) =
+              make_uint4(pk[4 * i], pk[4 * i + 1], pk[4 * i + 2], pk[4 * i + 3]);
+        }
+      }
+      l_run = fmaf(l_run, corr, rs);
+      // S[a] fully read, P_j written: hand both to the MMA warp
+      ft_tc_fence_before();
+      ft_fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) {
+        ft_mbar_arrive(s_empty(a));
+        ft_mbar_arrive(p_full);
+      }
+    }
+    // ---- last tile's P.V, normalise, store ----
+    ft_mbar_wait(o_full, (uint32_t)(nk - 1) & 1u);
+    ft_tc_fence_after();
+    fold_t(corr_pending);
+    const float inv = 1.f / l_run;
+    __half* orow = p.o + ((size_t)b * p.sq + m0 + r) * p.ldo + col0;
+    if (m0 + r < p.sq) {
+#pragma unroll
+      for (int i = 0; i < HD / 8; ++i) {
+        float f[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) f[e] = o_acc[i * 8 + e] * inv;
+        *reinterpret_cast<uint4*>(orow + i * 8) = pack8(f);
+      }
+    }
+  }
+  ft_tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    ft_tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+  }
+}
+
+template <int HD>
+int ft_launch(const __half* q, int64_t ldq, const __half* k, int64_t ldk, const __half* v, int64_t ldv, __half* o, int64_t ldo,
+              int batch, int heads, int sq, int skv, cudaStream_t st) {
+  using Cfg = FtCfg<HD>;
+  static bool configured = false;
+  if (!configured) {
+    L2D_CUDA(cudaFuncSetAttribute(flash_tcgen05_kernel<HD>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
+    configured = true;
+  }
+  CUtensorMap tq, tk, tv;
+  int rc = get_tmap_2d(q, (int64_t)batch * sq, (int64_t)heads * HD, ldq, 128, &tq);
+  if (rc != L2D_OK) return rc;
+  rc = get_tmap_2d(k, (int64_t)batch * skv, (int64_t)heads * HD, ldk, 128, &tk);
+  if (rc != L2D_OK) return rc;
+  rc = get_tmap_2d(v, (int64_t)batch * skv, (int64_t)heads * HD, ldv, 128, &tv);
+  if (rc != L2D_OK) return rc;
+  FtParams p{o, ldo, sq, skv, heads, 1.4426950408889634f / sqrtf((float)HD)};
+  launch_pdl_if(pdl_family(2), flash_tcgen05_kernel<HD>, dim3(sq / 128, heads, batch), dim3(FT_THREADS), (size_t)Cfg::SMEM, st, tq, tk,
+                tv, p);
+  L2D_LAUNCH_CHECK();
+  return L2D_OK;
+}
+
+}  // namespace
+
+// hd 40 / 80, whole 128-query tiles, 16-byte aligned operands with row pitches that are multiples of 8 elements
+bool attention_tcgen05_supported(const void* q, const void* k, const void* v, const void* o, int64_t ldq, int64_t ldk, int64_t ldv,
+                                 int64_t ldo, int sq, int skv, int hd) {
+  static const bool off = [] {
+    const char* e = getenv("L2D_FLASH_LEGACY");
+    return e && e[0] == '1';
+  }();
+  if (off) return false;
+  auto al = [](const void* ptr) { return (reinterpret_cast<uintptr_t>(ptr) & 15u) == 0; };
+  return (hd == 40 || hd == 80) && sq % 128 == 0 && skv >= 1 && al(q) && al(k) && al(v) && al(o) && ldq % 8 == 0 &&
+         ldk % 8 == 0 && ldv % 8 == 0 && ldo % 8 == 0;
+}
+
+int attention_tcgen05_launch(const __half* q, int64_t ldq, const __half* k, int64_t ldk, const __half* v, int64_t ldv, __half* o,
+                             int64_t ldo, int batch, int heads, int sq, int skv, int hd, cudaStream_t st) {
+  if (hd == 40) return ft_launch<40>(q, ldq, k, ldk, v, ldv, o, ldo, batch, heads, sq, skv, st);
+  if (hd == 80) return ft_launch<80>(q, ldq, k, ldk, v, ldv, o, ldo, batch, heads, sq, skv, st);
+  return fail(L2D_ERR_INVALID, "attention(tcgen05): unsupported head_dim");
+}
+
+}  // namespace l2d

@@ -70,6 +70,13 @@ int conv3x3_launch(const __half* x, int n_img, int h, int w, int cin, const __ha
 int attention_launch(const __half* q, int64_t ldq, const __half* k, int64_t ldk, const __half* v, int64_t ldv, __half* o,
                      int64_t ldo, int batch, int heads, int sq, int skv, int hd, cudaStream_t st);
 
+// tcgen05 / TMEM / TMA flash attention (flash_tcgen05.cu): hd 40 / 80, sq % 128 == 0; everything else takes the legacy
+// mma.sync kernel in flash_attn.cu
+bool attention_tcgen05_supported(const void* q, const void* k, const void* v, const void* o, int64_t ldq, int64_t ldk, int64_t ldv,
+                                 int64_t ldo, int sq, int skv, int hd);
+int attention_tcgen05_launch(const __half* q, int64_t ldq, const __half* k, int64_t ldk, const __half* v, int64_t ldv, __half* o,
+                             int64_t ldo, int batch, int heads, int sq, int skv, int hd, cudaStream_t st);
+
 // engine.cu internals used by the device-resident stream (stream_state.cu)
 int unet_run_eager(::l2d_unet* u, const l2d_unet_step_args* a, cudaStream_t st);   // enqueue one step on st (capturable)
 // time-embedding MLP + stacked time_emb_proj + stacked cross-attention K|V projection: once per (timestep, prompt)

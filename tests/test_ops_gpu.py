@@ -233,7 +233,9 @@ def test_lcm_step_matches_reference_golden():
 # ------------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("b,heads,sq,skv,hd", [(2, 8, 1024, 1024, 40), (2, 8, 256, 256, 80), (2, 8, 64, 64, 160),
                                                (2, 8, 1024, 77, 40), (2, 8, 256, 77, 160), (2, 8, 16, 16, 8),
-                                               (1, 8, 4, 77, 16), (2, 8, 4096, 4096, 40)])
+                                               (1, 8, 4, 77, 16), (2, 8, 4096, 4096, 40), (2, 8, 1024, 1024, 80),
+                                               (2, 8, 1024, 77, 80), (2, 8, 256, 300, 40), (1, 8, 128, 128, 40),
+                                               (3, 8, 384, 129, 80)])
 def test_attention(b, heads, sq, skv, hd):
     from live2diff_b200 import ops
 
@@ -248,6 +250,27 @@ def test_attention(b, heads, sq, skv, hd):
     ref16 = F.scaled_dot_product_attention(split(q, sq), split(k, skv), split(v, skv))
     merge = lambda t: t.transpose(1, 2).reshape(b * sq, c)
     referee(out, merge(ref32), merge(ref16), f"attention b{b} s{sq}x{skv} hd{hd}")
+
+
+@pytest.mark.parametrize("hd,sq", [(40, 1024), (80, 256)])
+def test_attention_fused_qkv_views(hd, sq):
+    """The engine's call pattern: q / k / v are column slices of one fused [M, 3C] projection buffer (row pitch 3C,
+    16-byte aligned column offsets) -- the layout the tcgen05 kernel's TMA tensor maps are built over."""
+    from live2diff_b200 import ops
+
+    b, heads = 2, 8
+    c = heads * hd
+    qkv = rnd(b * sq, 3 * c, seed=27)
+    q, k, v = qkv[:, :c], qkv[:, c:2 * c], qkv[:, 2 * c:]
+    out = ops.attention(q, k, v, b, heads, sq, sq, hd)
+
+    def split(t):
+        return t.reshape(b, sq, heads, hd).transpose(1, 2)
+
+    ref32 = F.scaled_dot_product_attention(split(q.float()), split(k.float()), split(v.float()))
+    ref16 = F.scaled_dot_product_attention(split(q), split(k), split(v))
+    merge = lambda t: t.transpose(1, 2).reshape(b * sq, c)
+    referee(out, merge(ref32), merge(ref16), f"attention fused-qkv views hd{hd} s{sq}")
 
 
 def test_gemm_splitk_workspace_is_restored():
