@@ -127,6 +127,9 @@ struct Lin {          // y = x W^T + b, W [n,k] (ldw = k)
   __half* w = nullptr;
   __half* b = nullptr;
   int n = 0, k = 0;
+  // LayerNorm folded in (Core::fold_ln): w is gamma-scaled, y = rstd (x W'^T - mean ln_s) + ln_b  (ops.cuh GemmFusion)
+  float* ln_s = nullptr;
+  float* ln_b = nullptr;
 };
 struct Norm {
   __half* g = nullptr;
@@ -163,6 +166,7 @@ struct Scratch {
   __half *cols = nullptr, *t = nullptr, *t0 = nullptr, *ln = nullptr, *att = nullptr, *qkv = nullptr, *ff = nullptr,
          *q2 = nullptr, *h1 = nullptr, *sc = nullptr;
   float* gn_ws = nullptr;
+  float2* ln_stats = nullptr;   // [M][slots] row (sum, sumsq) of the current LayerNorm input, written by its producing GEMM
 };
 
 enum Family { FAM_KV = 0, FAM_GEMM = 1, FAM_ATTN = 2, FAM_NORM = 3, FAM_IM2COL = 4, FAM_OTHER = 5, FAM_COUNT = 6 };
@@ -224,11 +228,11 @@ struct Core {
   };
   int gemm_raw(const __half* a, int64_t lda, const __half* w, int64_t ldw, __half* out, int64_t ldo, int m, int n, int k,
                const __half* bias, const __half* rg, int64_t rg_ld, int rpg, const __half* residual, int64_t ldr, int act,
-               int force_bn) {
+               int force_bn, const GemmFusion* fx = nullptr) {
     if (skip_mask & (1 << FAM_GEMM)) return L2D_OK;
     Scope sc(*this, FAM_GEMM);
     GemmConstWeights cw;
-    return gemm_launch(a, lda, w, ldw, out, ldo, m, n, k, bias, rg, rg_ld, rpg, residual, ldr, act, force_bn, st);
+    return gemm_launch(a, lda, w, ldw, out, ldo, m, n, k, bias, rg, rg_ld, rpg, residual, ldr, act, force_bn, st, fx);
   }
   // conv3x3 (pad 1, stride 1) over a channels-last tensor as an implicit GEMM (no im2col matrix)
   int conv3x3(const __half* x, int n_img, int h, int w, int cin, const __half* wt, __half* out, int64_t ldo, int cout,
@@ -331,10 +335,36 @@ struct Core {
     return L2D_OK;
   }
 
+  // LayerNorm(norm) -> Linear(l) becomes one GEMM: scale the weight columns by gamma once, keep the two fp32 vectors
+  int fold_ln(Lin* l, const Norm& norm) {
+    RC(pool.alloc(reinterpret_cast<void**>(&l->ln_s), (size_t)l->n * sizeof(float)));
+    RC(pool.alloc(reinterpret_cast<void**>(&l->ln_b), (size_t)l->n * sizeof(float)));
+    return ln_fold_weights(l->w, l->b, norm.g, norm.b, l->ln_s, l->ln_b, l->n, l->k, st);
+  }
+  static size_t ln_stats_bytes(int m, int c) { return (size_t)m * gemm_stats_slots(m, c, c) * sizeof(float2); }
+
   // ---- op wrappers -------------------------------------------------------------------------
   int gemm(const __half* a, int64_t lda, const Lin& l, __half* out, int64_t ldo, int m, const __half* residual = nullptr,
            int64_t ldr = 0, int act = L2D_ACT_NONE, int force_bn = 0) {
     return gemm_raw(a, lda, l.w, l.k, out, ldo, m, l.n, l.k, l.b, nullptr, 0, 1, residual, ldr, act, force_bn);
+  }
+  // C x C projection whose [m, C] output is the next LayerNorm's input: also emits the row statistics
+  int gemm_emit(const __half* a, int64_t lda, const Lin& l, __half* out, int64_t ldo, int m, const __half* residual = nullptr,
+                int64_t ldr = 0) {
+    GemmFusion fx;
+    fx.stats_out = s.ln_stats;
+    return gemm_raw(a, lda, l.w, l.k, out, ldo, m, l.n, l.k, l.b, nullptr, 0, 1, residual, ldr, L2D_ACT_NONE, 0, &fx);
+  }
+  // Linear(LayerNorm(a)) with the LayerNorm folded into l (fold_ln); a = the un-normalised [m, C] rows
+  int gemm_ln(const __half* a, int64_t lda, const Lin& l, __half* out, int64_t ldo, int m, int act = L2D_ACT_NONE,
+              int force_bn = 0) {
+    GemmFusion fx;
+    fx.ln_stats = s.ln_stats;
+    fx.ln_slots = gemm_stats_slots(m, l.k, l.k);
+    fx.ln_s = l.ln_s;
+    fx.ln_b = l.ln_b;
+    fx.ln_c = l.k;
+    return gemm_raw(a, lda, l.w, l.k, out, ldo, m, l.n, l.k, nullptr, nullptr, 0, 1, nullptr, 0, act, force_bn, &fx);
   }
   int layernorm(const __half* x, const Norm& n, __half* y, int rows, int c) {
     if (skip_mask & ((1 << FAM_NORM) | 64)) return L2D_OK;    // bit 6: LayerNorm only
@@ -369,11 +399,13 @@ struct Core {
       __half* pe_copy = nullptr;
       RC(upload_copy(&pe_copy, static_cast<const __half*>(pe->data), (size_t)L * c));
       RC(pool.halfs(&t->pe_tab[i], (size_t)L * 3 * c));
-      RC(gemm(pe_copy, c, t->qkv[i], t->pe_tab[i], 3 * c, L));
+      RC(gemm(pe_copy, c, t->qkv[i], t->pe_tab[i], 3 * c, L));   // PE tables use the plain projections ...
+      RC(fold_ln(&t->qkv[i], t->ln[i]));                          // ... the step's projections absorb norms[i]
     }
     RC(load_geglu(wt, b + ".ff.net.0.proj", c, m_rows, &t->ff1, &t->ff1_tile));
     RC(load_lin(wt, b + ".ff.net.2", c, 4 * c, true, &t->ff2));
     RC(load_norm(wt, b + ".ff_norm", c, &t->ff_norm));
+    RC(fold_ln(&t->ff1, t->ff_norm));
     RC(load_lin(wt, pp + "proj_out", c, c, true, &t->proj_out));
     return L2D_OK;
   }
@@ -383,11 +415,10 @@ struct Core {
                        const __half* mask, const int64_t* pe_idx, const int64_t* update_idx) {
     const int c = t.c, hw = h * w, m = n_rows * hw;
     RC(gn(x, c, nullptr, 0, t.norm, s.t0, n_rows, h, w, 1e-6f, 0, 0));
-    RC(gemm(s.t0, c, t.proj_in, s.t, c, m));
+    RC(gemm_emit(s.t0, c, t.proj_in, s.t, c, m));
     void* caches[2] = {cache0, cache1};
     for (int i = 0; i < 2; ++i) {
-      RC(layernorm(s.t, t.ln[i], s.ln, m, c));
-      RC(gemm(s.ln, c, t.qkv[i], s.qkv, 3 * c, m));
+      RC(gemm_ln(s.t, c, t.qkv[i], s.qkv, 3 * c, m));   // norms[i] folded in (motion_module.py:420-428)
       if (warm_frames > 0) {   // VersatileAttention over the frames + sink-slot fill (motion_module.py:469-530)
         WarmupAttnParams wp{};
         wp.q = s.qkv; wp.k = s.qkv + c; wp.v = s.qkv + 2 * c; wp.ld = 3 * c;
@@ -399,7 +430,7 @@ struct Core {
           Scope sc(*this, FAM_KV);
           RC(warmup_attn_launch(wp, st));
         }
-        RC(gemm(s.att, c, t.out[i], s.t, c, m, s.t, c));
+        RC(gemm_emit(s.att, c, t.out[i], s.t, c, m, s.t, c));
         continue;
       }
       KvAttnParams p{};
@@ -410,10 +441,9 @@ struct Core {
       p.n_rows = n_rows; p.hw = hw; p.L = L; p.C = c; p.heads = heads;
       p.pdl = 1;   // behind the QKV GEMM: the kernel's cache / PE prefetch overlaps that GEMM's tail
       RC(kv(p));
-      RC(gemm(s.att, c, t.out[i], s.t, c, m, s.t, c));
+      RC(gemm_emit(s.att, c, t.out[i], s.t, c, m, s.t, c));
     }
-    RC(layernorm(s.t, t.ff_norm, s.ln, m, c));
-    RC(gemm(s.ln, c, t.ff1, s.ff, 4 * c, m, nullptr, 0, L2D_ACT_GEGLU, t.ff1_tile));
+    RC(gemm_ln(s.t, c, t.ff1, s.ff, 4 * c, m, L2D_ACT_GEGLU, t.ff1_tile));   // ff_norm folded in
     RC(gemm(s.ff, 4 * c, t.ff2, s.t, c, m, s.t, c));
     RC(gemm(s.t, c, t.proj_out, out, c, m, x, c));
     return L2D_OK;
@@ -452,6 +482,7 @@ extern "C" int l2d_tt_create(l2d_tt** out, const l2d_tensor* weights, int n_weig
   RC(k.pool.halfs(&k.s.ff, m * 4 * c));
   RC(k.pool.alloc(reinterpret_cast<void**>(&k.s.gn_ws), (size_t)l2d_groupnorm_workspace_bytes(n_rows, groups)));
   L2D_CUDA(cudaMemsetAsync(k.s.gn_ws, 0, (size_t)l2d_groupnorm_workspace_bytes(n_rows, groups), k.st));
+  RC(k.pool.alloc(reinterpret_cast<void**>(&k.s.ln_stats), Core::ln_stats_bytes((int)m, channels)));
   RC(k.pool.halfs(&t->x_nhwc, m * c));
   RC(k.pool.halfs(&t->y_nhwc, m * c));
   WeightTable wt;
@@ -556,6 +587,9 @@ int load_spatial(l2d_unet* u, const WeightTable& wt, const std::string& p, int c
   RC(k.load_lin(wt, b + ".ff.net.2", c, 4 * c, true, &s->ff2));
   RC(k.load_norm(wt, b + ".norm3", c, &s->ln3));
   RC(k.load_lin(wt, p + ".proj_out", c, c, true, &s->proj_out));
+  RC(k.fold_ln(&s->qkv, s->ln1));     // norm1 -> attn1.to_q/k/v, norm2 -> attn2.to_q, norm3 -> ff (attention.py:243-268)
+  RC(k.fold_ln(&s->q2, s->ln2));
+  RC(k.fold_ln(&s->ff1, s->ln3));
   (void)cd;
   return L2D_OK;
 }
@@ -614,21 +648,18 @@ int spatial_forward(l2d_unet* u, const SpatialP& sp, const __half* x, __half* ou
   const int c = sp.c, m = lv.m, hw = lv.h * lv.w, n = k.n_rows, hd = c / k.heads;
   const int ctx = u->cfg.ctx_len;
   RC(k.gn(x, c, nullptr, 0, sp.norm, s.t0, n, lv.h, lv.w, 1e-6f, 0, 0));
-  RC(k.gemm(s.t0, c, sp.proj_in, s.t, c, m));
-  // self-attention
-  RC(k.layernorm(s.t, sp.ln1, s.ln, m, c));
-  RC(k.gemm(s.ln, c, sp.qkv, s.qkv, 3 * c, m));
+  RC(k.gemm_emit(s.t0, c, sp.proj_in, s.t, c, m));
+  // self-attention (norm1 folded into the fused q/k/v projection)
+  RC(k.gemm_ln(s.t, c, sp.qkv, s.qkv, 3 * c, m));
   RC(k.attn(s.qkv, 3 * c, s.qkv + c, 3 * c, s.qkv + 2 * c, 3 * c, s.att, c, n, hw, hw, hd));
-  RC(k.gemm(s.att, c, sp.out1, s.t, c, m, s.t, c));
-  // cross-attention against the (pre-projected) text context
-  RC(k.layernorm(s.t, sp.ln2, s.ln, m, c));
-  RC(k.gemm(s.ln, c, sp.q2, s.q2, c, m));
+  RC(k.gemm_emit(s.att, c, sp.out1, s.t, c, m, s.t, c));
+  // cross-attention against the (pre-projected) text context (norm2 folded into to_q)
+  RC(k.gemm_ln(s.t, c, sp.q2, s.q2, c, m));
   const __half* kv = u->kv2 + sp.kv2_off;
   RC(k.attn(s.q2, c, kv, u->kv2_all.n, kv + c, u->kv2_all.n, s.att, c, n, hw, ctx, hd));
-  RC(k.gemm(s.att, c, sp.out2, s.t, c, m, s.t, c));
-  // feed-forward
-  RC(k.layernorm(s.t, sp.ln3, s.ln, m, c));
-  RC(k.gemm(s.ln, c, sp.ff1, s.ff, 4 * c, m, nullptr, 0, L2D_ACT_GEGLU, sp.ff1_tile));
+  RC(k.gemm_emit(s.att, c, sp.out2, s.t, c, m, s.t, c));
+  // feed-forward (norm3 folded into the GEGLU projection)
+  RC(k.gemm_ln(s.t, c, sp.ff1, s.ff, 4 * c, m, L2D_ACT_GEGLU, sp.ff1_tile));
   RC(k.gemm(s.ff, 4 * c, sp.ff2, s.t, c, m, s.t, c));
   RC(k.gemm(s.t, c, sp.proj_out, out, c, m, x, c));
   return L2D_OK;
@@ -846,6 +877,11 @@ extern "C" int l2d_unet_create(l2d_unet** out, const l2d_unet_config* cfg, const
   RC(k.pool.halfs(&s.ff, max_mc * 4));
   RC(k.pool.alloc(reinterpret_cast<void**>(&s.gn_ws), (size_t)l2d_groupnorm_workspace_bytes(n, cfg->groups)));
   L2D_CUDA(cudaMemsetAsync(s.gn_ws, 0, (size_t)l2d_groupnorm_workspace_bytes(n, cfg->groups), k.st));
+  {
+    size_t ln_bytes = 16;
+    for (int i = 0; i < nlev; ++i) ln_bytes = std::max(ln_bytes, Core::ln_stats_bytes(u->lv[i].m, u->lv[i].c));
+    RC(k.pool.alloc(reinterpret_cast<void**>(&s.ln_stats), ln_bytes));
+  }
   RC(k.pool.halfs(&u->hA, max_mc));
   RC(k.pool.halfs(&u->hB, max_mc));
   RC(k.pool.halfs(&u->map_a, max_map));

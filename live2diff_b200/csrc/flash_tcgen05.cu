@@ -12,8 +12,10 @@
 //                                  of two S accumulators in TMEM, so that S_{j+1} is computed while S_j is in the softmax
 //                T_j = P_j . V_j   (M = 128, N = hd rounded to 16, K = 128 keys; A = P from shared memory, K-major;
 //                                  B = the V tile exactly as TMA delivered it = MN-major, 128B swizzle)
-//   warps 2-5  softmax + correction + epilogue: thread = one query row (tcgen05.ld 32x32b: TMEM lane = row), so row max /
-//              row sum need no shuffles; P is rounded to fp16 (like the fused SDPA kernels the reference dispatches to)
+//   warps 2-9  softmax + correction + epilogue: two threads per query row (tcgen05.ld 32x32b: TMEM lane = row; warps w and
+//              w + 4 share a lane quarter and split the 128 keys / the output channels), so the row max costs one 64-thread
+//              named barrier per tile and no shuffles; the 64 scores of a thread stay in registers between the max and the
+//              exp pass, so the S accumulator is released right after one TMEM read; P is rounded to fp16 (like the fused SDPA kernels the reference dispatches to)
 //              and written into shared memory in the UMMA K-major swizzled layout; the running output lives in registers
 //              (o = o * corr + T_j, flash-attention's online softmax in fp32), the 1/l normalisation is applied once.
 // hd = 40: the K extent of Q.K^T is padded to 48 by zeroing columns 40..47 of the Q tile in shared memory (the K tile's
@@ -96,6 +98,11 @@ __device__ __forceinline__ void ft_tmem_ld16(uint32_t addr, uint32_t (&r)[16]) {
         "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
       : "r"(addr));
 }
+__device__ __forceinline__ void ft_tmem_ld8(uint32_t addr, uint32_t* r) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(addr));
+}
 __device__ __forceinline__ float ft_ex2(float x) {   // arguments <= 0: no overflow; tiny results flush to zero
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
@@ -128,7 +135,7 @@ struct FtParams {
   float scale_log2;   // log2(e) / sqrt(hd)
 };
 
-constexpr int FT_THREADS = 192;   // TMA warp, MMA warp, 4 softmax warps
+constexpr int FT_THREADS = 320;   // TMA warp, MMA warp, 8 softmax warps (two threads per query row)
 constexpr int FT_TILE = 128 * 128;   // bytes of one [128 rows x 64 fp16] swizzled block
 
 template <int HD>
@@ -139,7 +146,8 @@ struct FtCfg {
   static constexpr int ON_MMA = NBLK * 64;          // MMA N of P.V: whole 64-channel swizzle atoms of the V tile
   static constexpr int STAGES = HD <= 64 ? 3 : 2;   // K / V ring depth
   static constexpr int TILE_BYTES = NBLK * FT_TILE;
-  static constexpr int SMEM = TILE_BYTES * (1 + 2 * STAGES) + 2 * FT_TILE /* P */ + 256 /* barriers */ + 1024 /* align */;
+  static constexpr int SMEM = TILE_BYTES * (1 + 2 * STAGES) + 2 * FT_TILE /* P */ + 256 /* barriers */ +
+                              6 * 128 * 4 /* row max / row sum exchange */ + 1024 /* align */;
 };
 
 template <int HD>
@@ -165,6 +173,7 @@ flash_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
   auto s_full = [&](int b) { return bar0 + 40 + 8u * (4 * ST + b); };
   auto s_empty = [&](int b) { return bar0 + 40 + 8u * (4 * ST + 2 + b); };
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 5 + 4 * ST + 4);
+  float* s_xch = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 256);   // [2 S buffers][2 halves][128] max, [2][128] sums
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int b = blockIdx.z, h = blockIdx.y, m0 = blockIdx.x * 128;
@@ -177,10 +186,10 @@ flash_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_k) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_v) : "memory");
     ft_mbar_init(q_full, 1);
-    ft_mbar_init(q_ready, 4);
-    ft_mbar_init(p_full, 4);
+    ft_mbar_init(q_ready, 8);
+    ft_mbar_init(p_full, 8);
     ft_mbar_init(o_full, 1);
-    ft_mbar_init(o_empty, 4);
+    ft_mbar_init(o_empty, 8);
     for (int s = 0; s < ST; ++s) {
       ft_mbar_init(k_full(s), 1);
       ft_mbar_init(k_empty(s), 1);
@@ -189,7 +198,7 @@ flash_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
     }
     for (int a = 0; a < 2; ++a) {
       ft_mbar_init(s_full(a), 1);
-      ft_mbar_init(s_empty(a), 4);
+      ft_mbar_init(s_empty(a), 8);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -266,12 +275,16 @@ flash_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
       }
     }
   } else {
-    // ===================== softmax / correction / epilogue (warps 2..5) =====================
+    // ===================== softmax / correction / epilogue (warps 2..9) =====================
+    // Two threads per query row: warps w and w + 4 may touch the same TMEM lane quarter; `half` 0 owns keys 0..63 of the
+    // tile (P block 0) and the first OC output channels, `half` 1 keys 64..127 and the rest.  The pair meets once per
+    // tile (named barrier of 64 threads) to exchange the partial row max; row sums stay partial until the end.
     const int q = warp & 3;                    // TMEM lane quarter this warp may touch
+    const int half = (warp - 2) >> 2;
     const int r = q * 32 + lane;               // query row inside the tile
     const uint32_t t_lane = tmem_base + ((uint32_t)(q * 32) << 16);
     ft_mbar_wait(q_full, 0);
-    if (HD % 16 != 0) {   // zero columns HD .. KSTEPS*16-1 of this row (hd = 40: chunk 5 of block 0)
+    if (HD % 16 != 0 && half == 0) {   // zero columns HD .. KSTEPS*16-1 of this row (hd = 40: chunk 5 of block 0)
       constexpr int chunk = HD / 8;
       *reinterpret_cast<uint4*>(sQ + (chunk >> 3) * FT_TILE + r * 128 + (((chunk & 7) ^ (r & 7)) << 4)) = make_uint4(0, 0, 0, 0);
     }
@@ -279,45 +292,52 @@ flash_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
     __syncwarp();
     if (lane == 0) ft_mbar_arrive(q_ready);
 
+    constexpr int OC = ON / 2;                 // output channels per thread (24 / 40), in 8-column TMEM loads
     float m_run = -INFINITY, l_run = 0.f, corr_pending = 0.f;
-    float o_acc[ON];
+    float o_acc[OC];
 #pragma unroll
-    for (int i = 0; i < ON; ++i) o_acc[i] = 0.f;
+    for (int i = 0; i < OC; ++i) o_acc[i] = 0.f;
     const float c = p.scale_log2;
+    const uint32_t o_addr = t_lane + TM_O + (uint32_t)(half * OC);
 
     auto fold_t = [&](float corr) {   // o = o * corr + T   (T = P.V of the previous tile, in TMEM)
+      uint32_t t[OC];
 #pragma unroll
-      for (int cc = 0; cc < ON / 16; ++cc) {
-        uint32_t t[16];
-        ft_tmem_ld16(t_lane + TM_O + cc * 16, t);
-        ft_tmem_ld_wait();
+      for (int cc = 0; cc < OC / 8; ++cc) ft_tmem_ld8(o_addr + cc * 8, &t[cc * 8]);
+      ft_tmem_ld_wait();
 #pragma unroll
-        for (int e = 0; e < 16; ++e) o_acc[cc * 16 + e] = fmaf(o_acc[cc * 16 + e], corr, __uint_as_float(t[e]));
-      }
+      for (int e = 0; e < OC; ++e) o_acc[e] = fmaf(o_acc[e], corr, __uint_as_float(t[e]));
     };
 
     for (int j = 0; j < nk; ++j) {
       const int a = j & 1;
-      const int nvalid = min(128, p.skv - j * 128);
+      const int nvalid = min(128, p.skv - j * 128) - half * 64;   // valid keys among this thread's 64
       ft_mbar_wait(s_full(a), (uint32_t)(j >> 1) & 1u);
       ft_tc_fence_after();
-      const uint32_t s_addr = t_lane + TM_S + (uint32_t)a * 128;
-      // ---- pass 1: row max of the raw scores ----
+      const uint32_t s_addr = t_lane + TM_S + (uint32_t)(a * 128 + half * 64);
+      // ---- this thread's 64 scores -> registers; S[a] can then be overwritten by the tile after next ----
+      uint32_t v0[32], v1[32];
+      ft_tmem_ld32(s_addr, v0);
+      ft_tmem_ld32(s_addr + 32, v1);
+      ft_tmem_ld_wait();
+      ft_tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ft_mbar_arrive(s_empty(a));
       float mx = -INFINITY;
-#pragma unroll 1
-      for (int cc = 0; cc < 4; ++cc) {
-        uint32_t v[32];
-        ft_tmem_ld32(s_addr + cc * 32, v);
-        ft_tmem_ld_wait();
-        if (nvalid < 128) {
+      if (nvalid < 64) {
 #pragma unroll
-          for (int e = 0; e < 32; ++e)
-            if (cc * 32 + e < nvalid) mx = fmaxf(mx, __uint_as_float(v[e]));
-        } else {
-#pragma unroll
-          for (int e = 0; e < 32; ++e) mx = fmaxf(mx, __uint_as_float(v[e]));
+        for (int e = 0; e < 32; ++e) {
+          if (e < nvalid) mx = fmaxf(mx, __uint_as_float(v0[e]));
+          if (32 + e < nvalid) mx = fmaxf(mx, __uint_as_float(v1[e]));
         }
+      } else {
+#pragma unroll
+        for (int e = 0; e < 32; ++e) mx = fmaxf(mx, fmaxf(__uint_as_float(v0[e]), __uint_as_float(v1[e])));
       }
+      // ---- exchange the partial max with the thread holding the other 64 keys of this row ----
+      s_xch[(a * 2 + half) * 128 + r] = mx;
+      asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");
+      mx = fmaxf(mx, s_xch[(a * 2 + (half ^ 1)) * 128 + r]);
       const float m_new = fmaxf(m_run, mx);
       const float corr = ft_ex2((m_run - m_new) * c);   // 0 for the first tile (m_run = -inf)
       const float mneg = -m_new * c;
@@ -332,56 +352,53 @@ flash_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
         if (lane == 0) ft_mbar_arrive(o_empty);
       }
       corr_pending = corr;
-      // ---- pass 2: p = 2^(s*c - m*c), row sum in fp32, P -> fp16 in the UMMA K-major swizzled layout ----
+      // ---- p = 2^(s*c - m*c), partial row sum in fp32, P -> fp16 into block `half` of the UMMA K-major swizzled tile ----
       float rs = 0.f;
-#pragma unroll 1
-      for (int cc = 0; cc < 4; ++cc) {
-        uint32_t v[32];
-        ft_tmem_ld32(s_addr + cc * 32, v);
-        ft_tmem_ld_wait();
+      uint8_t* prow = sP + half * FT_TILE + r * 128;
+      auto emit = [&](const uint32_t (&v)[32], int cb) {   // keys cb*32 .. +31 of this thread's 64
         uint32_t pk[16];
 #pragma unroll
         for (int e = 0; e < 32; e += 2) {
           float p0 = ft_ex2(fmaf(__uint_as_float(v[e]), c, mneg));
           float p1 = ft_ex2(fmaf(__uint_as_float(v[e + 1]), c, mneg));
-          if (nvalid < 128) {
-            if (cc * 32 + e >= nvalid) p0 = 0.f;
-            if (cc * 32 + e + 1 >= nvalid) p1 = 0.f;
+          if (nvalid < 64) {
+            if (cb * 32 + e >= nvalid) p0 = 0.f;
+            if (cb * 32 + e + 1 >= nvalid) p1 = 0.f;
           }
           rs += p0 + p1;
           pk[e >> 1] = h2_as_u32(__floats2half2_rn(p0, p1));
         }
-        // keys cc*32 .. +31 = 16-byte chunks 4cc .. 4cc+3 of this row: block (4cc+i)/8, swizzled chunk ((4cc+i)%8) ^ (r%8)
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const int ch = cc * 4 + i;
-          *reinterpret_cast<uint4*>(sP + (ch >> 3) * FT_TILE + r * 128 + (((ch & 7) ^ (r & 7)) << 4)) =
-              make_uint4(pk[4 * i], pk[4 * i + 1], pk[4 * i + 2], pk[4 * i + 3]);
+        for (int i = 0; i < 4; ++i) {   // 16-byte chunk cb*4 + i of the row, swizzled with the row index
+          const int ch = cb * 4 + i;
+          *reinterpret_cast<uint4*>(prow + ((ch ^ (r & 7)) << 4)) = make_uint4(pk[4 * i], pk[4 * i + 1], pk[4 * i + 2], pk[4 * i + 3]);
         }
-      }
+      };
+      emit(v0, 0);
+      emit(v1, 1);
       l_run = fmaf(l_run, corr, rs);
-      // S[a] fully read, P_j written: hand both to the MMA warp
-      ft_tc_fence_before();
+      // P_j written: hand it to the MMA warp
       ft_fence_proxy_async();
       __syncwarp();
-      if (lane == 0) {
-        ft_mbar_arrive(s_empty(a));
-        ft_mbar_arrive(p_full);
-      }
+      if (lane == 0) ft_mbar_arrive(p_full);
     }
-    // ---- last tile's P.V, normalise, store ----
+    // ---- last tile's P.V, total row sum, normalise, store this thread's channels ----
     ft_mbar_wait(o_full, (uint32_t)(nk - 1) & 1u);
     ft_tc_fence_after();
     fold_t(corr_pending);
-    const float inv = 1.f / l_run;
-    __half* orow = p.o + ((size_t)b * p.sq + m0 + r) * p.ldo + col0;
+    s_xch[(4 + half) * 128 + r] = l_run;
+    asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");
+    const float inv = 1.f / (l_run + s_xch[(4 + (half ^ 1)) * 128 + r]);
+    __half* orow = p.o + ((size_t)b * p.sq + m0 + r) * p.ldo + col0 + half * OC;
     if (m0 + r < p.sq) {
 #pragma unroll
-      for (int i = 0; i < HD / 8; ++i) {
-        float f[8];
+      for (int i = 0; i < OC / 8; ++i) {
+        if (half * OC + i * 8 < HD) {
+          float f[8];
 #pragma unroll
-        for (int e = 0; e < 8; ++e) f[e] = o_acc[i * 8 + e] * inv;
-        *reinterpret_cast<uint4*>(orow + i * 8) = pack8(f);
+          for (int e = 0; e < 8; ++e) f[e] = o_acc[i * 8 + e] * inv;
+          *reinterpret_cast<uint4*>(orow + i * 8) = pack8(f);
+        }
       }
     }
   }

@@ -160,6 +160,14 @@ struct GemmEpilogue {
   int64_t ws_ld;
   int64_t ws_slice;   // elements per split slice = M_pad * ws_ld
   long long* dbg;     // optional per-CTA timeline (8 clock64 stamps per CTA), see l2d_gemm_set_debug
+  // LayerNorm fusion (ops.cuh GemmFusion)
+  float2* stats_out;        // producer: [M][stats_slots] (sum, sumsq) of the stored fp16 row values
+  int stats_slots;
+  const float2* ln_stats;   // consumer: row statistics of A
+  int ln_slots;
+  const float* ln_s;
+  const float* ln_b;
+  float ln_inv_c, ln_eps;
 };
 
 template <int BN>
@@ -176,7 +184,12 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
 // Persistent kernel: grid = min(#tiles, #SMs); every CTA walks tiles t = blockIdx.x, +gridDim.x, ... (N-tile fastest,
 // then M-tile, then K-split).  The smem operand ring runs continuously across tiles and the accumulator is
 // double-buffered in TMEM, so tile i's epilogue overlaps tile i+1's TMA loads and MMAs.
-template <int BN, int STAGES>
+// CL = true: split-K inside a thread-block cluster.  The `splits` CTAs of one output tile form a cluster (blockIdx.x =
+// tile * splits + z); each runs its K range into TMEM, then scatters its fp32 partial tile over the cluster through
+// distributed shared memory -- CTA z' receives, from every CTA, the column slice [z' * BN/splits, +BN/splits) -- and after
+// one cluster barrier reduces its slice in CTA-rank order (deterministic) and applies the epilogue.  No fp32 workspace in
+// HBM/L2 and no second kernel (the non-cluster path below keeps the slice buffer + splitk_finish_kernel).
+template <int BN, int STAGES, bool CL = false>
 __global__ void __launch_bounds__(320, 1)
 gemm_f16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                         const GemmEpilogue epi, const ConvGeom cg, int M, int N, int K, int tiles_n, int tiles_m,
@@ -200,13 +213,15 @@ gemm_f16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid
   const int total_kb = (K + BK - 1) / BK;
   const int kb_per = (total_kb + splits - 1) / splits;
   const int total_tiles = tiles_n * tiles_m * splits;
-  const int my_tiles = ((int)blockIdx.x < total_tiles) ? (total_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+  const int my_tiles = CL ? 1 : ((int)blockIdx.x < total_tiles) ? (total_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+  float* cl_part = reinterpret_cast<float*>(smem + STAGES * S::STAGE_BYTES + 256);   // CL: [splits][128 rows][BN / splits] fp32
 
   struct Tile {
     int n0, m0, mt, z, kb_begin, num_kb, cn0, ch0, cw0;
   };
   auto decode = [&](int i) {
-    const int t = (int)blockIdx.x + i * (int)gridDim.x;
+    const int t = CL ? (int)blockIdx.x / splits + ((int)blockIdx.x % splits) * (tiles_n * tiles_m)
+                     : (int)blockIdx.x + i * (int)gridDim.x;
     Tile tl;
     tl.z = t / (tiles_n * tiles_m);
     const int rem = t - tl.z * (tiles_n * tiles_m);
@@ -354,11 +369,51 @@ gemm_f16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid
         res0 = *reinterpret_cast<const uint4*>(res_ptr + cc_begin * 16);          // plain loads: may alias `out`
         if (n0 + cc_begin * 16 + 8 < N) res1 = *reinterpret_cast<const uint4*>(res_ptr + cc_begin * 16 + 8);
       }
+      // LayerNorm consumer: this row's mean / rstd from the producer's per-tile partial sums (fixed slot order)
+      float ln_rstd = 1.f, ln_mr = 0.f;   // y = rstd * acc - (rstd * mean) * s[n] + b'[n]
+      if (epi.ln_stats && row_ok) {
+        const float2* sp = epi.ln_stats + (size_t)row * epi.ln_slots;
+        float sm = 0.f, sq = 0.f;
+        for (int t2 = 0; t2 < epi.ln_slots; ++t2) {
+          const float2 v2 = __ldcg(sp + t2);
+          sm += v2.x;
+          sq += v2.y;
+        }
+        const float mean = sm * epi.ln_inv_c;
+        ln_rstd = rsqrtf(fmaxf(sq * epi.ln_inv_c - mean * mean, 0.f) + epi.ln_eps);
+        ln_mr = ln_rstd * mean;
+      }
+      float st_sum = 0.f, st_sq = 0.f;    // LayerNorm producer: sums over this warp's columns of the row
       mbar_wait(smem_u32(&tmem_full_bar[as]), (uint32_t)(i >> 1) & 1u);
       if (dbg && i == 0 && threadIdx.x == 64) dbg[4] = clock64();   // accumulator ready
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN);
-      if (splits > 1) {
+      if (CL) {
+        // ---- cluster split-K, phase A: scatter this CTA's fp32 partial tile into the owners' shared memory ----
+        const int W = BN / splits;                       // columns reduced by each CTA of the cluster (8 .. 64)
+        const uint32_t my_slot = smem_u32(cl_part) + (uint32_t)((tl.z * 128 + q * 32 + lane) * W) * 4u;
+#pragma unroll 1
+        for (int cc = cc_begin; cc < cc_end; ++cc) {
+          uint32_t r[16];
+          if (tl.num_kb > 0) {
+            tmem_ld16(taddr + cc * 16, r);
+            tmem_ld_wait();
+          } else {
+#pragma unroll
+            for (int e = 0; e < 16; ++e) r[e] = 0u;
+          }
+#pragma unroll
+          for (int g4 = 0; g4 < 4; ++g4) {
+            const int col = cc * 16 + g4 * 4;
+            const int owner = col / W, cin = col - owner * W;
+            uint32_t raddr;
+            asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(raddr) : "r"(my_slot + (uint32_t)cin * 4u), "r"(owner));
+            asm volatile("st.shared::cluster.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(raddr), "r"(r[g4 * 4]), "r"(r[g4 * 4 + 1]),
+                         "r"(r[g4 * 4 + 2]), "r"(r[g4 * 4 + 3])
+                         : "memory");
+          }
+        }
+      } else if (splits > 1) {
         // ---- split-K: store this split's fp32 partial tile (zeros when the split owns no k-blocks); slices are
         //      indexed by output row and summed by splitk_finish_kernel ----
         float* wrow = epi.ws + (size_t)tl.z * epi.ws_slice + (size_t)row * epi.ws_ld + n0;
@@ -396,6 +451,21 @@ gemm_f16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid
 #pragma unroll
           for (int e = 0; e < 16; ++e) v[e] = __uint_as_float(r[e]);
           const bool lo_ok = n0 + c0 < N, hi_ok = n0 + c0 + 8 < N;
+          if (epi.ln_stats) {
+            const float* sv = epi.ln_s + n0 + c0;
+            const float* bv = epi.ln_b + n0 + c0;
+#pragma unroll
+            for (int q4 = 0; q4 < 4; ++q4) {
+              if (n0 + c0 + q4 * 4 < N) {
+                const float4 s4 = __ldg(reinterpret_cast<const float4*>(sv + q4 * 4));
+                const float4 b4 = __ldg(reinterpret_cast<const float4*>(bv + q4 * 4));
+                v[q4 * 4 + 0] = fmaf(v[q4 * 4 + 0], ln_rstd, fmaf(-ln_mr, s4.x, b4.x));
+                v[q4 * 4 + 1] = fmaf(v[q4 * 4 + 1], ln_rstd, fmaf(-ln_mr, s4.y, b4.y));
+                v[q4 * 4 + 2] = fmaf(v[q4 * 4 + 2], ln_rstd, fmaf(-ln_mr, s4.z, b4.z));
+                v[q4 * 4 + 3] = fmaf(v[q4 * 4 + 3], ln_rstd, fmaf(-ln_mr, s4.w, b4.w));
+              }
+            }
+          }
           if (bias_ptr) {
             float b[8];
             if (lo_ok) {
@@ -442,12 +512,34 @@ gemm_f16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid
               lo[e] = v[e];
               hi[e] = v[8 + e];
             }
-            if (lo_ok) *reinterpret_cast<uint4*>(out_ptr + c0) = pack8(lo);
-            if (hi_ok) *reinterpret_cast<uint4*>(out_ptr + c0 + 8) = pack8(hi);
+            const uint4 plo = pack8(lo), phi = pack8(hi);
+            if (lo_ok) *reinterpret_cast<uint4*>(out_ptr + c0) = plo;
+            if (hi_ok) *reinterpret_cast<uint4*>(out_ptr + c0 + 8) = phi;
+            if (epi.stats_out) {   // statistics of the values as stored (fp16-rounded), like a LayerNorm reading them back
+              float f[8];
+              if (lo_ok) {
+                unpack8(plo, f);
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                  st_sum += f[e];
+                  st_sq = fmaf(f[e], f[e], st_sq);
+                }
+              }
+              if (hi_ok) {
+                unpack8(phi, f);
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                  st_sum += f[e];
+                  st_sq = fmaf(f[e], f[e], st_sq);
+                }
+              }
+            }
           }
           res0 = nres0;
           res1 = nres1;
         }
+        if (epi.stats_out && row_ok)
+          epi.stats_out[(size_t)row * epi.stats_slots + (n0 / BN) * 2 + h] = make_float2(st_sum, st_sq);
       } else {
         // GEGLU: tile columns [0,BN/2) = value half, [BN/2,BN) = matching gate half (weights interleaved by
         // l2d_geglu_interleave); output columns (n0/2) + ...
@@ -472,11 +564,32 @@ gemm_f16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid
               unpack8(ldg_cached(bias_ptr + cc * 16 + hlf * 8), bh);
               unpack8(ldg_cached(bias_ptr + HB + cc * 16 + hlf * 8), bg);
             }
+            float sh[8], sg[8];
+            if (epi.ln_stats && colh + hlf * 8 < N) {   // LayerNorm consumer: (s, b') of the value and gate columns
+              const float* svh = epi.ln_s + n0 + cc * 16 + hlf * 8;
+              const float* bvh = epi.ln_b + n0 + cc * 16 + hlf * 8;
+#pragma unroll
+              for (int q4 = 0; q4 < 2; ++q4) {
+                const float4 a4 = __ldg(reinterpret_cast<const float4*>(svh + q4 * 4));
+                const float4 b4 = __ldg(reinterpret_cast<const float4*>(svh + HB + q4 * 4));
+                const float4 c4 = __ldg(reinterpret_cast<const float4*>(bvh + q4 * 4));
+                const float4 d4 = __ldg(reinterpret_cast<const float4*>(bvh + HB + q4 * 4));
+                sh[q4 * 4 + 0] = a4.x; sh[q4 * 4 + 1] = a4.y; sh[q4 * 4 + 2] = a4.z; sh[q4 * 4 + 3] = a4.w;
+                sg[q4 * 4 + 0] = b4.x; sg[q4 * 4 + 1] = b4.y; sg[q4 * 4 + 2] = b4.z; sg[q4 * 4 + 3] = b4.w;
+                bh[q4 * 4 + 0] = c4.x; bh[q4 * 4 + 1] = c4.y; bh[q4 * 4 + 2] = c4.z; bh[q4 * 4 + 3] = c4.w;
+                bg[q4 * 4 + 0] = d4.x; bg[q4 * 4 + 1] = d4.y; bg[q4 * 4 + 2] = d4.z; bg[q4 * 4 + 3] = d4.w;
+              }
+            } else {
+#pragma unroll
+              for (int e = 0; e < 8; ++e) sh[e] = sg[e] = 0.f;
+            }
 #pragma unroll
             for (int e = 0; e < 8; ++e) {
               // the reference rounds the projection to fp16 before h * gelu(g) (GEGLU.forward on an fp16 Linear output)
-              const float hval = __half2float(__float2half_rn(__uint_as_float(rh[hlf * 8 + e]) + bh[e]));
-              const float gval = __half2float(__float2half_rn(__uint_as_float(rgt[hlf * 8 + e]) + bg[e]));
+              const float ah = fmaf(__uint_as_float(rh[hlf * 8 + e]), ln_rstd, fmaf(-ln_mr, sh[e], bh[e]));
+              const float ag = fmaf(__uint_as_float(rgt[hlf * 8 + e]), ln_rstd, fmaf(-ln_mr, sg[e], bg[e]));
+              const float hval = __half2float(__float2half_rn(ah));
+              const float gval = __half2float(__float2half_rn(ag));
               v[hlf * 8 + e] = hval * gelu_erf_f(gval);
             }
           }
@@ -498,6 +611,62 @@ gemm_f16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid
       __syncwarp();
       if (lane == 0) mbar_arrive(smem_u32(&tmem_empty_bar[as]));
       if (dbg && i == 0 && threadIdx.x == 64) dbg[5] = clock64();   // epilogue of the first tile done (warp 2)
+    }
+  }
+  if constexpr (CL) {
+    // every thread of every CTA of the cluster: partial tiles have landed in their owners' shared memory
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+    if (warp >= 2) {
+      // ---- phase B: this CTA reduces column slice z of the tile over the cluster, in CTA-rank order ----
+      const Tile tl = decode(0);
+      const int W = BN / splits;
+      const int te = (int)threadIdx.x - 64;            // 0..255
+      const int trow = te & 127, part = te >> 7;
+      const int Wp = W >= 16 ? W / 2 : W;              // columns per thread group (multiple of 8)
+      int row = tl.m0 + trow;
+      bool row_ok = row < M;
+      if (cg.enabled) {
+        const int iw = trow % cg.bw, ih = (trow / cg.bw) % cg.bh, in = trow / (cg.bw * cg.bh);
+        row_ok = tl.cn0 + in < cg.N;
+        row = ((tl.cn0 + in) * cg.H + tl.ch0 + ih) * cg.W + tl.cw0 + iw;
+      }
+      if (row_ok && (W >= 16 || part == 0)) {
+        const int cbase = part * Wp;                   // first column of this thread inside the slice
+        for (int c8 = 0; c8 < Wp; c8 += 8) {
+          const int col = tl.n0 + tl.z * W + cbase + c8;   // global output column
+          if (col >= N) break;
+          float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+          for (int z2 = 0; z2 < splits; ++z2) {
+            const float* src = cl_part + (size_t)(z2 * 128 + trow) * W + cbase + c8;
+            const float4 a = *reinterpret_cast<const float4*>(src), b2 = *reinterpret_cast<const float4*>(src + 4);
+            v[0] += a.x; v[1] += a.y; v[2] += a.z; v[3] += a.w; v[4] += b2.x; v[5] += b2.y; v[6] += b2.z; v[7] += b2.w;
+          }
+          if (epi.bias) {
+            float b[8];
+            unpack8(ldg_cached(epi.bias + col), b);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) v[e] += b[e];
+          }
+          if (epi.rowgroup_bias) {
+            float b[8];
+            unpack8(ldg_act(epi.rowgroup_bias + (size_t)(row / epi.rows_per_group) * epi.rg_ld + col), b);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) v[e] += b[e];
+          }
+          if (epi.act == L2D_ACT_SILU) {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) v[e] = silu_f(v[e]);
+          }
+          if (epi.residual) {
+            float rr[8];
+            unpack8(*reinterpret_cast<const uint4*>(epi.residual + (size_t)row * epi.ldr + col), rr);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) v[e] += rr[e];
+          }
+          *reinterpret_cast<uint4*>(epi.out + (size_t)row * epi.ldo + col) = pack8(v);
+        }
+      }
     }
   }
   tc_fence_before();
@@ -624,13 +793,23 @@ constexpr int64_t kWsElems = 12 << 20;  // fp32 split-K workspace (48 MB)
 
 struct GemmPlan {
   int bn, splits;
+  bool cluster;   // split-K reduced inside a thread-block cluster (DSMEM) instead of slice buffer + finish kernel
 };
+
+static bool cluster_splitk_enabled() {
+  static const bool on = [] {
+    const char* e = getenv("L2D_SPLITK_CLUSTER");
+    return !(e && e[0] == '0');
+  }();
+  return on;
+}
 
 static GemmPlan gemm_plan(int m, int n, int k, bool allow_split, int force_bn) {
   const int cands[4] = {256, 160, 128, 64};
   const int tiles_m = ceil_div(m, BM), num_kb = ceil_div(k, BK);
-  GemmPlan best{64, 1};
+  GemmPlan best{64, 1, false};
   double best_cost = 1e30;
+  const bool cl = cluster_splitk_enabled();
   for (int bn : cands) {
     if (force_bn > 0 && bn != force_bn) continue;
     const int tiles_n = ceil_div(n, bn), tiles = tiles_m * tiles_n;
@@ -640,15 +819,25 @@ static GemmPlan gemm_plan(int m, int n, int k, bool allow_split, int force_bn) {
     for (int sp = 1; sp <= max_s; ++sp) {
       const int kb_per = ceil_div(num_kb, sp);
       if (sp > 1 && kb_per * (sp - 1) >= num_kb) continue;        // an empty last split: pointless
-      if (sp > 1 && (int64_t)sp * tiles_m * BM * tiles_n * bn > kWsElems) continue;
-      const int waves = ceil_div(tiles * sp, kNumSms);
-      double cta = kb_per * kb_cyc + 3000.0;
-      if (sp > 1) cta += 13.0 * bn;                               // fp32 store of the partial tile
-      double cost = waves * cta;
-      if (sp > 1) cost += 6000.0 + (double)sp * m * n * 4.0 / (kNumSms * 40.0);   // finish kernel: launch + slice reads
+      double cost;
+      if (sp > 1 && cl) {
+        // cluster split-K: the splits of a tile are one cluster of 2 / 4 / 8 CTAs, N tile 64 or 128 (partial tiles live in
+        // shared memory next to a shortened operand ring); clusters of 8 fill at most 16 per GPU (GPC granularity)
+        if (!(sp == 2 || sp == 4 || sp == 8) || !(bn == 64 || bn == 128)) continue;
+        const int slots = sp == 8 ? 128 : sp == 4 ? 144 : 148;
+        const int waves = ceil_div(tiles * sp, slots);
+        cost = waves * (kb_per * kb_cyc + 3000.0 + 1500.0 + 6.0 * bn);   // + DSMEM scatter, cluster barrier, slice reduce
+      } else {
+        if (sp > 1 && (int64_t)sp * tiles_m * BM * tiles_n * bn > kWsElems) continue;
+        const int waves = ceil_div(tiles * sp, kNumSms);
+        double cta = kb_per * kb_cyc + 3000.0;
+        if (sp > 1) cta += 13.0 * bn;                               // fp32 store of the partial tile
+        cost = waves * cta;
+        if (sp > 1) cost += 6000.0 + (double)sp * m * n * 4.0 / (kNumSms * 40.0);   // finish kernel: launch + slice reads
+      }
       if (cost < best_cost * 0.97 || (cost < best_cost && sp < best.splits)) {
         best_cost = cost;
-        best = {bn, sp};
+        best = {bn, sp, sp > 1 && cl};
       }
     }
   }
@@ -656,6 +845,8 @@ static GemmPlan gemm_plan(int m, int n, int k, bool allow_split, int force_bn) {
 }
 
 int gemm_pick_tile_n(int m, int n, int k) { return gemm_plan(m, n, k, false, 0).bn; }
+// row-statistics slots a producer GEMM of this shape writes per row: (N tiles) x (2 column halves)
+int gemm_stats_slots(int m, int n, int k) { return 2 * ceil_div(n, gemm_plan(m, n, k, false, 0).bn); }
 
 // exported for the K1 tensor-core kernel (kv_attn_mma.cu): 2-D map, box [box_rows, 64 columns], 128B swizzle
 int get_tmap_2d(const void* ptr, int64_t rows, int64_t cols, int64_t ld, int box_rows, CUtensorMap* out) {
@@ -717,6 +908,37 @@ static int ensure_splitk_workspace() {
   return L2D_OK;
 }
 
+// cluster split-K launch: grid = tiles * splits, cluster = the `splits` CTAs of one tile
+template <int BN, int STAGES>
+static int launch_gemm_cluster(const CUtensorMap& ta, const CUtensorMap& tb, const GemmEpilogue& e, const ConvGeom& cg, int M,
+                               int N, int K, int splits, int tiles_m, cudaStream_t st) {
+  constexpr size_t smem = (size_t)STAGES * GemmSmem<BN>::STAGE_BYTES + 256 + (size_t)128 * BN * sizeof(float) + 1024;
+  static bool configured = false;
+  if (!configured) {
+    L2D_CUDA(cudaFuncSetAttribute(gemm_f16_tcgen05_kernel<BN, STAGES, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)smem));
+    configured = true;
+  }
+  const int tiles_n = ceil_div(N, BN);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(tiles_n * tiles_m * splits);
+  cfg.blockDim = dim3(320);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[2];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = splits;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = (pdl_family(0) && t_weights_constant && pdl_enabled()) ? 2 : 1;
+  L2D_CUDA(cudaLaunchKernelEx(&cfg, gemm_f16_tcgen05_kernel<BN, STAGES, true>, ta, tb, e, cg, M, N, K, tiles_n, tiles_m, splits));
+  L2D_LAUNCH_CHECK();
+  return L2D_OK;
+}
+
 template <int BN, int STAGES>
 static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmEpilogue& e, const ConvGeom& cg, int M,
                        int N, int K, int splits, int tiles_m, cudaStream_t st) {
@@ -739,13 +961,30 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmE
 static int gemm_dispatch(const CUtensorMap& ta, const __half* w, int64_t ldw, const ConvGeom& cg, int tiles_m, int m_pad,
                          __half* out, int64_t ldo, int m, int n, int k, const __half* bias, const __half* rowgroup_bias,
                          int64_t rg_ld, int rows_per_group, const __half* residual, int64_t ldr, int act,
-                         const GemmPlan& plan, cudaStream_t st) {
+                         const GemmPlan& plan, cudaStream_t st, const GemmFusion* fx = nullptr) {
   const int bn = plan.bn;
   CUtensorMap tb;
   int rc = get_tmap(w, n, k, ldw, bn, &tb);
   if (rc != L2D_OK) return rc;
   GemmEpilogue e{out, ldo, bias, rowgroup_bias, rg_ld, rows_per_group > 0 ? rows_per_group : 1, residual, ldr, act,
                  nullptr, 0, 0, g_dbg};
+  if (fx) {
+    if (plan.splits != 1) return fail(L2D_ERR_INVALID, "gemm: LayerNorm fusion needs an unsplit plan");
+    e.stats_out = fx->stats_out;
+    e.stats_slots = 2 * ceil_div(n, bn);
+    e.ln_stats = fx->ln_stats;
+    e.ln_slots = fx->ln_slots;
+    e.ln_s = fx->ln_s;
+    e.ln_b = fx->ln_b;
+    e.ln_inv_c = fx->ln_c > 0 ? 1.0f / (float)fx->ln_c : 0.f;
+    e.ln_eps = fx->ln_eps;
+    if (fx->ln_stats && (!fx->ln_s || !fx->ln_b || fx->ln_slots <= 0 || bias))
+      return fail(L2D_ERR_INVALID, "gemm: LayerNorm consumer needs ln_s / ln_b / ln_slots and no separate bias");
+  }
+  if (plan.splits > 1 && plan.cluster) {
+    if (bn == 64) return launch_gemm_cluster<64, 6>(ta, tb, e, cg, m, n, k, plan.splits, tiles_m, st);
+    return launch_gemm_cluster<128, 4>(ta, tb, e, cg, m, n, k, plan.splits, tiles_m, st);
+  }
   if (plan.splits > 1) {
     rc = ensure_splitk_workspace();
     if (rc != L2D_OK) return rc;
@@ -770,15 +1009,56 @@ static int gemm_dispatch(const CUtensorMap& ta, const __half* w, int64_t ldw, co
 
 int gemm_launch(const __half* a, int64_t lda, const __half* w, int64_t ldw, __half* out, int64_t ldo, int m, int n, int k,
                 const __half* bias, const __half* rowgroup_bias, int64_t rg_ld, int rows_per_group,
-                const __half* residual, int64_t ldr, int act, int force_bn, cudaStream_t st) {
-  const GemmPlan plan = gemm_plan(m, n, k, act != L2D_ACT_GEGLU, force_bn);
+                const __half* residual, int64_t ldr, int act, int force_bn, cudaStream_t st, const GemmFusion* fx) {
+  const bool fused = fx && (fx->stats_out || fx->ln_stats);
+  const GemmPlan plan = gemm_plan(m, n, k, act != L2D_ACT_GEGLU && !fused, force_bn);
   CUtensorMap ta;
   int rc = get_tmap(a, m, k, lda, BM, &ta);
   if (rc != L2D_OK) return rc;
   ConvGeom cg{};
   const int tiles_m = ceil_div(m, BM);
   return gemm_dispatch(ta, w, ldw, cg, tiles_m, tiles_m * BM, out, ldo, m, n, k, bias, rowgroup_bias, rg_ld, rows_per_group,
-                       residual, ldr, act, plan, st);
+                       residual, ldr, act, plan, st, fused ? fx : nullptr);
+}
+
+// w'[n,k] = fp16(gamma[k] * w[n,k]) in place; ln_s[n] = sum_k w'[n,k]; ln_b[n] = bias[n] + sum_k beta[k] * w[n,k]  (one warp per row)
+__global__ void __launch_bounds__(256) ln_fold_kernel(__half* __restrict__ w, const __half* __restrict__ bias,
+                                                      const __half* __restrict__ gamma, const __half* __restrict__ beta,
+                                                      float* __restrict__ ln_s, float* __restrict__ ln_b, int n, int k) {
+  const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (row >= n) return;
+  __half* wr = w + (size_t)row * k;
+  float s = 0.f, b = 0.f;
+  for (int c = lane * 8; c < k; c += 256) {
+    float wf[8], g[8], be[8], o[8];
+    unpack8(*reinterpret_cast<const uint4*>(wr + c), wf);
+    unpack8(*reinterpret_cast<const uint4*>(gamma + c), g);
+    unpack8(*reinterpret_cast<const uint4*>(beta + c), be);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      o[e] = wf[e] * g[e];
+      b = fmaf(be[e], wf[e], b);
+    }
+    const uint4 packed = pack8(o);
+    *reinterpret_cast<uint4*>(wr + c) = packed;
+    unpack8(packed, o);   // the sum runs over the weights the tensor cores will actually multiply by
+#pragma unroll
+    for (int e = 0; e < 8; ++e) s += o[e];
+  }
+  s = warp_sum(s);
+  b = warp_sum(b);
+  if (lane == 0) {
+    ln_s[row] = s;
+    ln_b[row] = b + (bias ? __half2float(bias[row]) : 0.f);
+  }
+}
+
+int ln_fold_weights(__half* w, const __half* bias, const __half* gamma, const __half* beta, float* ln_s, float* ln_b, int n, int k,
+                    cudaStream_t st) {
+  if (k % 8 != 0) return fail(L2D_ERR_INVALID, "ln_fold_weights: K % 8 != 0");
+  ln_fold_kernel<<<ceil_div(n, 8), 256, 0, st>>>(w, bias, gamma, beta, ln_s, ln_b, n, k);
+  L2D_LAUNCH_CHECK();
+  return L2D_OK;
 }
 
 // out[N*H*W, cout] = epilogue( conv3x3(x[N,H,W,cin], w[cout, 9*cin]) ), pad 1, stride 1, x channels-last contiguous

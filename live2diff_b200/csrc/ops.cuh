@@ -58,9 +58,30 @@ struct GemmConstWeights {
   GemmConstWeights() { gemm_weights_constant(true); }
   ~GemmConstWeights() { gemm_weights_constant(false); }
 };
+// LayerNorm folded into the GEMMs around it (attention.py:243-268, motion_module.py:401-435: every LayerNorm's input is
+// the output of a C x C projection and its output feeds a Linear):
+//   producer  (stats_out != null): the epilogue also writes, per output row, (sum, sum of squares) of the fp16 values it
+//             stores -- one float2 per (N tile, column half) = `gemm_stats_slots(m, n, k)` slots per row, summed by the
+//             consumer in slot order (deterministic, no atomics)
+//   consumer  (ln_stats != null): A holds the UN-normalised rows; W is gamma-scaled (w'[n,k] = gamma[k] w[n,k]) and
+//             y[r,n] = rstd_r * (acc[r,n] - mean_r * ln_s[n]) + ln_b[n],  ln_s[n] = sum_k w'[n,k],  ln_b[n] = b[n] + sum_k beta[k] w[n,k]
+//             which equals Linear(LayerNorm(x)) without materialising the normalised tensor (-1 launch, -2 passes over [M,C])
+struct GemmFusion {
+  float2* stats_out = nullptr;
+  const float2* ln_stats = nullptr;
+  int ln_slots = 0;
+  const float* ln_s = nullptr;
+  const float* ln_b = nullptr;
+  int ln_c = 0;
+  float ln_eps = 1e-5f;
+};
+int gemm_stats_slots(int m, int n, int k);
 int gemm_launch(const __half* a, int64_t lda, const __half* w, int64_t ldw, __half* out, int64_t ldo, int m, int n, int k,
                 const __half* bias, const __half* rowgroup_bias, int64_t rg_ld, int rows_per_group,
-                const __half* residual, int64_t ldr, int act, int force_bn, cudaStream_t st);
+                const __half* residual, int64_t ldr, int act, int force_bn, cudaStream_t st, const GemmFusion* fx = nullptr);
+// in place: w[n,k] *= gamma[k] (fp16 rounding), ln_s[n] = sum_k w'[n,k], ln_b[n] = bias[n] + sum_k beta[k] w[n,k]
+int ln_fold_weights(__half* w, const __half* bias, const __half* gamma, const __half* beta, float* ln_s, float* ln_b, int n, int k,
+                    cudaStream_t st);
 
 bool conv3x3_implicit_supported(int n_img, int h, int w, int cin);
 int conv3x3_launch(const __half* x, int n_img, int h, int w, int cin, const __half* weight, __half* out, int64_t ldo, int cout,
