@@ -467,6 +467,38 @@ def run_native(args):
     bytes_in = 2 * host_x[0].numel() * 2
     bytes_out = host_out.numel() * 2
 
+    # ---------------- image in -> image out (a1: TAESD encode x2 + frame + TAESD decode + uint8 pre/post), N = 1 ----------------
+    e2e_image = None
+    if world == 1 and stream is not pipe and not args.no_image:
+        from live2diff_b200.image_pipeline import B200ImageStream
+        from live2diff_b200.taesd import B200TinyVAE, random_taesd_state_dict
+
+        vae = B200TinyVAE(random_taesd_state_dict(0), LAT_H * 8, LAT_W * 8, max_batch=1, device=dev)
+        img_stream = B200ImageStream(unet, vae, T_INDEX, seed=2)
+        img_stream.prepare(prompt, kv)
+        frames_u8 = [torch.randint(0, 256, (LAT_H * 8, LAT_W * 8, 3), generator=gen, dtype=torch.uint8).pin_memory()
+                     for _ in range(4)]
+        depth_maps = [torch.rand(1, LAT_H * 8, LAT_W * 8, generator=gen).half().to(dev) for _ in range(4)]
+        out_u8 = torch.empty(LAT_H * 8, LAT_W * 8, 3, dtype=torch.uint8).pin_memory()
+        for i in range(3 * WINDOW + 3):                       # fill this stream's ring, warm the VAE kernels
+            img_stream.frame_u8(frames_u8[i % 4], depth_maps[i % 4], out=out_u8)
+        torch.cuda.synchronize(dev)
+        k_img = max(10, min(args.steps, 40))
+        l_img0 = lib.l2d_launch_count()
+        ev0.record()
+        for i in range(k_img):
+            img_stream.frame_u8(frames_u8[i % 4], depth_maps[i % 4], out=out_u8)
+            torch.cuda.current_stream().synchronize()
+        ev1.record()
+        torch.cuda.synchronize(dev)
+        img_ms = ev0.elapsed_time(ev1) / k_img
+        e2e_image = {"value": 1e3 / img_ms, "unit": UNIT, "ms_per_step": img_ms, "h2d_bytes_per_step": frames_u8[0].numel(),
+                     "d2h_bytes_per_step": out_u8.numel(), "launches_per_step": int((lib.l2d_launch_count() - l_img0) / k_img),
+                     "what": "uint8 frame (pinned host) -> preprocess -> TAESD encode (frame) + TAESD encode (depth map, supplied: "
+                             "MiDaS is not built) -> add_noise -> stream frame -> TAESD decode -> uint8 frame (pinned host), "
+                             "sync per frame; seeded random TAESD weights with the real shapes"}
+        del img_stream, vae
+
     line = None
     if rank == 0:
         # ---------------- per-family CUDA-event profile of real steps (eager), K1 roofline ----------------
@@ -538,6 +570,8 @@ def run_native(args):
                             if stream is not pipe else "host-scheduled B200StreamPipeline, UNet step = 1 CUDA graph",
                 "roofline": roofline, "roofline_tensor": tensor, "kernel_time_breakdown_ms": breakdown,
                 "engine_device_gib": round(unet.device_bytes / 2 ** 30, 2), "value_per_stream": value / world}
+        if e2e_image is not None:
+            line["e2e_image"] = e2e_image
     if world > 1:
         dist.barrier()
     if rank == 0:
@@ -571,6 +605,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the (~1 min) CPU oracle leg")
     ap.add_argument("--no-torch-baseline", action="store_true", help="skip the eager torch fp16 GPU leg")
     ap.add_argument("--no-ablation", action="store_true", help="skip the in-graph marginal-cost passes")
+    ap.add_argument("--no-image", action="store_true", help="skip the image-in/image-out (TAESD) leg")
     ap.add_argument("--pipeline", default="device", choices=["device", "host"],
                     help="device: B200DeviceStream (state in HBM, whole-frame graph); host: B200StreamPipeline")
     args = ap.parse_args()

@@ -106,11 +106,14 @@ int l2d_nhwc_to_nchw(const void* x, const void* residual_nchw, void* y, int n_im
  * A rows have `lda` elements (K <= lda), W is [N,K] contiguous (nn.Linear layout; a conv3x3 weight
  * repacked to [Cout, 9*Cin] (tap,cin) order), out rows have `ldo` elements.
  * Epilogue, in order:  + bias[n]  + rowgroup_bias[m / rows_per_group, n]  -> act  -> + residual[m,n].
- * act: 0 none, 1 SiLU, 2 GEGLU (W rows must be tile-interleaved by l2d_geglu_interleave; out has N/2 cols).
+ * act: 0 none, 1 SiLU, 2 GEGLU (W rows must be tile-interleaved by l2d_geglu_interleave; out has N/2 cols), 3 ReLU,
+ *      4 ReLU applied after the residual add.
  * Any of bias / rowgroup_bias / residual may be NULL.  K % 8 == 0, N % 8 == 0. */
 #define L2D_ACT_NONE 0
 #define L2D_ACT_SILU 1
 #define L2D_ACT_GEGLU 2
+#define L2D_ACT_RELU 3        /* ReLU in the activation slot (before the residual) */
+#define L2D_ACT_RELU_POST 4   /* no activation before the residual, ReLU after it: ReLU(conv(x) + skip) (AutoencoderTinyBlock.fuse) */
 int l2d_gemm(const void* a, int64_t lda, const void* w, void* out, int64_t ldo, int m, int n, int k,
              const void* bias, const void* rowgroup_bias, int rows_per_group, const void* residual,
              int64_t ldr, int act, void* stream);
@@ -267,6 +270,26 @@ int l2d_ring_schedule_host(int32_t* valid, int64_t* pe_idx, int64_t* update_idx,
                            int init, int advance_frames);
 int l2d_stream_randn_host(uint64_t seed, uint64_t frame, uint32_t row, float* out, int count);
 void l2d_philox4x32_10_host(const uint32_t* counter4, const uint32_t* key2, uint32_t* out4);
+
+/* ---------------------------------------------------------------------------------------------
+ * f3: the tiny VAE around the step -- `stream.vae` = diffusers AutoencoderTiny (live2diff/utils/wrapper.py:468-470) as
+ * called by encode_image / encode_depth / decode_image (pipeline_stream_animation_depth.py:517-542, 565-571), and the
+ * uint8 <-> [-1,1] conversions of __call__ (:630; live2diff/image_utils.py:9-30).  Weights: AutoencoderTiny.state_dict()
+ * (keys encoder.layers.N..., decoder.layers.N...; fp16, device).  scaling_factor is 1.0 and applied by the caller.
+ *   encode: image [n,3,H,W] fp16 in [-1,1] -> latents [n,4,H/8,W/8]           (vae.encode(x).latents)
+ *   decode: latents [n,4,H/8,W/8] -> image [n,3,H,W] fp16; clip != 0 also applies .clip(-1,1)   (vae.decode(z)[0])
+ * H, W multiples of 8 whose power-of-two divisors tile 128 pixels at every scale (512x512, 768x512, ...).
+ * ------------------------------------------------------------------------------------------- */
+typedef struct l2d_taesd l2d_taesd;
+int l2d_taesd_create(l2d_taesd** out, const l2d_tensor* weights, int n_weights, int max_batch, int height, int width);
+int l2d_taesd_encode(l2d_taesd* t, const void* image_nchw, void* latents, int n, void* stream);
+int l2d_taesd_decode(l2d_taesd* t, const void* latents, void* image_nchw, int n, int clip, void* stream);
+int64_t l2d_taesd_device_bytes(const l2d_taesd* t);
+void l2d_taesd_destroy(l2d_taesd* t);
+/* uint8 [n,H,W,3] -> fp16 [n,3,H,W] = x/255*2-1 (VaeImageProcessor.preprocess), and back: (x/2+0.5).clamp(0,1)*255 rounded
+ * half-to-even (image_utils.denormalize + numpy_to_pil). */
+int l2d_image_u8_to_f16(const void* u8_nhwc, void* f16_nchw, int n, int h, int w, void* stream);
+int l2d_image_f16_to_u8(const void* f16_nchw, void* u8_nhwc, int n, int h, int w, void* stream);
 
 #ifdef __cplusplus
 }

@@ -24,6 +24,8 @@ void l2d_unet_set_ablation(l2d_unet* u, int family_mask);
 /* Drop the captured whole-frame graph of a device-resident stream (it still holds the launches an ablation mask
  * removed / restored); the next l2d_stream_frame captures again. */
 void l2d_stream_invalidate_graph(l2d_stream* s);
+/* Resident CTAs per SM of the tcgen05 spatial-attention kernel (head_dim 40 -> 2 expected, 80 -> 1). */
+int l2d_debug_flash_ctas_per_sm(int hd);
 
 #ifdef __cplusplus
 }

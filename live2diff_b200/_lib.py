@@ -68,6 +68,13 @@ SIGNATURES = {
     "l2d_unet_device_bytes": (i64, [vp]),
     "l2d_unet_launches_per_step": (i64, [vp]),
     "l2d_unet_destroy": (None, [vp]),
+    "l2d_taesd_create": (i32, [C.POINTER(vp), C.POINTER(L2DTensor), i32, i32, i32, i32]),
+    "l2d_taesd_encode": (i32, [vp, vp, vp, i32, vp]),
+    "l2d_taesd_decode": (i32, [vp, vp, vp, i32, i32, vp]),
+    "l2d_taesd_device_bytes": (i64, [vp]),
+    "l2d_taesd_destroy": (None, [vp]),
+    "l2d_image_u8_to_f16": (i32, [vp, vp, i32, i32, i32, vp]),
+    "l2d_image_f16_to_u8": (i32, [vp, vp, i32, i32, i32, vp]),
     "l2d_stream_create": (i32, [C.POINTER(vp), vp, C.POINTER(i64), C.POINTER(f32), i32, u64, i32, i32]),
     "l2d_stream_destroy": (None, [vp]),
     "l2d_stream_reset": (i32, [vp, vp]),
@@ -90,6 +97,7 @@ DEBUG_SIGNATURES = {
     "l2d_gemm_set_debug": (None, [vp]),
     "l2d_unet_set_ablation": (None, [vp, i32]),
     "l2d_stream_invalidate_graph": (None, [vp]),
+    "l2d_debug_flash_ctas_per_sm": (i32, [i32]),
 }
 
 ABI_VERSION = 3

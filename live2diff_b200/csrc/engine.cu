@@ -335,8 +335,17 @@ struct Core {
     return L2D_OK;
   }
 
+  // L2D_LN_FOLD=0 keeps the separate LayerNorm kernels (A/B switch; default: folded)
+  static bool ln_fold_enabled() {
+    static const bool on = [] {
+      const char* e = getenv("L2D_LN_FOLD");
+      return !(e && e[0] == '0');
+    }();
+    return on;
+  }
   // LayerNorm(norm) -> Linear(l) becomes one GEMM: scale the weight columns by gamma once, keep the two fp32 vectors
   int fold_ln(Lin* l, const Norm& norm) {
+    if (!ln_fold_enabled()) return L2D_OK;
     RC(pool.alloc(reinterpret_cast<void**>(&l->ln_s), (size_t)l->n * sizeof(float)));
     RC(pool.alloc(reinterpret_cast<void**>(&l->ln_b), (size_t)l->n * sizeof(float)));
     return ln_fold_weights(l->w, l->b, norm.g, norm.b, l->ln_s, l->ln_b, l->n, l->k, st);
@@ -351,13 +360,18 @@ struct Core {
   // C x C projection whose [m, C] output is the next LayerNorm's input: also emits the row statistics
   int gemm_emit(const __half* a, int64_t lda, const Lin& l, __half* out, int64_t ldo, int m, const __half* residual = nullptr,
                 int64_t ldr = 0) {
+    if (!ln_fold_enabled()) return gemm(a, lda, l, out, ldo, m, residual, ldr);
     GemmFusion fx;
     fx.stats_out = s.ln_stats;
     return gemm_raw(a, lda, l.w, l.k, out, ldo, m, l.n, l.k, l.b, nullptr, 0, 1, residual, ldr, L2D_ACT_NONE, 0, &fx);
   }
   // Linear(LayerNorm(a)) with the LayerNorm folded into l (fold_ln); a = the un-normalised [m, C] rows
-  int gemm_ln(const __half* a, int64_t lda, const Lin& l, __half* out, int64_t ldo, int m, int act = L2D_ACT_NONE,
-              int force_bn = 0) {
+  int gemm_ln(const __half* a, int64_t lda, const Lin& l, const Norm& norm, __half* out, int64_t ldo, int m,
+              int act = L2D_ACT_NONE, int force_bn = 0) {
+    if (!l.ln_s) {   // not folded: separate LayerNorm kernel, then the plain projection
+      RC(layernorm(a, norm, s.ln, m, l.k));
+      return gemm(s.ln, l.k, l, out, ldo, m, nullptr, 0, act, force_bn);
+    }
     GemmFusion fx;
     fx.ln_stats = s.ln_stats;
     fx.ln_slots = gemm_stats_slots(m, l.k, l.k);
@@ -418,7 +432,7 @@ struct Core {
     RC(gemm_emit(s.t0, c, t.proj_in, s.t, c, m));
     void* caches[2] = {cache0, cache1};
     for (int i = 0; i < 2; ++i) {
-      RC(gemm_ln(s.t, c, t.qkv[i], s.qkv, 3 * c, m));   // norms[i] folded in (motion_module.py:420-428)
+      RC(gemm_ln(s.t, c, t.qkv[i], t.ln[i], s.qkv, 3 * c, m));   // norms[i] folded in (motion_module.py:420-428)
       if (warm_frames > 0) {   // VersatileAttention over the frames + sink-slot fill (motion_module.py:469-530)
         WarmupAttnParams wp{};
         wp.q = s.qkv; wp.k = s.qkv + c; wp.v = s.qkv + 2 * c; wp.ld = 3 * c;
@@ -443,7 +457,7 @@ struct Core {
       RC(kv(p));
       RC(gemm_emit(s.att, c, t.out[i], s.t, c, m, s.t, c));
     }
-    RC(gemm_ln(s.t, c, t.ff1, s.ff, 4 * c, m, L2D_ACT_GEGLU, t.ff1_tile));   // ff_norm folded in
+    RC(gemm_ln(s.t, c, t.ff1, t.ff_norm, s.ff, 4 * c, m, L2D_ACT_GEGLU, t.ff1_tile));   // ff_norm folded in
     RC(gemm(s.ff, 4 * c, t.ff2, s.t, c, m, s.t, c));
     RC(gemm(s.t, c, t.proj_out, out, c, m, x, c));
     return L2D_OK;
@@ -650,16 +664,16 @@ int spatial_forward(l2d_unet* u, const SpatialP& sp, const __half* x, __half* ou
   RC(k.gn(x, c, nullptr, 0, sp.norm, s.t0, n, lv.h, lv.w, 1e-6f, 0, 0));
   RC(k.gemm_emit(s.t0, c, sp.proj_in, s.t, c, m));
   // self-attention (norm1 folded into the fused q/k/v projection)
-  RC(k.gemm_ln(s.t, c, sp.qkv, s.qkv, 3 * c, m));
+  RC(k.gemm_ln(s.t, c, sp.qkv, sp.ln1, s.qkv, 3 * c, m));
   RC(k.attn(s.qkv, 3 * c, s.qkv + c, 3 * c, s.qkv + 2 * c, 3 * c, s.att, c, n, hw, hw, hd));
   RC(k.gemm_emit(s.att, c, sp.out1, s.t, c, m, s.t, c));
   // cross-attention against the (pre-projected) text context (norm2 folded into to_q)
-  RC(k.gemm_ln(s.t, c, sp.q2, s.q2, c, m));
+  RC(k.gemm_ln(s.t, c, sp.q2, sp.ln2, s.q2, c, m));
   const __half* kv = u->kv2 + sp.kv2_off;
   RC(k.attn(s.q2, c, kv, u->kv2_all.n, kv + c, u->kv2_all.n, s.att, c, n, hw, ctx, hd));
   RC(k.gemm_emit(s.att, c, sp.out2, s.t, c, m, s.t, c));
   // feed-forward (norm3 folded into the GEGLU projection)
-  RC(k.gemm_ln(s.t, c, sp.ff1, s.ff, 4 * c, m, L2D_ACT_GEGLU, sp.ff1_tile));
+  RC(k.gemm_ln(s.t, c, sp.ff1, sp.ln3, s.ff, 4 * c, m, L2D_ACT_GEGLU, sp.ff1_tile));
   RC(k.gemm(s.ff, 4 * c, sp.ff2, s.t, c, m, s.t, c));
   RC(k.gemm(s.t, c, sp.proj_out, out, c, m, x, c));
   return L2D_OK;

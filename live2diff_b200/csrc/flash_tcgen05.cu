@@ -12,10 +12,8 @@
 //                                  of two S accumulators in TMEM, so that S_{j+1} is computed while S_j is in the softmax
 //                T_j = P_j . V_j   (M = 128, N = hd rounded to 16, K = 128 keys; A = P from shared memory, K-major;
 //                                  B = the V tile exactly as TMA delivered it = MN-major, 128B swizzle)
-//   warps 2-9  softmax + correction + epilogue: two threads per query row (tcgen05.ld 32x32b: TMEM lane = row; warps w and
-//              w + 4 share a lane quarter and split the 128 keys / the output channels), so the row max costs one 64-thread
-//              named barrier per tile and no shuffles; the 64 scores of a thread stay in registers between the max and the
-//              exp pass, so the S accumulator is released right after one TMEM read; P is rounded to fp16 (like the fused SDPA kernels the reference dispatches to)
+//   warps 2-5  softmax + correction + epilogue: thread = one query row (tcgen05.ld 32x32b: TMEM lane = row), so row max /
+//              row sum need no shuffles; P is rounded to fp16 (like the fused SDPA kernels the reference dispatches to)
 //              and written into shared memory in the UMMA K-major swizzled layout; the running output lives in registers
 //              (o = o * corr + T_j, flash-attention's online softmax in fp32), the 1/l normalisation is applied once.
 // hd = 40: the K extent of Q.K^T is padded to 48 by zeroing columns 40..47 of the Q tile in shared memory (the K tile's
@@ -135,7 +133,7 @@ struct FtParams {
   float scale_log2;   // log2(e) / sqrt(hd)
 };
 
-constexpr int FT_THREADS = 320;   // TMA warp, MMA warp, 8 softmax warps (two threads per query row)
+constexpr int FT_THREADS = 192;   // TMA warp, MMA warp, 4 softmax warps (one thread per query row)
 constexpr int FT_TILE = 128 * 128;   // bytes of one [128 rows x 64 fp16] swizzled block
 
 template <int HD>
@@ -144,24 +142,32 @@ struct FtCfg {
   static constexpr int NBLK = (HD + 63) / 64;       // 64-column blocks of a Q / K / V tile
   static constexpr int ON = KSTEPS * 16;            // columns of T = P.V that are read back (hd rounded up to 16)
   static constexpr int ON_MMA = NBLK * 64;          // MMA N of P.V: whole 64-channel swizzle atoms of the V tile
-  static constexpr int STAGES = HD <= 64 ? 3 : 2;   // K / V ring depth
+  static constexpr int STAGES = 2;                  // K ring depth
+  static constexpr int VSTAGES = HD <= 64 ? 1 : 2;  // V ring depth (V_j is needed a whole softmax later than K_j)
+  // hd <= 64: 96 KB of shared memory and 256 TMEM columns per CTA -> TWO CTAs per SM.  Their softmax phases (MUFU-bound,
+  // ~1000 cycles per tile) and their synchronisation chains (S ready -> softmax -> P ready -> P.V -> T ready) run out of
+  // phase and hide each other; one S accumulator per CTA is then enough.  hd = 80 (192 KB): one CTA per SM, two S buffers.
+  static constexpr int SBUF = HD <= 64 ? 1 : 2;
+  static constexpr int TMEM_COLS = SBUF == 1 ? 256 : 512;
+  static constexpr int TM_O = SBUF * 128;
+  static constexpr int CTAS_PER_SM = HD <= 64 ? 2 : 1;
   static constexpr int TILE_BYTES = NBLK * FT_TILE;
-  static constexpr int SMEM = TILE_BYTES * (1 + 2 * STAGES) + 2 * FT_TILE /* P */ + 256 /* barriers */ +
-                              6 * 128 * 4 /* row max / row sum exchange */ + 1024 /* align */;
+  static constexpr int SLACK = 1024;
+  static constexpr int SMEM = TILE_BYTES * (1 + STAGES + VSTAGES) + 2 * FT_TILE /* P */ + 256 /* barriers */ + SLACK;
 };
 
 template <int HD>
-__global__ void __launch_bounds__(FT_THREADS, 1)
+__global__ void __launch_bounds__(FT_THREADS, FtCfg<HD>::CTAS_PER_SM)
 flash_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
                      const __grid_constant__ CUtensorMap tmap_v, const FtParams p) {
   using Cfg = FtCfg<HD>;
-  constexpr int ST = Cfg::STAGES, NBLK = Cfg::NBLK, KSTEPS = Cfg::KSTEPS, ON = Cfg::ON;
+  constexpr int ST = Cfg::STAGES, VST = Cfg::VSTAGES, NBLK = Cfg::NBLK, KSTEPS = Cfg::KSTEPS, ON = Cfg::ON, SBUF = Cfg::SBUF;
   extern __shared__ __align__(1024) uint8_t ft_smem_raw[];
   uint8_t* smem = ft_smem_raw + ((1024u - (ft_smem_u32(ft_smem_raw) & 1023u)) & 1023u);
   uint8_t* sQ = smem;
   uint8_t* sK = sQ + Cfg::TILE_BYTES;
   uint8_t* sV = sK + ST * Cfg::TILE_BYTES;
-  uint8_t* sP = sV + ST * Cfg::TILE_BYTES;
+  uint8_t* sP = sV + VST * Cfg::TILE_BYTES;
   uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 2 * FT_TILE);
   const uint32_t bar0 = ft_smem_u32(bars);
   // barrier map
@@ -173,7 +179,6 @@ flash_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
   auto s_full = [&](int b) { return bar0 + 40 + 8u * (4 * ST + b); };
   auto s_empty = [&](int b) { return bar0 + 40 + 8u * (4 * ST + 2 + b); };
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 5 + 4 * ST + 4);
-  float* s_xch = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 256);   // [2 S buffers][2 halves][128] max, [2][128] sums
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int b = blockIdx.z, h = blockIdx.y, m0 = blockIdx.x * 128;
@@ -186,10 +191,10 @@ flash_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_k) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_v) : "memory");
     ft_mbar_init(q_full, 1);
-    ft_mbar_init(q_ready, 8);
-    ft_mbar_init(p_full, 8);
+    ft_mbar_init(q_ready, 4);
+    ft_mbar_init(p_full, 4);
     ft_mbar_init(o_full, 1);
-    ft_mbar_init(o_empty, 8);
+    ft_mbar_init(o_empty, 4);
     for (int s = 0; s < ST; ++s) {
       ft_mbar_init(k_full(s), 1);
       ft_mbar_init(k_empty(s), 1);
@@ -198,19 +203,19 @@ flash_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
     }
     for (int a = 0; a < 2; ++a) {
       ft_mbar_init(s_full(a), 1);
-      ft_mbar_init(s_empty(a), 8);
+      ft_mbar_init(s_empty(a), 4);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(ft_smem_u32(tmem_ptr_smem)), "r"(512u) : "memory");
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(ft_smem_u32(tmem_ptr_smem)), "r"((uint32_t)Cfg::TMEM_COLS) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   ft_tc_fence_before();
   __syncthreads();
   ft_tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
-  constexpr uint32_t TM_S = 0, TM_O = 256;   // TMEM columns: S[0] 0..127, S[1] 128..255, T 256..256+ON_MMA
+  constexpr uint32_t TM_S = 0, TM_O = Cfg::TM_O;   // TMEM columns: S buffers of 128 columns each, then T (ON_MMA columns)
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -218,18 +223,22 @@ flash_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
       pdl_wait();   // q / k / v were written by the projection GEMMs right before this kernel
       ft_mbar_expect_tx(q_full, Cfg::TILE_BYTES);
       for (int cb = 0; cb < NBLK; ++cb) ft_tma_2d(ft_smem_u32(sQ + cb * FT_TILE), &tmap_q, q_full, col0 + cb * 64, b * p.sq + m0);
-      for (int j = 0; j < nk; ++j) {
+      auto load_k = [&](int j) {
         const int s = j % ST;
-        const uint32_t ph = (uint32_t)(j / ST) & 1u;
-        const int row = b * p.skv + j * 128;
-        ft_mbar_wait(k_empty(s), ph ^ 1u);
+        ft_mbar_wait(k_empty(s), ((uint32_t)(j / ST) & 1u) ^ 1u);
         ft_mbar_expect_tx(k_full(s), Cfg::TILE_BYTES);
         for (int cb = 0; cb < NBLK; ++cb)
-          ft_tma_2d(ft_smem_u32(sK + s * Cfg::TILE_BYTES + cb * FT_TILE), &tmap_k, k_full(s), col0 + cb * 64, row);
-        ft_mbar_wait(v_empty(s), ph ^ 1u);
-        ft_mbar_expect_tx(v_full(s), Cfg::TILE_BYTES);
+          ft_tma_2d(ft_smem_u32(sK + s * Cfg::TILE_BYTES + cb * FT_TILE), &tmap_k, k_full(s), col0 + cb * 64, b * p.skv + j * 128);
+      };
+      // K runs one tile ahead of V: S_{j+1} is issued while the softmax of tile j is still busy, V_j only feeds P_j . V_j
+      load_k(0);
+      for (int j = 0; j < nk; ++j) {
+        if (j + 1 < nk) load_k(j + 1);
+        const int sv = j % VST;
+        ft_mbar_wait(v_empty(sv), ((uint32_t)(j / VST) & 1u) ^ 1u);
+        ft_mbar_expect_tx(v_full(sv), Cfg::TILE_BYTES);
         for (int cb = 0; cb < NBLK; ++cb)
-          ft_tma_2d(ft_smem_u32(sV + s * Cfg::TILE_BYTES + cb * FT_TILE), &tmap_v, v_full(s), col0 + cb * 64, row);
+          ft_tma_2d(ft_smem_u32(sV + sv * Cfg::TILE_BYTES + cb * FT_TILE), &tmap_v, v_full(sv), col0 + cb * 64, b * p.skv + j * 128);
       }
     }
   } else if (warp == 1) {
@@ -238,9 +247,9 @@ flash_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
       constexpr uint32_t idesc_s = ft_idesc(128, 0);
       constexpr uint32_t idesc_o = ft_idesc(Cfg::ON_MMA, 1);
       auto issue_s = [&](int j) {
-        const int s = j % ST, a = j & 1;
+        const int s = j % ST, a = j % SBUF;
         ft_mbar_wait(k_full(s), (uint32_t)(j / ST) & 1u);
-        ft_mbar_wait(s_empty(a), ((uint32_t)(j >> 1) & 1u) ^ 1u);   // the softmax has drained this S accumulator (tile j-2)
+        ft_mbar_wait(s_empty(a), ((uint32_t)(j / SBUF) & 1u) ^ 1u);   // the softmax has drained this S accumulator (tile j-SBUF)
         ft_tc_fence_after();
         const uint32_t qa = ft_smem_u32(sQ), ka = ft_smem_u32(sK + s * Cfg::TILE_BYTES);
 #pragma unroll
@@ -252,8 +261,8 @@ flash_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
         ft_commit(s_full(a));
       };
       auto issue_pv = [&](int j) {
-        const int s = j % ST;
-        ft_mbar_wait(v_full(s), (uint32_t)(j / ST) & 1u);
+        const int s = j % VST;
+        ft_mbar_wait(v_full(s), (uint32_t)(j / VST) & 1u);
         ft_mbar_wait(p_full, (uint32_t)j & 1u);
         if (j > 0) ft_mbar_wait(o_empty, (uint32_t)(j - 1) & 1u);   // T_{j-1} has been folded into the register accumulator
         ft_tc_fence_after();
@@ -270,21 +279,19 @@ flash_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
       ft_mbar_wait(q_ready, 0);
       issue_s(0);
       for (int j = 0; j < nk; ++j) {
+        // (with one S buffer this waits until the softmax of tile j has read S_j for the last time -- about two thirds into
+        //  its tile -- so S_{j+1} is still ready before the softmax threads come back for it)
         if (j + 1 < nk) issue_s(j + 1);
         issue_pv(j);
       }
     }
   } else {
-    // ===================== softmax / correction / epilogue (warps 2..9) =====================
-    // Two threads per query row: warps w and w + 4 may touch the same TMEM lane quarter; `half` 0 owns keys 0..63 of the
-    // tile (P block 0) and the first OC output channels, `half` 1 keys 64..127 and the rest.  The pair meets once per
-    // tile (named barrier of 64 threads) to exchange the partial row max; row sums stay partial until the end.
+    // ===================== softmax / correction / epilogue (warps 2..5) =====================
     const int q = warp & 3;                    // TMEM lane quarter this warp may touch
-    const int half = (warp - 2) >> 2;
     const int r = q * 32 + lane;               // query row inside the tile
     const uint32_t t_lane = tmem_base + ((uint32_t)(q * 32) << 16);
     ft_mbar_wait(q_full, 0);
-    if (HD % 16 != 0 && half == 0) {   // zero columns HD .. KSTEPS*16-1 of this row (hd = 40: chunk 5 of block 0)
+    if (HD % 16 != 0) {   // zero columns HD .. KSTEPS*16-1 of this row (hd = 40: chunk 5 of block 0)
       constexpr int chunk = HD / 8;
       *reinterpret_cast<uint4*>(sQ + (chunk >> 3) * FT_TILE + r * 128 + (((chunk & 7) ^ (r & 7)) << 4)) = make_uint4(0, 0, 0, 0);
     }
@@ -292,57 +299,51 @@ flash_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
     __syncwarp();
     if (lane == 0) ft_mbar_arrive(q_ready);
 
-    constexpr int OC = ON / 2;                 // output channels per thread (24 / 40), in 8-column TMEM loads
     float m_run = -INFINITY, l_run = 0.f, corr_pending = 0.f;
-    float o_acc[OC];
+    float o_acc[ON];
 #pragma unroll
-    for (int i = 0; i < OC; ++i) o_acc[i] = 0.f;
+    for (int i = 0; i < ON; ++i) o_acc[i] = 0.f;
     const float c = p.scale_log2;
-    const uint32_t o_addr = t_lane + TM_O + (uint32_t)(half * OC);
 
     auto fold_t = [&](float corr) {   // o = o * corr + T   (T = P.V of the previous tile, in TMEM)
-      uint32_t t[OC];
+      uint32_t t[ON];
 #pragma unroll
-      for (int cc = 0; cc < OC / 8; ++cc) ft_tmem_ld8(o_addr + cc * 8, &t[cc * 8]);
+      for (int cc = 0; cc < ON / 16; ++cc) ft_tmem_ld16(t_lane + TM_O + cc * 16, *reinterpret_cast<uint32_t(*)[16]>(&t[cc * 16]));
       ft_tmem_ld_wait();
 #pragma unroll
-      for (int e = 0; e < OC; ++e) o_acc[e] = fmaf(o_acc[e], corr, __uint_as_float(t[e]));
+      for (int e = 0; e < ON; ++e) o_acc[e] = fmaf(o_acc[e], corr, __uint_as_float(t[e]));
     };
 
     for (int j = 0; j < nk; ++j) {
-      const int a = j & 1;
-      const int nvalid = min(128, p.skv - j * 128) - half * 64;   // valid keys among this thread's 64
-      ft_mbar_wait(s_full(a), (uint32_t)(j >> 1) & 1u);
+      const int a = j % SBUF;
+      const int nvalid = min(128, p.skv - j * 128);
+      ft_mbar_wait(s_full(a), (uint32_t)(j / SBUF) & 1u);
       ft_tc_fence_after();
-      const uint32_t s_addr = t_lane + TM_S + (uint32_t)(a * 128 + half * 64);
-      // ---- this thread's 64 scores -> registers; S[a] can then be overwritten by the tile after next ----
-      uint32_t v0[32], v1[32];
-      ft_tmem_ld32(s_addr, v0);
-      ft_tmem_ld32(s_addr + 32, v1);
-      ft_tmem_ld_wait();
-      ft_tc_fence_before();
-      __syncwarp();
-      if (lane == 0) ft_mbar_arrive(s_empty(a));
+      const uint32_t s_addr = t_lane + TM_S + (uint32_t)a * 128;
+      // ---- pass 1: row max of the raw scores (two 32-column loads in flight) ----
       float mx = -INFINITY;
-      if (nvalid < 64) {
+#pragma unroll 1
+      for (int cc = 0; cc < 2; ++cc) {
+        uint32_t v0[32], v1[32];
+        ft_tmem_ld32(s_addr + cc * 64, v0);
+        ft_tmem_ld32(s_addr + cc * 64 + 32, v1);
+        ft_tmem_ld_wait();
+        if (nvalid < 128) {
 #pragma unroll
-        for (int e = 0; e < 32; ++e) {
-          if (e < nvalid) mx = fmaxf(mx, __uint_as_float(v0[e]));
-          if (32 + e < nvalid) mx = fmaxf(mx, __uint_as_float(v1[e]));
+          for (int e = 0; e < 32; ++e) {
+            if (cc * 64 + e < nvalid) mx = fmaxf(mx, __uint_as_float(v0[e]));
+            if (cc * 64 + 32 + e < nvalid) mx = fmaxf(mx, __uint_as_float(v1[e]));
+          }
+        } else {
+#pragma unroll
+          for (int e = 0; e < 32; ++e) mx = fmaxf(mx, fmaxf(__uint_as_float(v0[e]), __uint_as_float(v1[e])));
         }
-      } else {
-#pragma unroll
-        for (int e = 0; e < 32; ++e) mx = fmaxf(mx, fmaxf(__uint_as_float(v0[e]), __uint_as_float(v1[e])));
       }
-      // ---- exchange the partial max with the thread holding the other 64 keys of this row ----
-      s_xch[(a * 2 + half) * 128 + r] = mx;
-      asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");
-      mx = fmaxf(mx, s_xch[(a * 2 + (half ^ 1)) * 128 + r]);
       const float m_new = fmaxf(m_run, mx);
       const float corr = ft_ex2((m_run - m_new) * c);   // 0 for the first tile (m_run = -inf)
       const float mneg = -m_new * c;
       m_run = m_new;
-      // ---- fold the previous tile's P.V into the register accumulator (it finished long ago) ----
+      // ---- fold the previous tile's P.V into the register accumulator ----
       if (j > 0) {
         ft_mbar_wait(o_full, (uint32_t)(j - 1) & 1u);
         ft_tc_fence_after();
@@ -352,53 +353,57 @@ flash_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
         if (lane == 0) ft_mbar_arrive(o_empty);
       }
       corr_pending = corr;
-      // ---- p = 2^(s*c - m*c), partial row sum in fp32, P -> fp16 into block `half` of the UMMA K-major swizzled tile ----
+      // ---- pass 2: p = 2^(s*c - m*c), row sum in fp32, P -> fp16 in the UMMA K-major swizzled layout ----
       float rs = 0.f;
-      uint8_t* prow = sP + half * FT_TILE + r * 128;
-      auto emit = [&](const uint32_t (&v)[32], int cb) {   // keys cb*32 .. +31 of this thread's 64
+#pragma unroll 1
+      for (int cc = 0; cc < 4; ++cc) {
+        uint32_t v[32];
+        ft_tmem_ld32(s_addr + cc * 32, v);
+        ft_tmem_ld_wait();
+        if (cc == 3) {   // S[a] has been read for the last time: the MMA warp may overwrite it (tile j + SBUF)
+          ft_tc_fence_before();
+          __syncwarp();
+          if (lane == 0) ft_mbar_arrive(s_empty(a));
+        }
         uint32_t pk[16];
 #pragma unroll
         for (int e = 0; e < 32; e += 2) {
           float p0 = ft_ex2(fmaf(__uint_as_float(v[e]), c, mneg));
           float p1 = ft_ex2(fmaf(__uint_as_float(v[e + 1]), c, mneg));
-          if (nvalid < 64) {
-            if (cb * 32 + e >= nvalid) p0 = 0.f;
-            if (cb * 32 + e + 1 >= nvalid) p1 = 0.f;
+          if (nvalid < 128) {
+            if (cc * 32 + e >= nvalid) p0 = 0.f;
+            if (cc * 32 + e + 1 >= nvalid) p1 = 0.f;
           }
           rs += p0 + p1;
           pk[e >> 1] = h2_as_u32(__floats2half2_rn(p0, p1));
         }
+        // keys cc*32 .. +31 = 16-byte chunks 4cc .. 4cc+3 of this row: block (4cc+i)/8, swizzled chunk ((4cc+i)%8) ^ (r%8)
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {   // 16-byte chunk cb*4 + i of the row, swizzled with the row index
-          const int ch = cb * 4 + i;
-          *reinterpret_cast<uint4*>(prow + ((ch ^ (r & 7)) << 4)) = make_uint4(pk[4 * i], pk[4 * i + 1], pk[4 * i + 2], pk[4 * i + 3]);
+        for (int i = 0; i < 4; ++i) {
+          const int ch = cc * 4 + i;
+          *reinterpret_cast<uint4*>(sP + (ch >> 3) * FT_TILE + r * 128 + (((ch & 7) ^ (r & 7)) << 4)) =
+              make_uint4(pk[4 * i], pk[4 * i + 1], pk[4 * i + 2], pk[4 * i + 3]);
         }
-      };
-      emit(v0, 0);
-      emit(v1, 1);
+      }
       l_run = fmaf(l_run, corr, rs);
       // P_j written: hand it to the MMA warp
       ft_fence_proxy_async();
       __syncwarp();
       if (lane == 0) ft_mbar_arrive(p_full);
     }
-    // ---- last tile's P.V, total row sum, normalise, store this thread's channels ----
+    // ---- last tile's P.V, normalise, store ----
     ft_mbar_wait(o_full, (uint32_t)(nk - 1) & 1u);
     ft_tc_fence_after();
     fold_t(corr_pending);
-    s_xch[(4 + half) * 128 + r] = l_run;
-    asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");
-    const float inv = 1.f / (l_run + s_xch[(4 + (half ^ 1)) * 128 + r]);
-    __half* orow = p.o + ((size_t)b * p.sq + m0 + r) * p.ldo + col0 + half * OC;
+    const float inv = 1.f / l_run;
+    __half* orow = p.o + ((size_t)b * p.sq + m0 + r) * p.ldo + col0;
     if (m0 + r < p.sq) {
 #pragma unroll
-      for (int i = 0; i < OC / 8; ++i) {
-        if (half * OC + i * 8 < HD) {
-          float f[8];
+      for (int i = 0; i < HD / 8; ++i) {
+        float f[8];
 #pragma unroll
-          for (int e = 0; e < 8; ++e) f[e] = o_acc[i * 8 + e] * inv;
-          *reinterpret_cast<uint4*>(orow + i * 8) = pack8(f);
-        }
+        for (int e = 0; e < 8; ++e) f[e] = o_acc[i * 8 + e] * inv;
+        *reinterpret_cast<uint4*>(orow + i * 8) = pack8(f);
       }
     }
   }
@@ -406,7 +411,7 @@ flash_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
   __syncthreads();
   if (warp == 1) {
     ft_tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)Cfg::TMEM_COLS) : "memory");
   }
 }
 
@@ -417,6 +422,9 @@ int ft_launch(const __half* q, int64_t ldq, const __half* k, int64_t ldk, const 
   static bool configured = false;
   if (!configured) {
     L2D_CUDA(cudaFuncSetAttribute(flash_tcgen05_kernel<HD>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
+    // without this hint the driver sizes the shared-memory carve-out for ONE CTA and the second never becomes resident
+    L2D_CUDA(cudaFuncSetAttribute(flash_tcgen05_kernel<HD>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                  (int)cudaSharedmemCarveoutMaxShared));
     configured = true;
   }
   CUtensorMap tq, tk, tv;
@@ -434,6 +442,19 @@ int ft_launch(const __half* q, int64_t ldq, const __half* k, int64_t ldk, const 
 }
 
 }  // namespace
+
+int flash_tcgen05_ctas_per_sm(int hd) {
+  int n = 0;
+  if (hd == 40) {
+    cudaFuncSetAttribute(flash_tcgen05_kernel<40>, cudaFuncAttributeMaxDynamicSharedMemorySize, FtCfg<40>::SMEM);
+    cudaFuncSetAttribute(flash_tcgen05_kernel<40>, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, flash_tcgen05_kernel<40>, FT_THREADS, FtCfg<40>::SMEM);
+  } else if (hd == 80) {
+    cudaFuncSetAttribute(flash_tcgen05_kernel<80>, cudaFuncAttributeMaxDynamicSharedMemorySize, FtCfg<80>::SMEM);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, flash_tcgen05_kernel<80>, FT_THREADS, FtCfg<80>::SMEM);
+  }
+  return n;
+}
 
 // hd 40 / 80, whole 128-query tiles, 16-byte aligned operands with row pitches that are multiples of 8 elements
 bool attention_tcgen05_supported(const void* q, const void* k, const void* v, const void* o, int64_t ldq, int64_t ldk, int64_t ldv,
@@ -456,3 +477,6 @@ int attention_tcgen05_launch(const __half* q, int64_t ldq, const __half* k, int6
 }
 
 }  // namespace l2d
+
+// developer hook (include/l2d_b200_debug.h): resident CTAs per SM of the tcgen05 attention kernel for head_dim 40 / 80
+extern "C" int l2d_debug_flash_ctas_per_sm(int hd) { return l2d::flash_tcgen05_ctas_per_sm(hd); }

@@ -189,13 +189,16 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
 // distributed shared memory -- CTA z' receives, from every CTA, the column slice [z' * BN/splits, +BN/splits) -- and after
 // one cluster barrier reduces its slice in CTA-rank order (deterministic) and applies the epilogue.  No fp32 workspace in
 // HBM/L2 and no second kernel (the non-cluster path below keeps the slice buffer + splitk_finish_kernel).
-template <int BN, int STAGES, bool CL = false>
+// NACC: accumulator stages in TMEM (2 = tile i's epilogue overlaps tile i+1's MMAs).  ("Lean" instantiations -- half the
+// operand ring, <= 256 TMEM columns, so that the next kernel's CTAs could become resident beside a running GEMM CTA and
+// overlap their prologue under PDL -- were measured 8 % slower per frame and removed: profiles/README.md.)
+template <int BN, int STAGES, bool CL = false, int NACC = 2>
 __global__ void __launch_bounds__(320, 1)
 gemm_f16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                         const GemmEpilogue epi, const ConvGeom cg, int M, int N, int K, int tiles_n, int tiles_m,
                         int splits) {
   using S = GemmSmem<BN>;
-  constexpr uint32_t TMEM_COLS = 2 * BN <= 128 ? 128 : 2 * BN <= 256 ? 256 : 512;   // two accumulator stages
+  constexpr uint32_t TMEM_COLS = NACC * BN <= 64 ? 64 : NACC * BN <= 128 ? 128 : NACC * BN <= 256 ? 256 : 512;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // 1024 B alignment is required by the 128B swizzle atom (8 rows x 128 B)
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -309,9 +312,9 @@ gemm_f16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid
       int it = 0;
       for (int i = 0; i < my_tiles; ++i) {
         const Tile tl = decode(i);
-        const int as = i & 1;
-        // the epilogue must have drained this accumulator stage (tile i-2)
-        mbar_wait(smem_u32(&tmem_empty_bar[as]), ((uint32_t)(i >> 1) & 1u) ^ 1u);
+        const int as = i % NACC;
+        // the epilogue must have drained this accumulator stage (tile i-NACC)
+        mbar_wait(smem_u32(&tmem_empty_bar[as]), ((uint32_t)(i / NACC) & 1u) ^ 1u);
         tc_fence_after();
         const uint32_t tacc = tmem_base + (uint32_t)(as * BN);
         for (int kb = 0; kb < tl.num_kb; ++kb, ++it) {
@@ -348,7 +351,7 @@ gemm_f16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid
     const int cc_end = h == 0 ? (nch_eff + 1) / 2 : nch_eff;
     for (int i = 0; i < my_tiles; ++i) {
       const Tile tl = decode(i);
-      const int as = i & 1;
+      const int as = i % NACC;
       const int n0 = tl.n0;
       int row = tl.m0 + q * 32 + lane;
       bool row_ok = row < M;
@@ -384,7 +387,7 @@ gemm_f16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid
         ln_mr = ln_rstd * mean;
       }
       float st_sum = 0.f, st_sq = 0.f;    // LayerNorm producer: sums over this warp's columns of the row
-      mbar_wait(smem_u32(&tmem_full_bar[as]), (uint32_t)(i >> 1) & 1u);
+      mbar_wait(smem_u32(&tmem_full_bar[as]), (uint32_t)(i / NACC) & 1u);
       if (dbg && i == 0 && threadIdx.x == 64) dbg[4] = clock64();   // accumulator ready
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN);
@@ -495,6 +498,9 @@ gemm_f16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid
           if (epi.act == L2D_ACT_SILU) {
 #pragma unroll
             for (int e = 0; e < 16; ++e) v[e] = silu_f(v[e]);
+          } else if (epi.act == L2D_ACT_RELU) {
+#pragma unroll
+            for (int e = 0; e < 16; ++e) v[e] = fmaxf(v[e], 0.f);
           }
           if (use_res) {
             float b[8];
@@ -504,6 +510,10 @@ gemm_f16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid
             unpack8(res1, b);
 #pragma unroll
             for (int e = 0; e < 8; ++e) v[8 + e] += b[e];
+          }
+          if (epi.act == L2D_ACT_RELU_POST) {
+#pragma unroll
+            for (int e = 0; e < 16; ++e) v[e] = fmaxf(v[e], 0.f);
           }
           if (row_ok) {
             float lo[8], hi[8];
@@ -657,12 +667,19 @@ gemm_f16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid
           if (epi.act == L2D_ACT_SILU) {
 #pragma unroll
             for (int e = 0; e < 8; ++e) v[e] = silu_f(v[e]);
+          } else if (epi.act == L2D_ACT_RELU) {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) v[e] = fmaxf(v[e], 0.f);
           }
           if (epi.residual) {
             float rr[8];
             unpack8(*reinterpret_cast<const uint4*>(epi.residual + (size_t)row * epi.ldr + col), rr);
 #pragma unroll
             for (int e = 0; e < 8; ++e) v[e] += rr[e];
+          }
+          if (epi.act == L2D_ACT_RELU_POST) {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) v[e] = fmaxf(v[e], 0.f);
           }
           *reinterpret_cast<uint4*>(epi.out + (size_t)row * epi.ldo + col) = pack8(v);
         }
@@ -708,12 +725,19 @@ __global__ void __launch_bounds__(256) splitk_finish_kernel(const GemmEpilogue e
     if (epi.act == L2D_ACT_SILU) {
 #pragma unroll
       for (int e = 0; e < 8; ++e) v[e] = silu_f(v[e]);
+    } else if (epi.act == L2D_ACT_RELU) {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) v[e] = fmaxf(v[e], 0.f);
     }
     if (epi.residual) {
       float r[8];
       unpack8(*reinterpret_cast<const uint4*>(epi.residual + (size_t)row * epi.ldr + col), r);
 #pragma unroll
       for (int e = 0; e < 8; ++e) v[e] += r[e];
+    }
+    if (epi.act == L2D_ACT_RELU_POST) {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) v[e] = fmaxf(v[e], 0.f);
     }
     *reinterpret_cast<uint4*>(epi.out + (size_t)row * epi.ldo + col) = pack8(v);
   }
@@ -796,10 +820,12 @@ struct GemmPlan {
   bool cluster;   // split-K reduced inside a thread-block cluster (DSMEM) instead of slice buffer + finish kernel
 };
 
+// Off by default: measured neutral on B200 (profiles/README.md, "cluster split-K"): the shapes whose splits fit one wave of
+// clusters are the ones where the finish kernel was already cheap.  L2D_SPLITK_CLUSTER=1 enables it.
 static bool cluster_splitk_enabled() {
   static const bool on = [] {
     const char* e = getenv("L2D_SPLITK_CLUSTER");
-    return !(e && e[0] == '0');
+    return e && e[0] == '1';
   }();
   return on;
 }
@@ -819,25 +845,29 @@ static GemmPlan gemm_plan(int m, int n, int k, bool allow_split, int force_bn) {
     for (int sp = 1; sp <= max_s; ++sp) {
       const int kb_per = ceil_div(num_kb, sp);
       if (sp > 1 && kb_per * (sp - 1) >= num_kb) continue;        // an empty last split: pointless
-      double cost;
-      if (sp > 1 && cl) {
-        // cluster split-K: the splits of a tile are one cluster of 2 / 4 / 8 CTAs, N tile 64 or 128 (partial tiles live in
-        // shared memory next to a shortened operand ring); clusters of 8 fill at most 16 per GPU (GPC granularity)
-        if (!(sp == 2 || sp == 4 || sp == 8) || !(bn == 64 || bn == 128)) continue;
-        const int slots = sp == 8 ? 128 : sp == 4 ? 144 : 148;
-        const int waves = ceil_div(tiles * sp, slots);
-        cost = waves * (kb_per * kb_cyc + 3000.0 + 1500.0 + 6.0 * bn);   // + DSMEM scatter, cluster barrier, slice reduce
-      } else {
-        if (sp > 1 && (int64_t)sp * tiles_m * BM * tiles_n * bn > kWsElems) continue;
-        const int waves = ceil_div(tiles * sp, kNumSms);
-        double cta = kb_per * kb_cyc + 3000.0;
-        if (sp > 1) cta += 13.0 * bn;                               // fp32 store of the partial tile
-        cost = waves * cta;
-        if (sp > 1) cost += 6000.0 + (double)sp * m * n * 4.0 / (kNumSms * 40.0);   // finish kernel: launch + slice reads
-      }
-      if (cost < best_cost * 0.97 || (cost < best_cost && sp < best.splits)) {
-        best_cost = cost;
-        best = {bn, sp, sp > 1 && cl};
+      for (int mode = 0; mode < 2; ++mode) {                      // 0: slice buffer + finish kernel, 1: cluster reduce
+        if (mode == 1 && (sp == 1 || !cl)) continue;
+        double cost;
+        if (mode == 1) {
+          // cluster split-K: the splits of a tile are one cluster of 2 / 4 / 8 CTAs, N tile 64 or 128 (partial tiles live in
+          // shared memory next to a shortened operand ring); one wave only (the cluster kernel takes one tile per CTA);
+          // clusters of 8 fill at most 16 per GPU (GPC granularity)
+          if (!(sp == 2 || sp == 4 || sp == 8) || !(bn == 64 || bn == 128)) continue;
+          const int slots = sp == 8 ? 128 : sp == 4 ? 144 : 148;
+          if (tiles * sp > slots) continue;
+          cost = kb_per * kb_cyc + 3000.0 + 1500.0 + 6.0 * bn;    // + DSMEM scatter, cluster barrier, slice reduce
+        } else {
+          if (sp > 1 && (int64_t)sp * tiles_m * BM * tiles_n * bn > kWsElems) continue;
+          const int waves = ceil_div(tiles * sp, kNumSms);
+          double cta = kb_per * kb_cyc + 3000.0;
+          if (sp > 1) cta += 13.0 * bn;                             // fp32 store of the partial tile
+          cost = waves * cta;
+          if (sp > 1) cost += 6000.0 + (double)sp * m * n * 4.0 / (kNumSms * 40.0);   // finish kernel: launch + slice reads
+        }
+        if (cost < best_cost * 0.97 || (cost < best_cost && sp < best.splits)) {
+          best_cost = cost;
+          best = {bn, sp, mode == 1};
+        }
       }
     }
   }
@@ -939,21 +969,21 @@ static int launch_gemm_cluster(const CUtensorMap& ta, const CUtensorMap& tb, con
   return L2D_OK;
 }
 
-template <int BN, int STAGES>
+template <int BN, int STAGES, int NACC = 2>
 static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmEpilogue& e, const ConvGeom& cg, int M,
                        int N, int K, int splits, int tiles_m, cudaStream_t st) {
   constexpr size_t smem = (size_t)STAGES * GemmSmem<BN>::STAGE_BYTES + (2 * STAGES + 6) * 8 + 1024;
   static bool configured = false;
   if (!configured) {
-    L2D_CUDA(cudaFuncSetAttribute(gemm_f16_tcgen05_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    L2D_CUDA(cudaFuncSetAttribute(gemm_f16_tcgen05_kernel<BN, STAGES, false, NACC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)smem));
     configured = true;
   }
   const int tiles_n = ceil_div(N, BN);
   const int total = tiles_n * tiles_m * splits;
   const int grid = total < kNumSms ? total : kNumSms;
-  launch_pdl_if(pdl_family(0) && t_weights_constant, gemm_f16_tcgen05_kernel<BN, STAGES>, dim3(grid), dim3(320), smem, st, ta, tb, e, cg, M, N, K, tiles_n, tiles_m,
-             splits);
+  launch_pdl_if(pdl_family(0) && t_weights_constant, gemm_f16_tcgen05_kernel<BN, STAGES, false, NACC>, dim3(grid), dim3(320), smem, st,
+                ta, tb, e, cg, M, N, K, tiles_n, tiles_m, splits);
   L2D_LAUNCH_CHECK();
   return L2D_OK;
 }
@@ -992,12 +1022,14 @@ static int gemm_dispatch(const CUtensorMap& ta, const __half* w, int64_t ldw, co
     e.ws_ld = (int64_t)ceil_div(n, bn) * bn;
     e.ws_slice = (int64_t)m_pad * e.ws_ld;
   }
-  switch (bn) {
-    case 64: rc = launch_gemm<64, 6>(ta, tb, e, cg, m, n, k, plan.splits, tiles_m, st); break;
-    case 128: rc = launch_gemm<128, 6>(ta, tb, e, cg, m, n, k, plan.splits, tiles_m, st); break;
-    case 160: rc = launch_gemm<160, 5>(ta, tb, e, cg, m, n, k, plan.splits, tiles_m, st); break;
-    case 256: rc = launch_gemm<256, 4>(ta, tb, e, cg, m, n, k, plan.splits, tiles_m, st); break;
-    default: return fail(L2D_ERR_INVALID, "gemm: unsupported tile_n");
+  {
+    switch (bn) {
+      case 64: rc = launch_gemm<64, 6>(ta, tb, e, cg, m, n, k, plan.splits, tiles_m, st); break;
+      case 128: rc = launch_gemm<128, 6>(ta, tb, e, cg, m, n, k, plan.splits, tiles_m, st); break;
+      case 160: rc = launch_gemm<160, 5>(ta, tb, e, cg, m, n, k, plan.splits, tiles_m, st); break;
+      case 256: rc = launch_gemm<256, 4>(ta, tb, e, cg, m, n, k, plan.splits, tiles_m, st); break;
+      default: return fail(L2D_ERR_INVALID, "gemm: unsupported tile_n");
+    }
   }
   if (rc != L2D_OK || plan.splits == 1) return rc;
   const size_t work = (size_t)m * (n / 8);
@@ -1103,7 +1135,8 @@ extern "C" int l2d_conv3x3(const void* x, int n_img, int h, int w, int cin, cons
   L2D_CHECK_ARG(x && weight && out, "null pointer");
   L2D_CHECK_ARG(n_img > 0 && h > 0 && w > 0 && cin > 0 && cout > 0, "empty problem");
   L2D_CHECK_ARG(cout % 8 == 0 && ldo % 8 == 0 && ldo >= cout, "Cout and ldo must be multiples of 8");
-  L2D_CHECK_ARG(act == L2D_ACT_NONE || act == L2D_ACT_SILU, "act must be none or SiLU");
+  L2D_CHECK_ARG(act == L2D_ACT_NONE || act == L2D_ACT_SILU || act == L2D_ACT_RELU || act == L2D_ACT_RELU_POST,
+                "act must be none, SiLU, ReLU or ReLU-after-residual");
   L2D_CHECK_ARG(conv3x3_implicit_supported(n_img, h, w, cin), "need Cin % 64 == 0 and power-of-two tileable H, W");
   return conv3x3_launch((const __half*)x, n_img, h, w, cin, (const __half*)weight, (__half*)out, ldo, cout,
                         (const __half*)bias, (const __half*)rowgroup_bias, cout, h * w, (const __half*)residual, ldr, act,
@@ -1117,7 +1150,7 @@ extern "C" int l2d_gemm(const void* a, int64_t lda, const void* w, void* out, in
   L2D_CHECK_ARG(m > 0 && n > 0 && k > 0, "empty problem");
   L2D_CHECK_ARG(k % 8 == 0 && n % 8 == 0 && lda % 8 == 0 && ldo % 8 == 0, "K, N, lda, ldo must be multiples of 8");
   L2D_CHECK_ARG(lda >= k, "lda < K");
-  L2D_CHECK_ARG(act >= 0 && act <= 2, "bad act");
+  L2D_CHECK_ARG(act >= 0 && act <= 4, "bad act");
   L2D_CHECK_ARG(!residual || ldr % 8 == 0, "ldr must be a multiple of 8");
   L2D_CHECK_ARG(!rowgroup_bias || rows_per_group > 0, "rows_per_group must be > 0");
   L2D_CHECK_ARG(((uintptr_t)a % 16 == 0) && ((uintptr_t)w % 16 == 0) && ((uintptr_t)out % 16 == 0), "16-byte alignment");

@@ -13,7 +13,10 @@ sys.path.insert(0, os.path.abspath(os.path.join(os.path.dirname(__file__), "..")
 from live2diff_b200 import ops  # noqa: E402
 
 dev = "cuda:0"
-out = {"legacy": os.environ.get("L2D_FLASH_LEGACY", "0")}
+from live2diff_b200 import _lib  # noqa: E402
+
+out = {"legacy": os.environ.get("L2D_FLASH_LEGACY", "0"),
+       "ctas_per_sm": {hd: _lib.lib().l2d_debug_flash_ctas_per_sm(hd) for hd in (40, 80)}}
 for name, b, heads, sq, skv, hd in [("l0_self", 2, 8, 4096, 4096, 40), ("l0_cross", 2, 8, 4096, 77, 40),
                                     ("l1_self", 2, 8, 1024, 1024, 80), ("l1_cross", 2, 8, 1024, 77, 80),
                                     ("cfg3_l0_self", 2, 8, 6144, 6144, 40), ("cfg4_l0_self", 4, 8, 4096, 4096, 40)]:
