@@ -335,11 +335,14 @@ struct Core {
     return L2D_OK;
   }
 
-  // L2D_LN_FOLD=0 keeps the separate LayerNorm kernels (A/B switch; default: folded)
+  // L2D_LN_FOLD=1 folds every LayerNorm into the GEMMs around it (127 fewer launches per frame).  OFF by default: measured
+  // on B200 the folded frame is 2 % SLOWER (105.6 vs 107.5 frames/s, profiles/README.md): the small LayerNorm kernels are
+  // what lets programmatic dependent launch overlap a GEMM's prologue with its predecessor -- a GEMM CTA (190 KB of
+  // shared memory, up to 512 TMEM columns) cannot become resident next to another GEMM CTA, a LayerNorm CTA can.
   static bool ln_fold_enabled() {
     static const bool on = [] {
       const char* e = getenv("L2D_LN_FOLD");
-      return !(e && e[0] == '0');
+      return e && e[0] == '1';
     }();
     return on;
   }

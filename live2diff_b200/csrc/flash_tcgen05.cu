@@ -22,6 +22,8 @@
 // other rows of the same tensor or TMA zero fill, always finite.
 #include <cuda.h>
 
+#include <cstdio>
+
 #include "ops.cuh"
 
 namespace l2d {
@@ -133,55 +135,59 @@ struct FtParams {
   float scale_log2;   // log2(e) / sqrt(hd)
 };
 
-constexpr int FT_THREADS = 192;   // TMA warp, MMA warp, 4 softmax warps (one thread per query row)
 constexpr int FT_TILE = 128 * 128;   // bytes of one [128 rows x 64 fp16] swizzled block
 
-template <int HD>
+// NQ = 128-query tiles per CTA.  The driver keeps kernels that use tcgen05 at ONE CTA per SM whatever their shared-memory
+// and TMEM footprint (measured: cudaOccupancyMaxActiveBlocksPerMultiprocessor = 1 even at 48 KB / 256 columns), so the
+// latency hiding that two co-resident CTAs would give is built into one: with NQ = 2 two query tiles share every K/V tile
+// and run their own softmax warp quartets; while one tile's chain (S ready -> softmax -> P ready -> P.V -> T ready) waits on
+// the tensor core or a barrier, the other's exp pass keeps the MUFU pipe busy.  hd = 80 has no room for the second Q / P
+// tile (192 KB already) and keeps NQ = 1 with two S accumulators instead.
+template <int HD, int NQ>
 struct FtCfg {
   static constexpr int KSTEPS = (HD + 15) / 16;     // k16 steps of Q.K^T
   static constexpr int NBLK = (HD + 63) / 64;       // 64-column blocks of a Q / K / V tile
   static constexpr int ON = KSTEPS * 16;            // columns of T = P.V that are read back (hd rounded up to 16)
   static constexpr int ON_MMA = NBLK * 64;          // MMA N of P.V: whole 64-channel swizzle atoms of the V tile
-  static constexpr int STAGES = 2;                  // K ring depth
-  static constexpr int VSTAGES = HD <= 64 ? 1 : 2;  // V ring depth (V_j is needed a whole softmax later than K_j)
-  // hd <= 64: 96 KB of shared memory and 256 TMEM columns per CTA -> TWO CTAs per SM.  Their softmax phases (MUFU-bound,
-  // ~1000 cycles per tile) and their synchronisation chains (S ready -> softmax -> P ready -> P.V -> T ready) run out of
-  // phase and hide each other; one S accumulator per CTA is then enough.  hd = 80 (192 KB): one CTA per SM, two S buffers.
-  static constexpr int SBUF = HD <= 64 ? 1 : 2;
-  static constexpr int TMEM_COLS = SBUF == 1 ? 256 : 512;
-  static constexpr int TM_O = SBUF * 128;
-  static constexpr int CTAS_PER_SM = HD <= 64 ? 2 : 1;
+  static constexpr int STAGES = 2;                  // K / V ring depth
+  static constexpr int SBUF = 2 / NQ;               // S accumulators per query tile (NQ * SBUF = 2 x 128 TMEM columns)
+  static constexpr int TMEM_COLS = 512;             // S: 256, T: NQ x ON_MMA <= 256
+  static constexpr int THREADS = 64 + NQ * 128;     // TMA warp, MMA warp, 4 softmax warps per query tile
   static constexpr int TILE_BYTES = NBLK * FT_TILE;
-  static constexpr int SLACK = 1024;
-  static constexpr int SMEM = TILE_BYTES * (1 + STAGES + VSTAGES) + 2 * FT_TILE /* P */ + 256 /* barriers */ + SLACK;
+  static constexpr int SMEM = TILE_BYTES * (NQ + 2 * STAGES) + NQ * 2 * FT_TILE /* P */ + 256 /* barriers */ + 1024 /* align */;
+  static_assert(NQ * ON_MMA <= 256 && (NQ == 1 || NQ == 2), "TMEM layout");
 };
 
-template <int HD>
-__global__ void __launch_bounds__(FT_THREADS, FtCfg<HD>::CTAS_PER_SM)
+template <int HD, int NQ>
+__global__ void __launch_bounds__(FtCfg<HD, NQ>::THREADS, 1)
 flash_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
                      const __grid_constant__ CUtensorMap tmap_v, const FtParams p) {
-  using Cfg = FtCfg<HD>;
-  constexpr int ST = Cfg::STAGES, VST = Cfg::VSTAGES, NBLK = Cfg::NBLK, KSTEPS = Cfg::KSTEPS, ON = Cfg::ON, SBUF = Cfg::SBUF;
+  using Cfg = FtCfg<HD, NQ>;
+  constexpr int ST = Cfg::STAGES, NBLK = Cfg::NBLK, KSTEPS = Cfg::KSTEPS, ON = Cfg::ON, SBUF = Cfg::SBUF;
   extern __shared__ __align__(1024) uint8_t ft_smem_raw[];
   uint8_t* smem = ft_smem_raw + ((1024u - (ft_smem_u32(ft_smem_raw) & 1023u)) & 1023u);
-  uint8_t* sQ = smem;
-  uint8_t* sK = sQ + Cfg::TILE_BYTES;
+  uint8_t* sQ = smem;                                  // [NQ] query tiles
+  uint8_t* sK = sQ + NQ * Cfg::TILE_BYTES;
   uint8_t* sV = sK + ST * Cfg::TILE_BYTES;
-  uint8_t* sP = sV + VST * Cfg::TILE_BYTES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 2 * FT_TILE);
+  uint8_t* sP = sV + ST * Cfg::TILE_BYTES;             // [NQ] P tiles of 2 x 16 KB
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + NQ * 2 * FT_TILE);
   const uint32_t bar0 = ft_smem_u32(bars);
-  // barrier map
-  const uint32_t q_full = bar0, q_ready = bar0 + 8, p_full = bar0 + 16, o_full = bar0 + 24, o_empty = bar0 + 32;
-  auto k_full = [&](int s) { return bar0 + 40 + 8u * s; };
-  auto k_empty = [&](int s) { return bar0 + 40 + 8u * (ST + s); };
-  auto v_full = [&](int s) { return bar0 + 40 + 8u * (2 * ST + s); };
-  auto v_empty = [&](int s) { return bar0 + 40 + 8u * (3 * ST + s); };
-  auto s_full = [&](int b) { return bar0 + 40 + 8u * (4 * ST + b); };
-  auto s_empty = [&](int b) { return bar0 + 40 + 8u * (4 * ST + 2 + b); };
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 5 + 4 * ST + 4);
+  // barrier map: q_full, q_ready | per query tile t: p_full, o_full, o_empty, s_full[2], s_empty[2] | k/v full/empty[ST]
+  const uint32_t q_full = bar0, q_ready = bar0 + 8;
+  auto p_full = [&](int t) { return bar0 + 16 + 56u * t; };
+  auto o_full = [&](int t) { return bar0 + 24 + 56u * t; };
+  auto o_empty = [&](int t) { return bar0 + 32 + 56u * t; };
+  auto s_full = [&](int t, int a) { return bar0 + 40 + 56u * t + 8u * a; };
+  auto s_empty = [&](int t, int a) { return bar0 + 56 + 56u * t + 8u * a; };
+  const uint32_t kv0 = bar0 + 16 + 56u * NQ;
+  auto k_full = [&](int s) { return kv0 + 8u * s; };
+  auto k_empty = [&](int s) { return kv0 + 8u * (ST + s); };
+  auto v_full = [&](int s) { return kv0 + 8u * (2 * ST + s); };
+  auto v_empty = [&](int s) { return kv0 + 8u * (3 * ST + s); };
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 2 + 7 * NQ + 4 * ST);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int b = blockIdx.z, h = blockIdx.y, m0 = blockIdx.x * 128;
+  const int b = blockIdx.z, h = blockIdx.y, m0 = blockIdx.x * (128 * NQ);
   const int nk = (p.skv + 127) >> 7;
   const int col0 = h * HD;
 
@@ -191,19 +197,21 @@ flash_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_k) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_v) : "memory");
     ft_mbar_init(q_full, 1);
-    ft_mbar_init(q_ready, 4);
-    ft_mbar_init(p_full, 4);
-    ft_mbar_init(o_full, 1);
-    ft_mbar_init(o_empty, 4);
+    ft_mbar_init(q_ready, 4 * NQ);
+    for (int t = 0; t < NQ; ++t) {
+      ft_mbar_init(p_full(t), 4);
+      ft_mbar_init(o_full(t), 1);
+      ft_mbar_init(o_empty(t), 4);
+      for (int a = 0; a < 2; ++a) {
+        ft_mbar_init(s_full(t, a), 1);
+        ft_mbar_init(s_empty(t, a), 4);
+      }
+    }
     for (int s = 0; s < ST; ++s) {
       ft_mbar_init(k_full(s), 1);
       ft_mbar_init(k_empty(s), 1);
       ft_mbar_init(v_full(s), 1);
       ft_mbar_init(v_empty(s), 1);
-    }
-    for (int a = 0; a < 2; ++a) {
-      ft_mbar_init(s_full(a), 1);
-      ft_mbar_init(s_empty(a), 4);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -215,14 +223,18 @@ flash_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
   __syncthreads();
   ft_tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
-  constexpr uint32_t TM_S = 0, TM_O = Cfg::TM_O;   // TMEM columns: S buffers of 128 columns each, then T (ON_MMA columns)
+  // TMEM columns: S accumulator (tile t, buffer a) at (t * SBUF + a) * 128; T of tile t at 256 + t * ON_MMA
+  auto tm_s = [&](int t, int a) { return (uint32_t)((t * SBUF + a) * 128); };
+  auto tm_o = [&](int t) { return (uint32_t)(256 + t * Cfg::ON_MMA); };
 
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
       pdl_wait();   // q / k / v were written by the projection GEMMs right before this kernel
-      ft_mbar_expect_tx(q_full, Cfg::TILE_BYTES);
-      for (int cb = 0; cb < NBLK; ++cb) ft_tma_2d(ft_smem_u32(sQ + cb * FT_TILE), &tmap_q, q_full, col0 + cb * 64, b * p.sq + m0);
+      ft_mbar_expect_tx(q_full, NQ * Cfg::TILE_BYTES);
+      for (int t = 0; t < NQ; ++t)
+        for (int cb = 0; cb < NBLK; ++cb)
+          ft_tma_2d(ft_smem_u32(sQ + t * Cfg::TILE_BYTES + cb * FT_TILE), &tmap_q, q_full, col0 + cb * 64, b * p.sq + m0 + t * 128);
       auto load_k = [&](int j) {
         const int s = j % ST;
         ft_mbar_wait(k_empty(s), ((uint32_t)(j / ST) & 1u) ^ 1u);
@@ -234,8 +246,8 @@ flash_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
       load_k(0);
       for (int j = 0; j < nk; ++j) {
         if (j + 1 < nk) load_k(j + 1);
-        const int sv = j % VST;
-        ft_mbar_wait(v_empty(sv), ((uint32_t)(j / VST) & 1u) ^ 1u);
+        const int sv = j % ST;
+        ft_mbar_wait(v_empty(sv), ((uint32_t)(j / ST) & 1u) ^ 1u);
         ft_mbar_expect_tx(v_full(sv), Cfg::TILE_BYTES);
         for (int cb = 0; cb < NBLK; ++cb)
           ft_tma_2d(ft_smem_u32(sV + sv * Cfg::TILE_BYTES + cb * FT_TILE), &tmap_v, v_full(sv), col0 + cb * 64, b * p.skv + j * 128);
@@ -246,54 +258,59 @@ flash_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
     if (lane == 0) {
       constexpr uint32_t idesc_s = ft_idesc(128, 0);
       constexpr uint32_t idesc_o = ft_idesc(Cfg::ON_MMA, 1);
-      auto issue_s = [&](int j) {
+      auto issue_s = [&](int t, int j) {
         const int s = j % ST, a = j % SBUF;
-        ft_mbar_wait(k_full(s), (uint32_t)(j / ST) & 1u);
-        ft_mbar_wait(s_empty(a), ((uint32_t)(j / SBUF) & 1u) ^ 1u);   // the softmax has drained this S accumulator (tile j-SBUF)
+        if (t == 0) ft_mbar_wait(k_full(s), (uint32_t)(j / ST) & 1u);
+        ft_mbar_wait(s_empty(t, a), ((uint32_t)(j / SBUF) & 1u) ^ 1u);   // the softmax has drained this S accumulator (tile j-SBUF)
         ft_tc_fence_after();
-        const uint32_t qa = ft_smem_u32(sQ), ka = ft_smem_u32(sK + s * Cfg::TILE_BYTES);
+        const uint32_t qa = ft_smem_u32(sQ + t * Cfg::TILE_BYTES), ka = ft_smem_u32(sK + s * Cfg::TILE_BYTES);
 #pragma unroll
         for (int k = 0; k < KSTEPS; ++k) {
           const uint32_t off = (uint32_t)(k >> 2) * FT_TILE + (uint32_t)(k & 3) * 32;
-          ft_umma(tmem_base + TM_S + (uint32_t)a * 128, ft_desc(qa + off, 0), ft_desc(ka + off, 0), idesc_s, k != 0);
+          ft_umma(tmem_base + tm_s(t, a), ft_desc(qa + off, 0), ft_desc(ka + off, 0), idesc_s, k != 0);
         }
-        ft_commit(k_empty(s));
-        ft_commit(s_full(a));
+        if (t == NQ - 1) ft_commit(k_empty(s));   // every query tile has read K_j
+        ft_commit(s_full(t, a));
       };
-      auto issue_pv = [&](int j) {
-        const int s = j % VST;
-        ft_mbar_wait(v_full(s), (uint32_t)(j / VST) & 1u);
-        ft_mbar_wait(p_full, (uint32_t)j & 1u);
-        if (j > 0) ft_mbar_wait(o_empty, (uint32_t)(j - 1) & 1u);   // T_{j-1} has been folded into the register accumulator
+      auto issue_pv = [&](int t, int j) {
+        const int s = j % ST;
+        if (t == 0) ft_mbar_wait(v_full(s), (uint32_t)(j / ST) & 1u);
+        ft_mbar_wait(p_full(t), (uint32_t)j & 1u);
+        if (j > 0) ft_mbar_wait(o_empty(t), (uint32_t)(j - 1) & 1u);   // T_{j-1} has been folded into the register accumulator
         ft_tc_fence_after();
-        const uint32_t pa = ft_smem_u32(sP), va = ft_smem_u32(sV + s * Cfg::TILE_BYTES);
+        const uint32_t pa = ft_smem_u32(sP + t * 2 * FT_TILE), va = ft_smem_u32(sV + s * Cfg::TILE_BYTES);
 #pragma unroll
         for (int kk = 0; kk < 8; ++kk) {   // 128 keys = 8 k16 steps: P block kk/4, +32 B per step; V: 16 key rows = 2 KB per step
           const uint64_t da = ft_desc(pa + (uint32_t)(kk >> 2) * FT_TILE + (uint32_t)(kk & 3) * 32, 0);
           const uint64_t db = ft_desc(va + (uint32_t)kk * 2048, FT_TILE);
-          ft_umma(tmem_base + TM_O, da, db, idesc_o, kk != 0);
+          ft_umma(tmem_base + tm_o(t), da, db, idesc_o, kk != 0);
         }
-        ft_commit(v_empty(s));
-        ft_commit(o_full);
+        if (t == NQ - 1) ft_commit(v_empty(s));   // every query tile has read V_j
+        ft_commit(o_full(t));
       };
       ft_mbar_wait(q_ready, 0);
-      issue_s(0);
+      for (int t = 0; t < NQ; ++t) issue_s(t, 0);
       for (int j = 0; j < nk; ++j) {
-        // (with one S buffer this waits until the softmax of tile j has read S_j for the last time -- about two thirds into
-        //  its tile -- so S_{j+1} is still ready before the softmax threads come back for it)
-        if (j + 1 < nk) issue_s(j + 1);
-        issue_pv(j);
+        for (int t = 0; t < NQ; ++t) {
+          // (with one S buffer per tile this waits until the softmax of tile j has read S_j for the last time -- about two
+          //  thirds into its tile -- so S_{j+1} is still ready before the softmax threads come back for it)
+          if (j + 1 < nk) issue_s(t, j + 1);
+          issue_pv(t, j);
+        }
       }
     }
   } else {
-    // ===================== softmax / correction / epilogue (warps 2..5) =====================
+    // ===================== softmax / correction / epilogue (4 warps per query tile) =====================
+    const int t = (warp - 2) >> 2;             // query tile of this warp quartet
     const int q = warp & 3;                    // TMEM lane quarter this warp may touch
     const int r = q * 32 + lane;               // query row inside the tile
     const uint32_t t_lane = tmem_base + ((uint32_t)(q * 32) << 16);
+    uint8_t* myQ = sQ + t * Cfg::TILE_BYTES;
+    uint8_t* myP = sP + t * 2 * FT_TILE;
     ft_mbar_wait(q_full, 0);
     if (HD % 16 != 0) {   // zero columns HD .. KSTEPS*16-1 of this row (hd = 40: chunk 5 of block 0)
       constexpr int chunk = HD / 8;
-      *reinterpret_cast<uint4*>(sQ + (chunk >> 3) * FT_TILE + r * 128 + (((chunk & 7) ^ (r & 7)) << 4)) = make_uint4(0, 0, 0, 0);
+      *reinterpret_cast<uint4*>(myQ + (chunk >> 3) * FT_TILE + r * 128 + (((chunk & 7) ^ (r & 7)) << 4)) = make_uint4(0, 0, 0, 0);
     }
     ft_fence_proxy_async();
     __syncwarp();
@@ -306,20 +323,20 @@ flash_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
     const float c = p.scale_log2;
 
     auto fold_t = [&](float corr) {   // o = o * corr + T   (T = P.V of the previous tile, in TMEM)
-      uint32_t t[ON];
+      uint32_t tt[ON];
 #pragma unroll
-      for (int cc = 0; cc < ON / 16; ++cc) ft_tmem_ld16(t_lane + TM_O + cc * 16, *reinterpret_cast<uint32_t(*)[16]>(&t[cc * 16]));
+      for (int cc = 0; cc < ON / 16; ++cc) ft_tmem_ld16(t_lane + tm_o(t) + cc * 16, *reinterpret_cast<uint32_t(*)[16]>(&tt[cc * 16]));
       ft_tmem_ld_wait();
 #pragma unroll
-      for (int e = 0; e < ON; ++e) o_acc[e] = fmaf(o_acc[e], corr, __uint_as_float(t[e]));
+      for (int e = 0; e < ON; ++e) o_acc[e] = fmaf(o_acc[e], corr, __uint_as_float(tt[e]));
     };
 
     for (int j = 0; j < nk; ++j) {
       const int a = j % SBUF;
       const int nvalid = min(128, p.skv - j * 128);
-      ft_mbar_wait(s_full(a), (uint32_t)(j / SBUF) & 1u);
+      ft_mbar_wait(s_full(t, a), (uint32_t)(j / SBUF) & 1u);
       ft_tc_fence_after();
-      const uint32_t s_addr = t_lane + TM_S + (uint32_t)a * 128;
+      const uint32_t s_addr = t_lane + tm_s(t, a);
       // ---- pass 1: row max of the raw scores (two 32-column loads in flight) ----
       float mx = -INFINITY;
 #pragma unroll 1
@@ -345,12 +362,12 @@ flash_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
       m_run = m_new;
       // ---- fold the previous tile's P.V into the register accumulator ----
       if (j > 0) {
-        ft_mbar_wait(o_full, (uint32_t)(j - 1) & 1u);
+        ft_mbar_wait(o_full(t), (uint32_t)(j - 1) & 1u);
         ft_tc_fence_after();
         fold_t(corr_pending);
         ft_tc_fence_before();
         __syncwarp();
-        if (lane == 0) ft_mbar_arrive(o_empty);
+        if (lane == 0) ft_mbar_arrive(o_empty(t));
       }
       corr_pending = corr;
       // ---- pass 2: p = 2^(s*c - m*c), row sum in fp32, P -> fp16 in the UMMA K-major swizzled layout ----
@@ -360,10 +377,10 @@ flash_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
         uint32_t v[32];
         ft_tmem_ld32(s_addr + cc * 32, v);
         ft_tmem_ld_wait();
-        if (cc == 3) {   // S[a] has been read for the last time: the MMA warp may overwrite it (tile j + SBUF)
+        if (cc == 3) {   // S has been read for the last time: the MMA warp may overwrite it (tile j + SBUF)
           ft_tc_fence_before();
           __syncwarp();
-          if (lane == 0) ft_mbar_arrive(s_empty(a));
+          if (lane == 0) ft_mbar_arrive(s_empty(t, a));
         }
         uint32_t pk[16];
 #pragma unroll
@@ -381,7 +398,7 @@ flash_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           const int ch = cc * 4 + i;
-          *reinterpret_cast<uint4*>(sP + (ch >> 3) * FT_TILE + r * 128 + (((ch & 7) ^ (r & 7)) << 4)) =
+          *reinterpret_cast<uint4*>(myP + (ch >> 3) * FT_TILE + r * 128 + (((ch & 7) ^ (r & 7)) << 4)) =
               make_uint4(pk[4 * i], pk[4 * i + 1], pk[4 * i + 2], pk[4 * i + 3]);
         }
       }
@@ -389,15 +406,16 @@ flash_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
       // P_j written: hand it to the MMA warp
       ft_fence_proxy_async();
       __syncwarp();
-      if (lane == 0) ft_mbar_arrive(p_full);
+      if (lane == 0) ft_mbar_arrive(p_full(t));
     }
     // ---- last tile's P.V, normalise, store ----
-    ft_mbar_wait(o_full, (uint32_t)(nk - 1) & 1u);
+    ft_mbar_wait(o_full(t), (uint32_t)(nk - 1) & 1u);
     ft_tc_fence_after();
     fold_t(corr_pending);
     const float inv = 1.f / l_run;
-    __half* orow = p.o + ((size_t)b * p.sq + m0 + r) * p.ldo + col0;
-    if (m0 + r < p.sq) {
+    const int row = m0 + t * 128 + r;
+    __half* orow = p.o + ((size_t)b * p.sq + row) * p.ldo + col0;
+    if (row < p.sq) {
 #pragma unroll
       for (int i = 0; i < HD / 8; ++i) {
         float f[8];
@@ -415,16 +433,13 @@ flash_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
   }
 }
 
-template <int HD>
+template <int HD, int NQ>
 int ft_launch(const __half* q, int64_t ldq, const __half* k, int64_t ldk, const __half* v, int64_t ldv, __half* o, int64_t ldo,
               int batch, int heads, int sq, int skv, cudaStream_t st) {
-  using Cfg = FtCfg<HD>;
+  using Cfg = FtCfg<HD, NQ>;
   static bool configured = false;
   if (!configured) {
-    L2D_CUDA(cudaFuncSetAttribute(flash_tcgen05_kernel<HD>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
-    // without this hint the driver sizes the shared-memory carve-out for ONE CTA and the second never becomes resident
-    L2D_CUDA(cudaFuncSetAttribute(flash_tcgen05_kernel<HD>, cudaFuncAttributePreferredSharedMemoryCarveout,
-                                  (int)cudaSharedmemCarveoutMaxShared));
+    L2D_CUDA(cudaFuncSetAttribute(flash_tcgen05_kernel<HD, NQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
     configured = true;
   }
   CUtensorMap tq, tk, tv;
@@ -435,8 +450,8 @@ int ft_launch(const __half* q, int64_t ldq, const __half* k, int64_t ldk, const 
   rc = get_tmap_2d(v, (int64_t)batch * skv, (int64_t)heads * HD, ldv, 128, &tv);
   if (rc != L2D_OK) return rc;
   FtParams p{o, ldo, sq, skv, heads, 1.4426950408889634f / sqrtf((float)HD)};
-  launch_pdl_if(pdl_family(2), flash_tcgen05_kernel<HD>, dim3(sq / 128, heads, batch), dim3(FT_THREADS), (size_t)Cfg::SMEM, st, tq, tk,
-                tv, p);
+  launch_pdl_if(pdl_family(2), flash_tcgen05_kernel<HD, NQ>, dim3(sq / (128 * NQ), heads, batch), dim3(Cfg::THREADS),
+                (size_t)Cfg::SMEM, st, tq, tk, tv, p);
   L2D_LAUNCH_CHECK();
   return L2D_OK;
 }
@@ -446,12 +461,20 @@ int ft_launch(const __half* q, int64_t ldq, const __half* k, int64_t ldk, const 
 int flash_tcgen05_ctas_per_sm(int hd) {
   int n = 0;
   if (hd == 40) {
-    cudaFuncSetAttribute(flash_tcgen05_kernel<40>, cudaFuncAttributeMaxDynamicSharedMemorySize, FtCfg<40>::SMEM);
-    cudaFuncSetAttribute(flash_tcgen05_kernel<40>, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared);
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, flash_tcgen05_kernel<40>, FT_THREADS, FtCfg<40>::SMEM);
+    cudaFuncSetAttribute(flash_tcgen05_kernel<40, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, FtCfg<40, 2>::SMEM);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, flash_tcgen05_kernel<40, 2>, FtCfg<40, 2>::THREADS, FtCfg<40, 2>::SMEM);
+    if (getenv("L2D_FLASH_OCC_DEBUG")) {   // developer print: occupancy as a function of the dynamic shared-memory request
+      fprintf(stderr, "[flash occupancy] hd 40, NQ 2 (%d threads):", FtCfg<40, 2>::THREADS);
+      for (int kb : {48, 96, 112, 160}) {
+        int m = 0;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&m, flash_tcgen05_kernel<40, 2>, FtCfg<40, 2>::THREADS, (size_t)kb * 1024);
+        fprintf(stderr, " %dKB:%d", kb, m);
+      }
+      fprintf(stderr, "\n");
+    }
   } else if (hd == 80) {
-    cudaFuncSetAttribute(flash_tcgen05_kernel<80>, cudaFuncAttributeMaxDynamicSharedMemorySize, FtCfg<80>::SMEM);
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, flash_tcgen05_kernel<80>, FT_THREADS, FtCfg<80>::SMEM);
+    cudaFuncSetAttribute(flash_tcgen05_kernel<80, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, FtCfg<80, 1>::SMEM);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, flash_tcgen05_kernel<80, 1>, FtCfg<80, 1>::THREADS, FtCfg<80, 1>::SMEM);
   }
   return n;
 }
@@ -471,8 +494,9 @@ bool attention_tcgen05_supported(const void* q, const void* k, const void* v, co
 
 int attention_tcgen05_launch(const __half* q, int64_t ldq, const __half* k, int64_t ldk, const __half* v, int64_t ldv, __half* o,
                              int64_t ldo, int batch, int heads, int sq, int skv, int hd, cudaStream_t st) {
-  if (hd == 40) return ft_launch<40>(q, ldq, k, ldk, v, ldv, o, ldo, batch, heads, sq, skv, st);
-  if (hd == 80) return ft_launch<80>(q, ldq, k, ldk, v, ldv, o, ldo, batch, heads, sq, skv, st);
+  if (hd == 40 && sq % 256 == 0) return ft_launch<40, 2>(q, ldq, k, ldk, v, ldv, o, ldo, batch, heads, sq, skv, st);
+  if (hd == 40) return ft_launch<40, 1>(q, ldq, k, ldk, v, ldv, o, ldo, batch, heads, sq, skv, st);
+  if (hd == 80) return ft_launch<80, 1>(q, ldq, k, ldk, v, ldv, o, ldo, batch, heads, sq, skv, st);
   return fail(L2D_ERR_INVALID, "attention(tcgen05): unsupported head_dim");
 }
 

@@ -61,10 +61,8 @@ constexpr int KV_MAX_SLOTS = 4;
 // PE_REGS (L <= 16, <= 192 threads): the thread's K_pe / V_pe chunks of all L slots stay in registers for the whole
 // row n (every pixel of a row shares pe_idx[n]), so the slot loops are LDS.128 + 4 HADD2 + 8 cvt + 8 FFMA per slot
 // with no global loads and no index arithmetic.
-// (the general-window variant keeps <= 102 registers so that TWO CTAs fit per SM: long windows (L = 32) halve the pixels
-//  per tile, and the second CTA's loads / reductions hide the first one's barrier chain)
 template <bool PE_REGS>
-__global__ void __launch_bounds__(PE_REGS ? 192 : 320, PE_REGS ? 1 : 2)
+__global__ void __launch_bounds__(PE_REGS ? 192 : 320, 1)
 kv_attn_kernel(const KvAttnParams p, const int n_slots, const int slot_bytes, const int tiles_per_row) {
   constexpr int LR = 16;   // slots covered by the unrolled register path
   extern __shared__ __align__(128) uint8_t kv_smem[];
@@ -286,24 +284,19 @@ int kv_attn_launch(const KvAttnParams& p0, cudaStream_t stream) {
   p.hd8 = (p.C / p.heads) / 8;
   if (p.T > 320) return fail(L2D_ERR_INVALID, "kv_attn: channels too large for one block (C <= 2560)");
   int P = 160 / p.T;                 // 160 chunk-threads per CTA: 4/2/1 pixels at C = 320/640/1280
-  if (p.L > 16) P = P * 16 / p.L;    // long windows: keep a ring slot at <= 40 KB so that two CTAs share an SM
   if (P < 1) P = 1;
   if (P > p.hw) P = p.hw;
-  const bool pe_regs_geom = p.L <= 16 && ((P * p.T + 31) / 32) * 32 <= 192;
   p.P = P;
   const int threads = ((P * p.T + 31) / 32) * 32;
   p.scale = 1.0f / sqrtf((float)(p.C / p.heads));
   const int slot_bytes = (int)((size_t)P * p.L * p.C * sizeof(__half));
   const size_t fixed = ((size_t)P * p.L * p.T + (size_t)P * p.heads * p.L + KV_MAX_L) * sizeof(float) +
                        KV_MAX_L * sizeof(int) + KV_MAX_SLOTS * sizeof(uint64_t) + 128;
-  // general-window variant: two CTAs per SM when two ring slots of each fit in half the shared memory
-  const size_t budget = (!pe_regs_geom && 2 * (size_t)slot_bytes + fixed <= 110 * 1024) ? 110 * 1024 : 200 * 1024;
-  int n_slots = (int)((budget - fixed) / (size_t)slot_bytes);
+  int n_slots = (int)((200 * 1024 - fixed) / (size_t)slot_bytes);
   if (n_slots > KV_MAX_SLOTS) n_slots = KV_MAX_SLOTS;
   if (n_slots < 2) return fail(L2D_ERR_INVALID, "kv_attn: window L*C too large for the shared-memory ring");
   const size_t smem = (size_t)n_slots * slot_bytes + fixed;
-  const bool pe_regs = pe_regs_geom;
-  const int ctas_per_sm = (!pe_regs && budget == 110 * 1024) ? 2 : 1;
+  const bool pe_regs = p.L <= 16 && threads <= 192;
   static size_t configured[2] = {0, 0};
   if (smem > configured[pe_regs]) {
     if (pe_regs)
@@ -319,7 +312,7 @@ int kv_attn_launch(const KvAttnParams& p0, cudaStream_t stream) {
   }
   const int tiles_per_row = ceil_div(p.hw, P);
   const int total = tiles_per_row * p.n_rows;
-  const int grid = total < ctas_per_sm * g_num_sms ? total : ctas_per_sm * g_num_sms;
+  const int grid = total < g_num_sms ? total : g_num_sms;
   if (pe_regs)
     launch_pdl_if(p.pdl != 0, kv_attn_kernel<true>, dim3(grid), dim3(threads), smem, stream, p, n_slots, slot_bytes, tiles_per_row);
   else

@@ -14,6 +14,12 @@
 // into P pixel groups of W = 8/P warps that only synchronise among themselves (named barriers), so groups drift apart
 // and overlap each other's latencies.  The freshly projected k/v/q of the next tile are prefetched into registers.
 // Precondition (as in the reference, whose cache is zero-initialised): masked slots hold finite values.
+//
+// Window L == 32 (BASELINE config 4, LB = 2): a pixel's 32 slots are two consecutive 16-row blocks of the same matrix, so
+// a tile holds "half-pixels" -- pixel group pl works on block kb = pl % 2 of real pixel pl / 2 with the L == 16 code path
+// unchanged (own K/V rows, own PE-window block, own 16 mask bits); the two groups of a pixel meet twice per tile on a
+// named barrier to exchange the per-head max and sum of their halves (so P is the softmax over all 32 slots), park their
+// partial O^T in their own V windows, and split the gather of the summed output row between them.
 #include <cuda.h>
 
 #include "ops.cuh"
@@ -138,9 +144,10 @@ __device__ __forceinline__ uint32_t km_frag_off(const KmFrag& f, int i, int R) {
 // bytes only this warp reads and has already consumed for that very k-step; swizzled like the window, so the writes and
 // the gather are conflict-free.  The K plane is therefore free right after the scores and is released early.
 // CT/PT: compile-time C and pixels per tile (0 = run-time geometry, any C <= 640); NB: plane buffers in the ring.
-template <int CT, int PT, int NB>
+template <int CT, int PT, int NB, int LB = 1>
 __global__ void __launch_bounds__(KM_THREADS, 1)
 kv_attn_mma_kernel(const __grid_constant__ CUtensorMap tmap, const KvAttnParams p, const int tiles_per_row, long long* dbg) {
+  static_assert(LB == 1 || (CT != 0 && PT % 2 == 0), "the 32-slot path exists for the specialised geometries only");
   extern __shared__ __align__(1024) uint8_t km_smem_raw[];
   // align by pointer arithmetic (an integer round trip would turn every later access into a generic LD/ST)
   uint8_t* smem = km_smem_raw + ((1024u - (km_smem_u32(km_smem_raw) & 1023u)) & 1023u);
@@ -151,17 +158,21 @@ kv_attn_mma_kernel(const __grid_constant__ CUtensorMap tmap, const KvAttnParams 
   const int W = 8 / P, R = P * KM_L, T = C >> 3, ncb = C >> 6, nks = C >> 4;
   const uint32_t plane_bytes = (uint32_t)ncb * R * 128;          // K (or V) rows of one tile
   const uint32_t pe_plane = (uint32_t)ncb * KM_L * 128;          // one [16 x C] PE window
+  const int hwp = p.hw * LB;                                     // (half-)pixels per row: the unit tiles are made of
+  const int LW = KM_L * LB;                                      // window length
   uint8_t* ring = smem;
-  uint8_t* pek = ring + (size_t)NB * plane_bytes;                // K_pe[pi[j]] window of the current row n
-  uint8_t* pev = pek + pe_plane;
-  __half* s_q = reinterpret_cast<__half*>(pev + pe_plane);       // [P][C]  q + Q_pe
+  uint8_t* pek = ring + (size_t)NB * plane_bytes;                // K_pe[pi[j]] windows of the current row n: LB blocks of [16 x C]
+  uint8_t* pev = pek + LB * pe_plane;
+  __half* s_q = reinterpret_cast<__half*>(pev + LB * pe_plane);  // [P][C]  q + Q_pe
   __half* s_qpe = s_q + (size_t)P * C;                           // [C]     Q_pe[pi[u]] of the current row n
   __half* s_vn = s_qpe + C;                                      // [2][P][C] freshly projected v of this / the next tile
   float* s_part = reinterpret_cast<float*>(s_vn + (size_t)2 * P * C);   // [8 warps][32 lanes][4] partial scores
-  float* s_mask = s_part + 8 * 32 * 4;                           // [16]
-  int* s_pi = reinterpret_cast<int*>(s_mask + KM_L);             // [16]
-  int* s_misc = s_pi + KM_L;                                     // [0] = write slot u of the current row n
-  uint64_t* bars = reinterpret_cast<uint64_t*>(s_misc + 4);      // full[NB], empty[NB], go
+  float* s_mask = s_part + 8 * 32 * 4;                           // [32]
+  int* s_pi = reinterpret_cast<int*>(s_mask + 2 * KM_L);         // [32]
+  int* s_misc = s_pi + 2 * KM_L;                                 // [0] = write slot u of the current row n
+  float* s_xm = reinterpret_cast<float*>(s_misc + 4);            // [8 groups][8 heads] half-window max  (LB == 2)
+  float* s_xs = s_xm + 64;                                       // [8][8] half-window sum
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_xs + 64);       // full[NB], empty[NB], go
   uint8_t* s_head = reinterpret_cast<uint8_t*>(bars + 2 * NB + 1);   // [T] head of each 8-channel chunk
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -170,11 +181,14 @@ kv_attn_mma_kernel(const __grid_constant__ CUtensorMap tmap, const KvAttnParams 
     d_entry = clock64();
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(d_gt0));
   }
-  const int total_tiles = tiles_per_row * p.n_rows;
+  const int S = p.c_slices;                                       // channel slices: "virtual row" nv = n * S + slice
+  const int CF = p.c_full;                                       // row pitch (channels) of the cache / q / k / v / out rows
+  const int nrv = p.n_rows * S;
+  const int total_tiles = tiles_per_row * nrv;
   // contiguous tile range per CTA; when the grid divides into the rows no CTA straddles a row change (one PE staging)
   int t_begin, t_end;
-  if ((int)gridDim.x % p.n_rows == 0) {
-    const int cpr = (int)gridDim.x / p.n_rows, n0 = (int)blockIdx.x / cpr, r0 = (int)blockIdx.x - n0 * cpr;
+  if ((int)gridDim.x % nrv == 0) {
+    const int cpr = (int)gridDim.x / nrv, n0 = (int)blockIdx.x / cpr, r0 = (int)blockIdx.x - n0 * cpr;
     t_begin = n0 * tiles_per_row + (int)(((long long)tiles_per_row * r0) / cpr);
     t_end = n0 * tiles_per_row + (int)(((long long)tiles_per_row * (r0 + 1)) / cpr);
   } else {
@@ -190,10 +204,10 @@ kv_attn_mma_kernel(const __grid_constant__ CUtensorMap tmap, const KvAttnParams 
   // the first row's schedule is requested at kernel entry so its latency hides behind the prologue
   int e_pi = 0, e_u = 0;
   float e_mask = 0.f;
-  if (tid < KM_L && my_tiles > 0) {
-    const int n0 = t_begin / tiles_per_row;
-    e_pi = static_cast<int>(p.pe_idx[(size_t)n0 * KM_L + tid]);
-    e_mask = __half2float(p.mask[(size_t)n0 * KM_L + tid]);
+  if (tid < LW && my_tiles > 0) {
+    const int n0 = (t_begin / tiles_per_row) / S;
+    e_pi = static_cast<int>(p.pe_idx[(size_t)n0 * LW + tid]);
+    e_mask = __half2float(p.mask[(size_t)n0 * LW + tid]);
     e_u = static_cast<int>(p.update_idx[n0]);
   }
   pdl_launch();
@@ -219,10 +233,12 @@ kv_attn_mma_kernel(const __grid_constant__ CUtensorMap tmap, const KvAttnParams 
       // the first burst (NB planes from every SM) would put ~20 MB in front of the math warps' small dependent loads
       // (index tensors -> PE rows): let those be queued first
       km_mbar_wait(go_bar, 0);
+      int plane_col = 0;                                         // first channel of the tile's slice
       auto plane_row = [&](int s) {
         const int tile = t_begin + (s >> 1);
-        const int n = tile / tiles_per_row, p0 = (tile - n * tiles_per_row) * P;
-        return ((n * 2 + (s & 1)) * p.hw + p0) * KM_L;
+        const int nv = tile / tiles_per_row, p0 = (tile - nv * tiles_per_row) * P;
+        plane_col = (nv % S) * C;
+        return (((nv / S) * 2 + (s & 1)) * hwp + p0) * KM_L;
       };
       for (int s = 0; s < planes; ++s) {
         const int b = s % NB, use = s / NB;
@@ -230,7 +246,7 @@ kv_attn_mma_kernel(const __grid_constant__ CUtensorMap tmap, const KvAttnParams 
         const int row0 = plane_row(s);
         km_mbar_expect_tx(full_bar(b), plane_bytes);
         const uint32_t dst = km_smem_u32(ring + (size_t)b * plane_bytes);
-        for (int b2 = 0; b2 < ncb; ++b2) km_tma_2d(dst + b2 * (R * 128), &tmap, full_bar(b), b2 * 64, row0);
+        for (int b2 = 0; b2 < ncb; ++b2) km_tma_2d(dst + b2 * (R * 128), &tmap, full_bar(b), plane_col + b2 * 64, row0);
       }
     }
     return;
@@ -240,6 +256,8 @@ kv_attn_mma_kernel(const __grid_constant__ CUtensorMap tmap, const KvAttnParams 
   const int pl = warp / W, sub = warp - pl * W;
   const int GT = W * 32;                                         // threads of a pixel group
   const int gbar = 1 + pl;                                       // the group's named barrier
+  const int kb = LB == 2 ? (pl & 1) : 0;                         // which 16-slot block of the pixel's window this group owns
+  const int pbar = 9 + (pl >> 1);                                // LB == 2: named barrier of the two groups of one pixel
   const int cg = sub * 32 + lane;                                // the 16-byte chunk this thread appends / stages
   const bool has_chunk = cg < T;
   const int g = lane >> 2, t = lane & 3, mi = lane >> 3, r8 = lane & 7;
@@ -276,17 +294,19 @@ kv_attn_mma_kernel(const __grid_constant__ CUtensorMap tmap, const KvAttnParams 
   // k/v/q chunk of the NEXT tile, requested one tile ahead
   uint4 pf_k = make_uint4(0, 0, 0, 0), pf_q = pf_k;
   // pixel row of this group in tile `tile2` (-1: past the ragged end of a row); no division when P divides hw
-  const bool flat = (p.hw % P) == 0;
-  auto pixel_row = [&](int tile2) -> long long {
-    if (flat) return (long long)tile2 * P + pl;
+  const bool flat = S == 1 && (hwp % P) == 0;
+  auto pixel_row = [&](int tile2) -> long long {   // row of this group's REAL pixel in q / k_new / v_new / out
+    if (flat) return ((long long)tile2 * P + pl) / LB;
     const int n2 = tile2 / tiles_per_row, q0 = (tile2 - n2 * tiles_per_row) * P;
-    return q0 + pl < p.hw ? (long long)n2 * p.hw + q0 + pl : -1;
+    return q0 + pl < hwp ? (long long)(n2 / S) * p.hw + (q0 + pl) / LB : -1;
   };
+  auto slice_col = [&](int tile2) -> size_t { return (size_t)((tile2 / tiles_per_row) % S) * C; };
   auto load_kq = [&](int tile2) {
     const long long row = pixel_row(tile2);
     if (has_chunk && row >= 0) {
-      pf_k = ldg_act(p.k_new + (size_t)row * p.ld + (size_t)cg * 8);
-      pf_q = ldg_act(p.q + (size_t)row * p.ld + (size_t)cg * 8);
+      const size_t col = (S > 1 ? slice_col(tile2) : 0) + (size_t)cg * 8;
+      pf_k = ldg_act(p.k_new + (size_t)row * p.ld + col);
+      pf_q = ldg_act(p.q + (size_t)row * p.ld + col);
     }
   };
   // v is needed half a tile later than k / q and would pin four more registers for a whole tile: it is staged through
@@ -294,7 +314,8 @@ kv_attn_mma_kernel(const __grid_constant__ CUtensorMap tmap, const KvAttnParams 
   auto load_v = [&](int tile2, int buf) {
     const long long row = tile2 < t_end ? pixel_row(tile2) : -1;
     if (has_chunk && row >= 0) {
-      km_cp_async16(km_smem_u32(s_vn + ((size_t)buf * P + pl) * C + (size_t)cg * 8), p.v_new + (size_t)row * p.ld + (size_t)cg * 8);
+      km_cp_async16(km_smem_u32(s_vn + ((size_t)buf * P + pl) * C + (size_t)cg * 8),
+                    p.v_new + (size_t)row * p.ld + (S > 1 ? slice_col(tile2) : 0) + (size_t)cg * 8);
     }
     asm volatile("cp.async.commit_group;" ::: "memory");   // one group per tile, also when empty: wait_group 1 below counts them
   };
@@ -304,12 +325,14 @@ kv_attn_mma_kernel(const __grid_constant__ CUtensorMap tmap, const KvAttnParams 
   // per-row schedule + PE windows (block-uniform; all 8 math warps): Q_pe row and the K_pe / V_pe windows by cp.async
   int cur_n = -1;
   bool pe_pending = false;
-  auto stage_row = [&](int n) {
+  auto stage_row = [&](int nv) {                             // nv = virtual row: (denoise row n, channel slice)
+    const int n = nv / S;
+    const size_t coff = (size_t)(nv % S) * C;
     if (cur_n >= 0) km_bar(15, 256);                         // every group is done with the previous row's windows
-    if (tid < KM_L) {
+    if (tid < LW) {
       if (cur_n >= 0) {
-        e_pi = static_cast<int>(p.pe_idx[(size_t)n * KM_L + tid]);
-        e_mask = __half2float(p.mask[(size_t)n * KM_L + tid]);
+        e_pi = static_cast<int>(p.pe_idx[(size_t)n * LW + tid]);
+        e_mask = __half2float(p.mask[(size_t)n * LW + tid]);
         e_u = static_cast<int>(p.update_idx[n]);
       }
       s_pi[tid] = e_pi;
@@ -320,32 +343,37 @@ kv_attn_mma_kernel(const __grid_constant__ CUtensorMap tmap, const KvAttnParams 
     // window slot j <- table row pe_idx[n][j], copied asynchronously (no registers, no wait here): the copies are
     // queued ahead of the producer's first burst and land while the first K plane is in flight
     const int u0 = s_misc[0];
-    for (int idx = tid; idx < KM_L * T; idx += 256) {
+    for (int idx = tid; idx < LW * T; idx += 256) {
       const int j = idx / T, c = idx - j * T;
-      const uint32_t off = km_off(j, c, KM_L);
-      km_cp_async16(km_smem_u32(pek + off), p.k_pe + (size_t)s_pi[j] * p.pe_ld + (size_t)c * 8);
-      km_cp_async16(km_smem_u32(pev + off), p.v_pe + (size_t)s_pi[j] * p.pe_ld + (size_t)c * 8);
+      const uint32_t off = (uint32_t)(j >> 4) * pe_plane + km_off(j & 15, c, KM_L);   // block j / 16, slot j % 16
+      km_cp_async16(km_smem_u32(pek + off), p.k_pe + (size_t)s_pi[j] * p.pe_ld + coff + (size_t)c * 8);
+      km_cp_async16(km_smem_u32(pev + off), p.v_pe + (size_t)s_pi[j] * p.pe_ld + coff + (size_t)c * 8);
     }
     for (int c = tid; c < T; c += 256)
-      km_cp_async16(km_smem_u32(s_qpe + (size_t)c * 8), p.q_pe + (size_t)s_pi[u0] * p.pe_ld + (size_t)c * 8);
+      km_cp_async16(km_smem_u32(s_qpe + (size_t)c * 8), p.q_pe + (size_t)s_pi[u0] * p.pe_ld + coff + (size_t)c * 8);
     asm volatile("cp.async.commit_group;" ::: "memory");
     if (cur_n < 0) {
       __syncwarp();
       if (lane == 0) km_mbar_arrive(go_bar);
     }
     pe_pending = true;
-    cur_n = n;
+    cur_n = nv;
   };
   stage_row(t_begin / tiles_per_row);   // first row: queued before the PDL wait (and ahead of the producer's first burst)
   pdl_wait();
   load_kq(t_begin);
   load_v(t_begin, 0);
 
-  // gather addresses of this thread's (up to 3) channel pairs inside the V plane, incl. the head column: fixed per kernel
+  // gather addresses of this thread's (up to 3) channel pairs inside the V plane, incl. the head column: fixed per kernel.
+  // LB == 2: the 2*GT threads of a pixel's two groups share the row; every thread adds the two groups' partial O^T, which
+  // sit at the same swizzled offset of their windows, 16 rows (2 KB) apart
+  const int cgx = LB == 2 ? kb * GT + cg : cg;
+  const int GS = LB * GT;
+  const int partner = LB == 2 ? ((pl & 1) ? -16 * 128 : 16 * 128) : 0;
   uint32_t g_lo[3], g_hi[3];
 #pragma unroll
   for (int m = 0; m < 3; ++m) {
-    const int c = 2 * (cg + GT * m);
+    const int c = 2 * (cgx + GS * m);
     g_lo[m] = g_hi[m] = 0xffffffffu;
     if (c < C) {
       const int hb = 2 * (int)s_head[c >> 3], row = pl * KM_L + (c & 15), ch = 2 * (c >> 4);
@@ -366,10 +394,14 @@ kv_attn_mma_kernel(const __grid_constant__ CUtensorMap tmap, const KvAttnParams 
   const long long d_loop0 = tl ? clock64() : 0;
   for (int i = 0; i < my_tiles; ++i) {
     const int tile = t_begin + i;
-    const int n = tile / tiles_per_row, p0 = (tile - n * tiles_per_row) * P;
-    const bool active = p0 + pl < p.hw;
-    if (n != cur_n) stage_row(n);
-    const int u = s_misc[0];
+    const int nv = tile / tiles_per_row, p0 = (tile - nv * tiles_per_row) * P;
+    const int n = nv / S;
+    const size_t coff = (size_t)(nv % S) * C;                // first channel of this tile's slice
+    const bool active = p0 + pl < hwp;
+    if (nv != cur_n) stage_row(nv);
+    const int u_full = s_misc[0];
+    const int u = u_full & (KM_L - 1);                      // slot inside this group's 16-slot block
+    const bool owner = LB == 1 || (u_full >> 4) == kb;      // the group whose block receives the appended k / v
     const int sK = 2 * i, sV = 2 * i + 1;
     const int bK = sK % NB, bV = sV % NB;
     uint8_t* kplane = ring + (size_t)bK * plane_bytes;
@@ -385,9 +417,11 @@ kv_attn_mma_kernel(const __grid_constant__ CUtensorMap tmap, const KvAttnParams 
     if (active) {
       // ---- K append (HBM + window patch) and q~ staging: thread <-> one 16-byte chunk of the group's pixel ----
       if (has_chunk) {
-        __half* kdst = p.cache + ((((size_t)n * 2) * p.hw + p0 + pl) * KM_L + u) * C + (size_t)cg * 8;
-        *reinterpret_cast<uint4*>(kdst) = pf_k;                                              // PE-free append (:117-119)
-        *reinterpret_cast<uint4*>(kplane + km_off(pl * KM_L + u, cg, R)) = pf_k;             // the window sees the new slot
+        if (owner) {
+          __half* kdst = p.cache + ((((size_t)n * 2) * hwp + p0 + pl) * KM_L + u) * CF + coff + (size_t)cg * 8;
+          *reinterpret_cast<uint4*>(kdst) = pf_k;                                            // PE-free append (:117-119)
+          *reinterpret_cast<uint4*>(kplane + km_off(pl * KM_L + u, cg, R)) = pf_k;           // the window sees the new slot
+        }
         *reinterpret_cast<uint4*>(s_q + (size_t)pl * C + (size_t)cg * 8) =
             hadd8(pf_q, *reinterpret_cast<const uint4*>(s_qpe + (size_t)cg * 8));            // q + Q_pe[pi[u]] -> fp16
       }
@@ -399,12 +433,12 @@ kv_attn_mma_kernel(const __grid_constant__ CUtensorMap tmap, const KvAttnParams 
       // ---- scores: rows = slots, columns = heads; two accumulators halve the dependent mma chain ----
       float acc[4] = {0.f, 0.f, 0.f, 0.f}, acc2[4] = {0.f, 0.f, 0.f, 0.f};
       {
-        const uint32_t kb = km_smem_u32(kplane), pkb = km_smem_u32(pek);
+        const uint32_t kbase = km_smem_u32(kplane), pkb = km_smem_u32(pek) + (uint32_t)kb * pe_plane;
         const __half* qrow = s_q + (size_t)pl * C + sub * 16 + 2 * t;
         auto qk_step = [&](int ii, uint32_t koff, uint32_t pkoff, uint32_t m0, uint32_t m1, float (&dst)[4]) {
           uint32_t a[4], pe[4];
           // matrices: (slots 0-7, ch 0-7) (slots 8-15, ch 0-7) (slots 0-7, ch 8-15) (slots 8-15, ch 8-15)
-          km_ldsm(kb + koff, a);
+          km_ldsm(kbase + koff, a);
           km_ldsm(pkb + pkoff, pe);
 #pragma unroll
           for (int r = 0; r < 4; ++r) a[r] = km_hadd2(a[r], pe[r]);             // K + K_pe -> fp16
@@ -438,9 +472,9 @@ kv_attn_mma_kernel(const __grid_constant__ CUtensorMap tmap, const KvAttnParams 
       // ---- V append + patch (the V plane was requested one plane after K), then the group meets ----
       km_mbar_wait(full_bar(bV), (uint32_t)(sV / NB) & 1u);
       asm volatile("cp.async.wait_group 1;" ::: "memory");          // this tile's v (the next tile's may be in flight)
-      if (has_chunk) {
+      if (has_chunk && owner) {
         const uint4 pf_v = *reinterpret_cast<const uint4*>(s_vn + ((size_t)(i & 1) * P + pl) * C + (size_t)cg * 8);
-        __half* vdst = p.cache + ((((size_t)n * 2 + 1) * p.hw + p0 + pl) * KM_L + u) * C + (size_t)cg * 8;
+        __half* vdst = p.cache + ((((size_t)n * 2 + 1) * hwp + p0 + pl) * KM_L + u) * CF + coff + (size_t)cg * 8;
         *reinterpret_cast<uint4*>(vdst) = pf_v;
         *reinterpret_cast<uint4*>(vplane + km_off(pl * KM_L + u, cg, R)) = pf_v;
       }
@@ -457,7 +491,7 @@ kv_attn_mma_kernel(const __grid_constant__ CUtensorMap tmap, const KvAttnParams 
         }
       }
       // lane (g, t): acc[0] = S[slot g][head 2t], acc[1] = S[g][2t+1], acc[2] = S[g+8][2t], acc[3] = S[g+8][2t+1]
-      const float m_lo = s_mask[g], m_hi = s_mask[g + 8];
+      const float m_lo = s_mask[kb * KM_L + g], m_hi = s_mask[kb * KM_L + g + 8];
       float s0 = fmaf(acc[0], p.scale, m_lo), s1 = fmaf(acc[1], p.scale, m_lo);
       float s2 = fmaf(acc[2], p.scale, m_hi), s3 = fmaf(acc[3], p.scale, m_hi);
       float mxa = fmaxf(s0, s2), mxb = fmaxf(s1, s3);                        // heads 2t and 2t+1
@@ -465,6 +499,15 @@ kv_attn_mma_kernel(const __grid_constant__ CUtensorMap tmap, const KvAttnParams 
       for (int o = 4; o <= 16; o <<= 1) {                                    // reduce over g (the slots)
         mxa = fmaxf(mxa, __shfl_xor_sync(0xffffffffu, mxa, o));
         mxb = fmaxf(mxb, __shfl_xor_sync(0xffffffffu, mxb, o));
+      }
+      if constexpr (LB == 2) {   // the other half of the window: exchange the per-head max with the partner group
+        if (sub == 0 && g == 0) {
+          s_xm[pl * 8 + 2 * t] = mxa;
+          s_xm[pl * 8 + 2 * t + 1] = mxb;
+        }
+        km_bar(pbar, 2 * GT);
+        mxa = fmaxf(mxa, s_xm[(pl ^ 1) * 8 + 2 * t]);
+        mxb = fmaxf(mxb, s_xm[(pl ^ 1) * 8 + 2 * t + 1]);
       }
       s0 = __expf(s0 - mxa); s2 = __expf(s2 - mxa);
       s1 = __expf(s1 - mxb); s3 = __expf(s3 - mxb);
@@ -474,7 +517,16 @@ kv_attn_mma_kernel(const __grid_constant__ CUtensorMap tmap, const KvAttnParams 
         suma += __shfl_xor_sync(0xffffffffu, suma, o);
         sumb += __shfl_xor_sync(0xffffffffu, sumb, o);
       }
-      const float inva = __frcp_rn(suma), invb = __frcp_rn(sumb);            // sums are in [1, 16]
+      if constexpr (LB == 2) {   // ... and the per-head sum: P is the softmax over all 32 slots
+        if (sub == 0 && g == 0) {
+          s_xs[pl * 8 + 2 * t] = suma;
+          s_xs[pl * 8 + 2 * t + 1] = sumb;
+        }
+        km_bar(pbar, 2 * GT);
+        suma += s_xs[(pl ^ 1) * 8 + 2 * t];
+        sumb += s_xs[(pl ^ 1) * 8 + 2 * t + 1];
+      }
+      const float inva = __frcp_rn(suma), invb = __frcp_rn(sumb);            // sums are in [1, 32]
       const float pr0 = s0 * inva, pr1 = s1 * invb, pr2 = s2 * inva, pr3 = s3 * invb;   // P[slot g | g+8][head 2t | 2t+1]
       // B = P[16 slots x 8 heads]: lane (g, t) needs head g, slots 2t, 2t+1 (b0) and 2t+8, 2t+9 (b1).
       // P[slot s][head h] lives in lane (s % 8) * 4 + h / 2, register (s / 8) * 2 + h % 2.
@@ -491,7 +543,7 @@ kv_attn_mma_kernel(const __grid_constant__ CUtensorMap tmap, const KvAttnParams 
       // ---- O^T: rows = channels, columns = heads; every lane parks its two head columns of rows g and g + 8 in the
       //      pixel's (dead) K window, the gather below picks column head(c) ----
       {
-        const uint32_t vb = km_smem_u32(vplane), pvb = km_smem_u32(pev);
+        const uint32_t vb = km_smem_u32(vplane), pvb = km_smem_u32(pev) + (uint32_t)kb * pe_plane;
         auto pv_step = [&](uint32_t voff, uint32_t pvoff, uint32_t ooff) {
           uint32_t a[4], pe[4];
           // V~^T tile: matrices (slots 0-7, d 0-7) (slots 0-7, d 8-15) (slots 8-15, d 0-7) (slots 8-15, d 8-15), transposed
@@ -517,17 +569,26 @@ kv_attn_mma_kernel(const __grid_constant__ CUtensorMap tmap, const KvAttnParams 
           }
         }
       }
-      km_bar(gbar, GT);
+      if constexpr (LB == 2) km_bar(pbar, 2 * GT);   // both halves' partial O^T are parked
+      else km_bar(gbar, GT);
       stamp(d_pv);
       // ---- gather column head(c) of O^T and store the pixel's output row (two channels per thread) ----
       {
-        __half* orow = p.out + ((size_t)n * p.hw + p0 + pl) * C;
+        __half* orow = p.out + ((size_t)n * p.hw + (p0 + pl) / LB) * CF + coff;
 #pragma unroll
         for (int m = 0; m < 3; ++m) {
           if (g_lo[m] != 0xffffffffu) {
-            const uint32_t lo = *reinterpret_cast<const unsigned short*>(vplane + g_lo[m]);
-            const uint32_t hi = *reinterpret_cast<const unsigned short*>(vplane + g_hi[m]);
-            *reinterpret_cast<uint32_t*>(orow + 2 * (cg + GT * m)) = lo | (hi << 16);
+            uint32_t lo = *reinterpret_cast<const unsigned short*>(vplane + g_lo[m]);
+            uint32_t hi = *reinterpret_cast<const unsigned short*>(vplane + g_hi[m]);
+            if constexpr (LB == 2) {   // sum of the two 16-slot halves (fp32 add of the two fp16 partials, one rounding)
+              const __half2 mine = u32_as_h2(lo | (hi << 16));
+              const uint32_t lo2 = *reinterpret_cast<const unsigned short*>(vplane + g_lo[m] + partner);
+              const uint32_t hi2 = *reinterpret_cast<const unsigned short*>(vplane + g_hi[m] + partner);
+              const float2 fa = __half22float2(mine), fb = __half22float2(u32_as_h2(lo2 | (hi2 << 16)));
+              *reinterpret_cast<uint32_t*>(orow + 2 * (cgx + GS * m)) = h2_as_u32(__floats2half2_rn(fa.x + fb.x, fa.y + fb.y));
+            } else {
+              *reinterpret_cast<uint32_t*>(orow + 2 * (cg + GT * m)) = lo | (hi << 16);
+            }
           }
         }
       }
@@ -559,14 +620,14 @@ kv_attn_mma_kernel(const __grid_constant__ CUtensorMap tmap, const KvAttnParams 
 int g_km_sms = 0;
 long long* g_km_dbg = nullptr;
 
-template <int CT, int PT, int NB>
+template <int CT, int PT, int NB, int LB = 1>
 int km_launch(const CUtensorMap& tm, const KvAttnParams& p, int tiles_per_row, int grid, size_t smem, cudaStream_t stream) {
   static size_t configured = 0;
   if (smem > configured) {
-    L2D_CUDA(cudaFuncSetAttribute(kv_attn_mma_kernel<CT, PT, NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    L2D_CUDA(cudaFuncSetAttribute(kv_attn_mma_kernel<CT, PT, NB, LB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = smem;
   }
-  launch_pdl_if(p.pdl != 0 && pdl_family(3), kv_attn_mma_kernel<CT, PT, NB>, dim3(grid), dim3(KM_THREADS), smem, stream, tm, p, tiles_per_row,
+  launch_pdl_if(p.pdl != 0 && pdl_family(3), kv_attn_mma_kernel<CT, PT, NB, LB>, dim3(grid), dim3(KM_THREADS), smem, stream, tm, p, tiles_per_row,
                 g_km_dbg);
   L2D_LAUNCH_CHECK();
   return L2D_OK;
@@ -576,46 +637,80 @@ int km_launch(const CUtensorMap& tm, const KvAttnParams& p, int tiles_per_row, i
 
 void kv_attn_set_debug(long long* ptr) { g_km_dbg = ptr; }
 
+// L2D_K1_SLICE=1 (developer A/B): at L == 16 split C = 1280 rows into two 640-channel slices of one pixel each (more,
+// smaller tiles at the two coarse levels); default off
+static bool k1_slice16() {
+  static const bool on = [] {
+    const char* e = getenv("L2D_K1_SLICE");
+    return e && e[0] == '1';
+  }();
+  return on;
+}
+
 bool kv_attn_mma_supported(const KvAttnParams& p) {
   const int hd = p.heads > 0 ? p.C / p.heads : 0;
-  // C <= 640: ring of 4 x 40 KB planes + the row's two PE windows (<= 40 KB); C = 1280: 3 planes + 80 KB of PE windows.
+  // L == 16: C <= 640: ring of 4 x 40 KB planes + the row's two PE windows (<= 40 KB); C = 1280: 3 planes + 80 KB of PE windows.
+  // L == 32 (two 16-slot blocks per pixel): C = 320 / 640, and C = 1280 as two 640-channel slices of whole heads.
   // Other widths / window lengths take the scalar kernel.
-  return p.L == KM_L && p.C % 64 == 0 && (p.C <= 640 || p.C == 1280) && p.heads >= 1 && p.heads <= 8 &&
-         p.C % p.heads == 0 && hd % 8 == 0 && p.pe_ld % 8 == 0;
+  const bool common = p.C % 64 == 0 && p.heads >= 1 && p.heads <= 8 && p.C % p.heads == 0 && hd % 8 == 0 && p.pe_ld % 8 == 0;
+  if (p.L == KM_L) return common && (p.C <= 640 || p.C == 1280);
+  if (p.L == 2 * KM_L)
+    return common && p.hw >= 2 && (p.C == 320 || p.C == 640 || (p.C == 1280 && p.heads % 2 == 0 && 640 % hd == 0));
+  return false;
 }
 
 int kv_attn_mma_launch(const KvAttnParams& p0, cudaStream_t stream) {
   KvAttnParams p = p0;
   const int hd = p.C / p.heads;
+  const int LB = p.L / KM_L;                 // 16-slot blocks per pixel window
+  const int hwp = p.hw * LB;                 // tiles are made of (half-)pixels of 16 slots
+  const int c_full = p.C;
+  // channel slices: a slice of whole heads is scheduled like a row of its own (own PE windows, own tiles)
+  const bool sliced = p.C == 1280 && p.heads % 2 == 0 && 640 % hd == 0 && (LB == 2 || k1_slice16());
+  if (sliced) {
+    p.C = 640;
+    p.heads /= 2;
+  }
+  p.c_slices = sliced ? 2 : 1;
+  p.c_full = c_full;
   p.T = p.C / 8;
   p.hd8 = hd / 8;
-  int P = 1280 / p.C;                        // 80 KB of K+V per tile: 4 / 2 / 1 pixels at C = 320 / 640 / 1280
+  int P = 1280 / p.C;                        // 80 KB of K+V per tile: 4 / 2 / 1 (half-)pixels at C = 320 / 640 / 1280
   if (P >= 8) P = 8; else if (P >= 4) P = 4; else if (P >= 2) P = 2; else P = 1;   // 8 math warps, 8 / P per pixel
-  while (P > p.hw) P >>= 1;
+  if (sliced && LB == 1) P = 1;              // L == 16 slices: one pixel (40 KB of K+V) per tile
+  while (P > hwp) P >>= 1;
   if (P < 1) P = 1;
   p.P = P;
   p.scale = 1.0f / sqrtf((float)hd);
   const int ncb = p.C / 64;
-  const int NB = p.C == 1280 ? 3 : 4;
+  const int NB = (p.C == 1280 || (LB == 2 && p.C == 640)) ? 3 : 4;
   const size_t plane_bytes = (size_t)ncb * P * KM_L * 128;
-  const size_t smem = NB * plane_bytes + (size_t)2 * ncb * KM_L * 128 + (size_t)P * p.C * sizeof(__half) +
-                      (size_t)p.C * sizeof(__half) + (size_t)2 * P * p.C * sizeof(__half) + 8 * 32 * 16 + KM_L * 8 + 16 + (2 * NB + 1) * 8 + 192 + 1024;
+  const size_t smem = NB * plane_bytes + (size_t)2 * LB * ncb * KM_L * 128 + (size_t)P * p.C * sizeof(__half) +
+                      (size_t)p.C * sizeof(__half) + (size_t)2 * P * p.C * sizeof(__half) + 8 * 32 * 16 + 2 * KM_L * 8 + 16 + 128 * 4 +
+                      (2 * NB + 1) * 8 + 192 + 1024;
   if (smem > 227 * 1024) return fail(L2D_ERR_INVALID, "kv_attn(mma): tile does not fit in shared memory");
   CUtensorMap tm;
-  const int64_t rows = (int64_t)p.n_rows * 2 * p.hw * KM_L;
-  int rc = get_tmap_2d(p.cache, rows, p.C, p.C, P * KM_L, &tm);
+  const int64_t rows = (int64_t)p.n_rows * 2 * hwp * KM_L;
+  int rc = get_tmap_2d(p.cache, rows, c_full, c_full, P * KM_L, &tm);
   if (rc != L2D_OK) return rc;
   if (g_km_sms == 0) {
     int dev = 0;
     L2D_CUDA(cudaGetDevice(&dev));
     L2D_CUDA(cudaDeviceGetAttribute(&g_km_sms, cudaDevAttrMultiProcessorCount, dev));
   }
-  const int tiles_per_row = ceil_div(p.hw, P);
-  const int total = tiles_per_row * p.n_rows;
+  const int tiles_per_row = ceil_div(hwp, P);
+  const int nrv = p.n_rows * p.c_slices;
+  const int total = tiles_per_row * nrv;
   int grid = total < g_km_sms ? total : g_km_sms;
-  if (grid >= p.n_rows) grid -= grid % p.n_rows;                // whole CTAs per row: no CTA stages two rows' PE windows
+  if (grid >= nrv) grid -= grid % nrv;                          // whole CTAs per (row, slice): no CTA stages two sets of PE windows
+  if (LB == 2) {
+    if (p.C == 320 && P == 4) return km_launch<320, 4, 4, 2>(tm, p, tiles_per_row, grid, smem, stream);
+    if (p.C == 640 && P == 2) return km_launch<640, 2, 3, 2>(tm, p, tiles_per_row, grid, smem, stream);
+    return fail(L2D_ERR_INVALID, "kv_attn(mma): unsupported 32-slot geometry");
+  }
   if (p.C == 320 && P == 4) return km_launch<320, 4, 4>(tm, p, tiles_per_row, grid, smem, stream);
   if (p.C == 640 && P == 2) return km_launch<640, 2, 4>(tm, p, tiles_per_row, grid, smem, stream);
+  if (p.C == 640 && P == 1 && sliced) return km_launch<640, 1, 4>(tm, p, tiles_per_row, grid, smem, stream);
   if (p.C == 1280 && P == 1) return km_launch<1280, 1, 3>(tm, p, tiles_per_row, grid, smem, stream);
   if (p.C > 640) return fail(L2D_ERR_INVALID, "kv_attn(mma): unsupported geometry");
   return km_launch<0, 0, 4>(tm, p, tiles_per_row, grid, smem, stream);

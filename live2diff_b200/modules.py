@@ -157,6 +157,11 @@ class B200TemporalTransformer3DModel(nn.Module):
         self.enable_streaming = True
         self._handle = None
         self._handle_key = None
+        self._param_list = None
+
+    def _apply(self, fn, *args, **kwargs):       # .to() / .half() / .cuda() replace the parameter tensors
+        self._param_list = None
+        return super()._apply(fn, *args, **kwargs)
 
     def __del__(self):
         self._free()
@@ -167,10 +172,16 @@ class B200TemporalTransformer3DModel(nn.Module):
             self._handle = None
 
     def _native(self, n_rows, h, w):
-        sd = {k: v for k, v in self.state_dict().items() if not k.endswith(("q_pe", "k_pe", "v_pe"))}
-        key = (n_rows, h, w) + tuple((v._version, v.data_ptr()) for v in self.parameters())
+        # the key walks the cached parameter list only (no state_dict() per forward): the native object is rebuilt when the
+        # geometry changes or a parameter was replaced (.to()/.half()/load_state_dict change data_ptr or bump _version)
+        if self._param_list is None:
+            self._param_list = list(self.parameters())
+        key = (n_rows, h, w) + tuple((v._version, v.data_ptr()) for v in self._param_list)
         if self._handle is None or key != self._handle_key:
             self._free()
+            self._param_list = list(self.parameters())
+            key = (n_rows, h, w) + tuple((v._version, v.data_ptr()) for v in self._param_list)
+            sd = {k: v for k, v in self.state_dict().items() if not k.endswith(("q_pe", "k_pe", "v_pe"))}
             window = self.transformer_blocks[0].attention_blocks[0].window_size
             named = {k: v.detach().contiguous() for k, v in sd.items()}
             for k, v in named.items():

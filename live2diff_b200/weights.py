@@ -3,7 +3,7 @@
 The names are the reference's `state_dict` keys (UNet3DConditionStreamingModel,
 live2diff/animatediff/models/unet_depth_streaming.py:88-250 and the block/module constructors it
 calls), so a reference checkpoint can be handed to `B200UNetStep` unchanged; the native engine
-looks tensors up by these names (csrc/unet_engine.cu).  `tests/test_weights_spec.py` checks
+looks tensors up by these names (csrc/engine.cu).  `tests/test_oracle_golden.py` checks
 the inventory against the key/shape list dumped from the reference model itself
 (tests/golden/state_dict_spec_*.json).
 

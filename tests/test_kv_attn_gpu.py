@@ -67,7 +67,8 @@ def _random_case(n, hw, L, c, seed, steady=True):
 
 
 @pytest.mark.parametrize("n,hw,L,c,heads", [(2, 4096, 16, 320, 8), (2, 1024, 16, 640, 8), (2, 256, 16, 1280, 8),
-                                            (2, 64, 16, 1280, 8), (4, 1024, 32, 640, 8), (1, 4096, 4, 320, 8)])
+                                            (2, 64, 16, 1280, 8), (4, 1024, 32, 640, 8), (1, 4096, 4, 320, 8),
+                                            (4, 4096, 32, 320, 8), (4, 256, 32, 1280, 8), (4, 64, 32, 1280, 8)])
 def test_kv_attn_full_size_vs_oracle(n, hw, L, c, heads):
     """BASELINE.json sizes (configs 1, 2, 4): steady state, all slots valid."""
     from live2diff_b200 import ops
@@ -80,6 +81,32 @@ def test_kv_attn_full_size_vs_oracle(n, hw, L, c, heads):
     ref16 = O.kv_cache_attention(q, k, v, cache_ref16, pe[0], pe[1], pe[2], mask, pi, up, heads)
     referee(out, ref32, ref16, f"kv_attn N{n} hw{hw} L{L} C{c}")
     assert torch.equal(cache, cache_ref16), "cache append must be bit-exact"
+
+
+@pytest.mark.parametrize("c,hw", [(320, 67), (640, 33), (320, 1)])
+def test_kv_attn_window32_through_fill_and_wrap(c, hw):
+    """Window 32 on the tensor-core path (two 16-slot blocks per pixel, softmax exchanged between the two pixel groups):
+    every frame from the initial schedule (9 valid slots: the second block fully masked) through the fill phase, the
+    block boundary (write slot 15 -> 16) and the first wrap of the ring, incl. ragged tiles (odd hw) -- against the oracle
+    on a cache both sides advance in lock-step; the append must stay bit-exact."""
+    from live2diff_b200 import ops
+
+    n, L, heads, W0 = 4, 32, 8, 8
+    gen = torch.Generator().manual_seed(c + hw)
+    mk = lambda *s: torch.randn(*s, generator=gen).half().to(DEV)
+    cache = torch.zeros(n, 2, hw, L, c, dtype=torch.float16, device=DEV)
+    cache[:, :, :, :W0] = mk(n, 2, hw, W0, c)
+    cache32, cache16 = cache.float(), cache.clone()
+    pe = [mk(L, c) * 0.5 for _ in range(3)]
+    for f, (ab, pi, up) in enumerate(frames(n, L, W0, 30)):
+        q, k, v = mk(n, hw, c), mk(n, hw, c), mk(n, hw, c)
+        mask, pi, up = ab.half().to(DEV), pi.to(DEV), up.to(DEV)
+        out = ops.kv_attn(q, k, v, cache, pe[0], pe[1], pe[2], mask, pi, up, heads)
+        ref32 = O.kv_cache_attention(q.float(), k.float(), v.float(), cache32, pe[0].float(), pe[1].float(), pe[2].float(),
+                                     mask.float(), pi, up, heads)
+        ref16 = O.kv_cache_attention(q, k, v, cache16, pe[0], pe[1], pe[2], mask, pi, up, heads)
+        referee(out, ref32, ref16, f"kv_attn L32 C{c} hw{hw} frame {f}")
+        assert torch.equal(cache, cache16), f"frame {f}: cache append must be bit-exact"
 
 
 def test_kv_attn_append_properties():
