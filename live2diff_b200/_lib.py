@@ -11,7 +11,10 @@ import os
 from typing import Optional
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libl2d_b200.so")
+# L2D_LIB_OVERRIDE (developer A/B runs, profiles/ab_build.py): load another build of the library -- its source hash is then
+# not compared with the tree, and a line on stderr says so
+_OVERRIDE = os.environ.get("L2D_LIB_OVERRIDE")
+LIB_PATH = _OVERRIDE or os.path.join(_HERE, "libl2d_b200.so")
 
 vp, i64, i32, f32, u64 = C.c_void_p, C.c_int64, C.c_int, C.c_float, C.c_uint64
 
@@ -127,6 +130,11 @@ def lib() -> C.CDLL:
         except Exception:
             want = None
         got = handle.l2d_build_hash().decode()
+        if _OVERRIDE:
+            import sys
+
+            print(f"[live2diff_b200] L2D_LIB_OVERRIDE: using {LIB_PATH} (build {got[:12]}); source-hash check skipped", file=sys.stderr)
+            want = None
         if want is not None and got != want:
             raise RuntimeError(f"libl2d_b200.so was built from other sources (hash {got[:12]} != tree {want[:12]}): "
                                "rebuild with python live2diff_b200/csrc/build.py")

@@ -23,6 +23,7 @@
 #include <cuda.h>
 
 #include <cstdio>
+#include <type_traits>
 
 #include "ops.cuh"
 
@@ -337,28 +338,66 @@ flash_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
       ft_mbar_wait(s_full(t, a), (uint32_t)(j / SBUF) & 1u);
       ft_tc_fence_after();
       const uint32_t s_addr = t_lane + tm_s(t, a);
-      // ---- pass 1: row max of the raw scores (two 32-column loads in flight) ----
-      float mx = -INFINITY;
+      // Both passes exist twice: the full-tile version has NO per-element bounds checks (they doubled the instruction
+      // count of the hot loop when they were predicated in), the masked one runs for the last key tile only.
+      float mx = -INFINITY, corr = 0.f, mneg = 0.f, rs = 0.f;
+      auto pass1 = [&](auto masked) {   // row max of the raw scores (two 32-column loads in flight)
+        constexpr bool MASKED = decltype(masked)::value;
 #pragma unroll 1
-      for (int cc = 0; cc < 2; ++cc) {
-        uint32_t v0[32], v1[32];
-        ft_tmem_ld32(s_addr + cc * 64, v0);
-        ft_tmem_ld32(s_addr + cc * 64 + 32, v1);
-        ft_tmem_ld_wait();
-        if (nvalid < 128) {
+        for (int cc = 0; cc < 2; ++cc) {
+          uint32_t v0[32], v1[32];
+          ft_tmem_ld32(s_addr + cc * 64, v0);
+          ft_tmem_ld32(s_addr + cc * 64 + 32, v1);
+          ft_tmem_ld_wait();
 #pragma unroll
           for (int e = 0; e < 32; ++e) {
-            if (cc * 64 + e < nvalid) mx = fmaxf(mx, __uint_as_float(v0[e]));
-            if (cc * 64 + 32 + e < nvalid) mx = fmaxf(mx, __uint_as_float(v1[e]));
+            if (MASKED) {
+              if (cc * 64 + e < nvalid) mx = fmaxf(mx, __uint_as_float(v0[e]));
+              if (cc * 64 + 32 + e < nvalid) mx = fmaxf(mx, __uint_as_float(v1[e]));
+            } else {
+              mx = fmaxf(mx, fmaxf(__uint_as_float(v0[e]), __uint_as_float(v1[e])));
+            }
           }
-        } else {
-#pragma unroll
-          for (int e = 0; e < 32; ++e) mx = fmaxf(mx, fmaxf(__uint_as_float(v0[e]), __uint_as_float(v1[e])));
         }
-      }
+      };
+      auto pass2 = [&](auto masked) {   // p = 2^(s*c - m*c), row sum in fp32, P -> fp16 in the UMMA K-major swizzled layout
+        constexpr bool MASKED = decltype(masked)::value;
+#pragma unroll 1
+        for (int cc = 0; cc < 4; ++cc) {
+          uint32_t v[32];
+          ft_tmem_ld32(s_addr + cc * 32, v);
+          ft_tmem_ld_wait();
+          if (cc == 3) {   // S has been read for the last time: the MMA warp may overwrite it (tile j + SBUF)
+            ft_tc_fence_before();
+            __syncwarp();
+            if (lane == 0) ft_mbar_arrive(s_empty(t, a));
+          }
+          uint32_t pk[16];
+#pragma unroll
+          for (int e = 0; e < 32; e += 2) {
+            float p0 = ft_ex2(fmaf(__uint_as_float(v[e]), c, mneg));
+            float p1 = ft_ex2(fmaf(__uint_as_float(v[e + 1]), c, mneg));
+            if (MASKED) {
+              if (cc * 32 + e >= nvalid) p0 = 0.f;
+              if (cc * 32 + e + 1 >= nvalid) p1 = 0.f;
+            }
+            rs += p0 + p1;
+            pk[e >> 1] = h2_as_u32(__floats2half2_rn(p0, p1));
+          }
+          // keys cc*32 .. +31 = 16-byte chunks 4cc .. 4cc+3 of this row: block (4cc+i)/8, swizzled chunk ((4cc+i)%8) ^ (r%8)
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int ch = cc * 4 + i;
+            *reinterpret_cast<uint4*>(myP + (ch >> 3) * FT_TILE + r * 128 + (((ch & 7) ^ (r & 7)) << 4)) =
+                make_uint4(pk[4 * i], pk[4 * i + 1], pk[4 * i + 2], pk[4 * i + 3]);
+          }
+        }
+      };
+      if (nvalid < 128) pass1(std::true_type{});
+      else pass1(std::false_type{});
       const float m_new = fmaxf(m_run, mx);
-      const float corr = ft_ex2((m_run - m_new) * c);   // 0 for the first tile (m_run = -inf)
-      const float mneg = -m_new * c;
+      corr = ft_ex2((m_run - m_new) * c);   // 0 for the first tile (m_run = -inf)
+      mneg = -m_new * c;
       m_run = m_new;
       // ---- fold the previous tile's P.V into the register accumulator ----
       if (j > 0) {
@@ -370,38 +409,8 @@ flash_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
         if (lane == 0) ft_mbar_arrive(o_empty(t));
       }
       corr_pending = corr;
-      // ---- pass 2: p = 2^(s*c - m*c), row sum in fp32, P -> fp16 in the UMMA K-major swizzled layout ----
-      float rs = 0.f;
-#pragma unroll 1
-      for (int cc = 0; cc < 4; ++cc) {
-        uint32_t v[32];
-        ft_tmem_ld32(s_addr + cc * 32, v);
-        ft_tmem_ld_wait();
-        if (cc == 3) {   // S has been read for the last time: the MMA warp may overwrite it (tile j + SBUF)
-          ft_tc_fence_before();
-          __syncwarp();
-          if (lane == 0) ft_mbar_arrive(s_empty(t, a));
-        }
-        uint32_t pk[16];
-#pragma unroll
-        for (int e = 0; e < 32; e += 2) {
-          float p0 = ft_ex2(fmaf(__uint_as_float(v[e]), c, mneg));
-          float p1 = ft_ex2(fmaf(__uint_as_float(v[e + 1]), c, mneg));
-          if (nvalid < 128) {
-            if (cc * 32 + e >= nvalid) p0 = 0.f;
-            if (cc * 32 + e + 1 >= nvalid) p1 = 0.f;
-          }
-          rs += p0 + p1;
-          pk[e >> 1] = h2_as_u32(__floats2half2_rn(p0, p1));
-        }
-        // keys cc*32 .. +31 = 16-byte chunks 4cc .. 4cc+3 of this row: block (4cc+i)/8, swizzled chunk ((4cc+i)%8) ^ (r%8)
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const int ch = cc * 4 + i;
-          *reinterpret_cast<uint4*>(myP + (ch >> 3) * FT_TILE + r * 128 + (((ch & 7) ^ (r & 7)) << 4)) =
-              make_uint4(pk[4 * i], pk[4 * i + 1], pk[4 * i + 2], pk[4 * i + 3]);
-        }
-      }
+      if (nvalid < 128) pass2(std::true_type{});
+      else pass2(std::false_type{});
       l_run = fmaf(l_run, corr, rs);
       // P_j written: hand it to the MMA warp
       ft_fence_proxy_async();
