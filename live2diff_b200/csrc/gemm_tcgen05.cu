@@ -114,8 +114,10 @@ __device__ __forceinline__ void tmem_ld16(uint32_t addr, uint32_t (&r)[16]) {
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 // 256-bit global accesses (sm_100: LDG/STG.E.ENL2.256): one request per 32-byte sector instead of two.  The epilogue's
-// accesses are one row per lane (row pitch >= 640 B), so every 16-byte access is its own L2 request and the request rate,
-// not the byte rate, is what bounds the K = 320 GEMMs' epilogues (profiles/README.md).
+// accesses are one row per lane (row pitch >= 640 B), so every 16-byte access was its own L2 request; measured +2.2 % frames/s
+// in a same-box A/B (profiles/README.md, "GEMM family").  Hoisting all of a tile's bias / residual loads ahead of the
+// accumulator wait (bias staged in shared memory) shortened the isolated epilogue by a third but made the frame 4 % slower
+// (registers 126 -> 168, one more barrier per tile) and is not used.
 __device__ __forceinline__ void ldg256(const void* p, uint4& a, uint4& b) {
   asm volatile("ld.global.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
                : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w), "=r"(b.x), "=r"(b.y), "=r"(b.z), "=r"(b.w)
@@ -232,7 +234,6 @@ gemm_f16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid
   const int total_tiles = tiles_n * tiles_m * splits;
   const int my_tiles = CL ? 1 : ((int)blockIdx.x < total_tiles) ? (total_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
   float* cl_part = reinterpret_cast<float*>(smem + STAGES * S::STAGE_BYTES + 256);   // CL: [splits][128 rows][BN / splits] fp32
-  float* s_bias = cl_part;   // !CL: [NACC][BN] fp32 = bias (+ the tile's row-group bias when all its rows share one group)
 
   struct Tile {
     int n0, m0, mt, z, kb_begin, num_kb, cn0, ch0, cw0;
@@ -380,55 +381,17 @@ gemm_f16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid
       const __half* res_ptr = use_res ? epi.residual + (size_t)row * epi.ldr + n0 : nullptr;
       const __half* rg_ptr = (epi.rowgroup_bias && row_ok)
                                  ? epi.rowgroup_bias + (size_t)(row / epi.rows_per_group) * epi.rg_ld + n0 : nullptr;
-      const __half* bias_ptr = epi.bias ? epi.bias + n0 : nullptr;   // (CL path only; the main path reads the staged vector)
-      // Everything the epilogue reads from global memory is requested BEFORE the accumulator wait: with one 32-byte access
-      // per chunk and an L2 round trip each, a chunk-by-chunk epilogue spends ~700 cycles per chunk waiting (ncu: long
-      // scoreboard 5.0 per issue; profiles/README.md) -- 3-5x the mainloop of the K = 320 GEMMs.
-      //  * bias (+ the row-group bias when the whole tile lies in one group): staged once per tile in shared memory
-      //  * residual: all of this thread's chunks into registers
-      bool rg_staged = false;
-      if constexpr (!CL) {
-        int g_first = 0, g_last = 0;
-        if (epi.rowgroup_bias) {
-          if (cg.enabled) {
-            g_first = ((tl.cn0 * cg.H + tl.ch0) * cg.W + tl.cw0) / epi.rows_per_group;
-            g_last = (((tl.cn0 + cg.bn - 1) * cg.H + tl.ch0 + cg.bh - 1) * cg.W + tl.cw0 + cg.bw - 1) / epi.rows_per_group;
-          } else {
-            g_first = tl.m0 / epi.rows_per_group;
-            g_last = min(tl.m0 + BM - 1, M - 1) / epi.rows_per_group;
-          }
-          rg_staged = g_first == g_last;
-        }
-        float* sb = s_bias + as * BN;
-        for (int i2 = (int)threadIdx.x - 64; i2 < BN; i2 += 256) {
-          const int col = n0 + i2;
-          float bv = 0.f;
-          if (col < N) {
-            if (epi.bias) bv = __half2float(epi.bias[col]);
-            if (rg_staged) bv += __half2float(__ldcg(epi.rowgroup_bias + (size_t)g_first * epi.rg_ld + col));
-          }
-          sb[i2] = bv;
-        }
-        asm volatile("bar.sync 1, 256;" ::: "memory");   // the 8 epilogue warps (also orders reuse of the other stage's vector)
-      }
-      const bool use_bias = epi.bias != nullptr || rg_staged;
-      const __half* rg_ptr2 = rg_staged ? nullptr : rg_ptr;
-      // whole 32-byte sectors per access when the rows are 32-byte aligned (every activation of the UNet is)
+      const __half* bias_ptr = epi.bias ? epi.bias + n0 : nullptr;
+      // first chunk's residual is requested before the accumulator wait; each iteration requests the next one
+      uint4 res0 = make_uint4(0, 0, 0, 0), res1 = res0;
       const bool v32 = (reinterpret_cast<uintptr_t>(epi.out) & 31) == 0 && (epi.ldo & 15) == 0 &&
                        (!epi.residual || ((reinterpret_cast<uintptr_t>(epi.residual) & 31) == 0 && (epi.ldr & 15) == 0));
-      constexpr int NCHW = (NCH + 1) / 2;   // chunks per warp
-      uint4 resv[NCHW][2];
-#pragma unroll
-      for (int ci = 0; ci < NCHW; ++ci) {
-        resv[ci][0] = resv[ci][1] = make_uint4(0, 0, 0, 0);
-        const int c0 = (cc_begin + ci) * 16;
-        if (res_ptr && cc_begin + ci < cc_end && n0 + c0 < N) {
-          if (v32 && n0 + c0 + 8 < N) {
-            ldg256(res_ptr + c0, resv[ci][0], resv[ci][1]);                       // plain loads: may alias `out`
-          } else {
-            resv[ci][0] = *reinterpret_cast<const uint4*>(res_ptr + c0);
-            if (n0 + c0 + 8 < N) resv[ci][1] = *reinterpret_cast<const uint4*>(res_ptr + c0 + 8);
-          }
+      if (res_ptr && n0 + cc_begin * 16 < N) {
+        if (v32 && n0 + cc_begin * 16 + 8 < N) {
+          ldg256(res_ptr + cc_begin * 16, res0, res1);
+        } else {
+          res0 = *reinterpret_cast<const uint4*>(res_ptr + cc_begin * 16);
+          if (n0 + cc_begin * 16 + 8 < N) res1 = *reinterpret_cast<const uint4*>(res_ptr + cc_begin * 16 + 8);
         }
       }
       // LayerNorm consumer: this row's mean / rstd from the producer's per-tile partial sums (fixed slot order)
@@ -497,13 +460,21 @@ gemm_f16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid
         }
       } else if (!geglu) {
         __half* out_ptr = epi.out + (size_t)row * epi.ldo + n0;
-#pragma unroll
-        for (int ci = 0; ci < NCHW; ++ci) {
-          const int cc = cc_begin + ci;
-          if (cc >= cc_end) break;
+#pragma unroll 1
+        for (int cc = cc_begin; cc < cc_end; ++cc) {
           const int c0 = cc * 16;                        // column offset inside the tile
           uint32_t r[16];
           tmem_ld16(taddr + c0, r);
+          // request the next chunk's residual while the TMEM load is in flight
+          uint4 nres0 = make_uint4(0, 0, 0, 0), nres1 = nres0;
+          if (res_ptr && cc + 1 < cc_end && n0 + c0 + 16 < N) {
+            if (v32 && n0 + c0 + 24 < N) {
+              ldg256(res_ptr + c0 + 16, nres0, nres1);
+            } else {
+              nres0 = *reinterpret_cast<const uint4*>(res_ptr + c0 + 16);
+              if (n0 + c0 + 24 < N) nres1 = *reinterpret_cast<const uint4*>(res_ptr + c0 + 24);
+            }
+          }
           tmem_ld_wait();
           float v[16];
 #pragma unroll
@@ -524,23 +495,28 @@ gemm_f16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid
               }
             }
           }
-          if (use_bias) {   // staged bias (+ row-group bias): broadcast reads from shared memory
-            const float4* sb4 = reinterpret_cast<const float4*>(s_bias + as * BN + c0);
-#pragma unroll
-            for (int q4 = 0; q4 < 4; ++q4) {
-              const float4 b4 = sb4[q4];
-              v[q4 * 4 + 0] += b4.x; v[q4 * 4 + 1] += b4.y; v[q4 * 4 + 2] += b4.z; v[q4 * 4 + 3] += b4.w;
-            }
-          }
-          if (rg_ptr2) {    // a tile that straddles row groups (tiny images): per-row loads
+          if (bias_ptr) {
             float b[8];
             if (lo_ok) {
-              unpack8(ldg_act(rg_ptr2 + c0), b);
+              unpack8(ldg_cached(bias_ptr + c0), b);
 #pragma unroll
               for (int e = 0; e < 8; ++e) v[e] += b[e];
             }
             if (hi_ok) {
-              unpack8(ldg_act(rg_ptr2 + c0 + 8), b);
+              unpack8(ldg_cached(bias_ptr + c0 + 8), b);
+#pragma unroll
+              for (int e = 0; e < 8; ++e) v[8 + e] += b[e];
+            }
+          }
+          if (rg_ptr) {
+            float b[8];
+            if (lo_ok) {
+              unpack8(ldg_act(rg_ptr + c0), b);
+#pragma unroll
+              for (int e = 0; e < 8; ++e) v[e] += b[e];
+            }
+            if (hi_ok) {
+              unpack8(ldg_act(rg_ptr + c0 + 8), b);
 #pragma unroll
               for (int e = 0; e < 8; ++e) v[8 + e] += b[e];
             }
@@ -554,10 +530,10 @@ gemm_f16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid
           }
           if (use_res) {
             float b[8];
-            unpack8(resv[ci][0], b);
+            unpack8(res0, b);
 #pragma unroll
             for (int e = 0; e < 8; ++e) v[e] += b[e];
-            unpack8(resv[ci][1], b);
+            unpack8(res1, b);
 #pragma unroll
             for (int e = 0; e < 8; ++e) v[8 + e] += b[e];
           }
@@ -599,6 +575,8 @@ gemm_f16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid
               }
             }
           }
+          res0 = nres0;
+          res1 = nres1;
         }
         if (epi.stats_out && row_ok)
           epi.stats_out[(size_t)row * epi.stats_slots + (n0 / BN) * 2 + h] = make_float2(st_sum, st_sq);
@@ -622,13 +600,9 @@ gemm_f16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid
             float bh[8], bg[8];
 #pragma unroll
             for (int e = 0; e < 8; ++e) bh[e] = bg[e] = 0.f;
-            if (use_bias && colh + hlf * 8 < N) {
-              const float* sbh = s_bias + as * BN + cc * 16 + hlf * 8;
-#pragma unroll
-              for (int e = 0; e < 8; ++e) {
-                bh[e] = sbh[e];
-                bg[e] = sbh[HB + e];
-              }
+            if (bias_ptr && colh + hlf * 8 < N) {
+              unpack8(ldg_cached(bias_ptr + cc * 16 + hlf * 8), bh);
+              unpack8(ldg_cached(bias_ptr + HB + cc * 16 + hlf * 8), bg);
             }
             float sh[8], sg[8];
             if (epi.ln_stats && colh + hlf * 8 < N) {   // LayerNorm consumer: (s, b') of the value and gate columns
@@ -1032,7 +1006,7 @@ static int launch_gemm_cluster(const CUtensorMap& ta, const CUtensorMap& tb, con
 template <int BN, int STAGES, int NACC = 2>
 static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmEpilogue& e, const ConvGeom& cg, int M,
                        int N, int K, int splits, int tiles_m, cudaStream_t st) {
-  constexpr size_t smem = (size_t)STAGES * GemmSmem<BN>::STAGE_BYTES + 256 /* barriers */ + (size_t)NACC * BN * sizeof(float) /* staged bias */ + 1024;
+  constexpr size_t smem = (size_t)STAGES * GemmSmem<BN>::STAGE_BYTES + (2 * STAGES + 6) * 8 + 1024;
   static bool configured = false;
   if (!configured) {
     L2D_CUDA(cudaFuncSetAttribute(gemm_f16_tcgen05_kernel<BN, STAGES, false, NACC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
