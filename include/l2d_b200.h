@@ -215,6 +215,10 @@ typedef struct l2d_unet_step_args {
 } l2d_unet_step_args;
 
 int l2d_unet_create(l2d_unet** out, const l2d_unet_config* cfg, const l2d_tensor* weights, int n_weights);
+/* A second engine over the SAME repacked weights (no copy: it owns only its workspace): same topology as `base`, its own
+ * n_rows / latent size / warmup_frames / use_cuda_graph.  `base` must outlive it.  This is how the warm-up engine
+ * (cfg.warmup_frames > 0) sits next to the streaming engine without a second 2.6 GiB of weights. */
+int l2d_unet_create_shared(l2d_unet** out, const l2d_unet_config* cfg, const l2d_unet* base);
 int l2d_unet_step(l2d_unet* u, const l2d_unet_step_args* args, void* stream);
 /* Per-family kernel time of one step: the step is run eagerly once per family with CUDA events around that family's
  * launches only (so the host stays ahead of the GPU and the stream runs back to back, as in the graph replay), and

@@ -65,6 +65,7 @@ SIGNATURES = {
     "l2d_tt_forward": (i32, [vp, vp, vp, vp, vp, vp, vp, vp, vp]),
     "l2d_tt_destroy": (None, [vp]),
     "l2d_unet_create": (i32, [C.POINTER(vp), C.POINTER(L2DUnetConfig), C.POINTER(L2DTensor), i32]),
+    "l2d_unet_create_shared": (i32, [C.POINTER(vp), C.POINTER(L2DUnetConfig), vp]),
     "l2d_unet_step": (i32, [vp, C.POINTER(L2DUnetStepArgs), vp]),
     "l2d_unet_profile_step": (i32, [vp, C.POINTER(L2DUnetStepArgs), vp, C.POINTER(C.c_float), C.POINTER(C.c_int32)]),
     "l2d_unet_constants_epoch": (i64, [vp]),

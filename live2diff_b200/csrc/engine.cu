@@ -833,8 +833,11 @@ int run_step(l2d_unet* u, const l2d_unet_step_args* a) {
 
 }  // namespace
 
-extern "C" int l2d_unet_create(l2d_unet** out, const l2d_unet_config* cfg, const l2d_tensor* weights, int n_weights) {
-  L2D_CHECK_ARG(out && cfg && weights && n_weights > 0, "null arguments");
+// base != nullptr: build an engine VIEW that shares base's repacked weights (parameter holders are copied, not the device
+// memory they point to) and owns only its workspace -- the warm-up engine next to the streaming engine (unet_warmup.py)
+static int unet_create_impl(l2d_unet** out, const l2d_unet_config* cfg, const l2d_tensor* weights, int n_weights,
+                            const l2d_unet* base) {
+  L2D_CHECK_ARG(out && cfg && (base || (weights && n_weights > 0)), "null arguments");
   L2D_CHECK_ARG(cfg->n_levels >= 1 && cfg->n_levels <= 8 && cfg->layers_per_block >= 1, "bad topology");
   L2D_CHECK_ARG(cfg->n_rows >= 1 && cfg->n_rows <= 8, "n_rows must be in 1..8");
   L2D_CHECK_ARG(cfg->warmup_frames == 0 || (cfg->warmup_frames == cfg->n_rows && cfg->warmup_frames <= cfg->window),
@@ -907,9 +910,33 @@ extern "C" int l2d_unet_create(l2d_unet** out, const l2d_unet_config* cfg, const
   RC(k.pool.halfs(&u->temb1, (size_t)n * u->temb_dim));
   RC(k.pool.halfs(&u->emb, (size_t)n * u->temb_dim));
 
+  const int* c = cfg->block_out_channels;
+  if (base) {
+    // ---- parameters: shallow copies of the base engine's holders (device pointers into base's pool) ----
+    const l2d_unet_config& b = base->cfg;
+    bool same = b.n_levels == cfg->n_levels && b.layers_per_block == cfg->layers_per_block && b.heads == cfg->heads &&
+                b.cross_attention_dim == cfg->cross_attention_dim && b.groups == cfg->groups && b.window == cfg->window &&
+                b.n_mapping == cfg->n_mapping && b.norm_eps == cfg->norm_eps;
+    for (int i = 0; same && i < cfg->n_levels; ++i)
+      same = b.block_out_channels[i] == cfg->block_out_channels[i] && b.down_has_attn[i] == cfg->down_has_attn[i] &&
+             b.up_has_attn[i] == cfg->up_has_attn[i];
+    for (int i = 0; same && i < cfg->n_mapping; ++i) same = b.mapping_channels[i] == cfg->mapping_channels[i];
+    if (!same) return fail(L2D_ERR_INVALID, "l2d_unet_create_shared: the view's topology differs from the base engine's");
+    u->conv_in = base->conv_in; u->map_in = base->map_in; u->map_out = base->map_out; u->conv_out = base->conv_out;
+    u->map_blocks = base->map_blocks;
+    u->time1 = base->time1; u->time2 = base->time2; u->temb_all = base->temb_all; u->kv2_all = base->kv2_all;
+    u->norm_out = base->norm_out;
+    u->down_res = base->down_res; u->up_res = base->up_res; u->down_attn = base->down_attn; u->up_attn = base->up_attn;
+    u->down_mm = base->down_mm; u->up_mm = base->up_mm; u->down_samp = base->down_samp; u->up_samp = base->up_samp;
+    u->mid_res[0] = base->mid_res[0]; u->mid_res[1] = base->mid_res[1]; u->mid_attn = base->mid_attn;
+    u->temb_total = base->temb_total;
+    u->skip_c = base->skip_c;
+    RC(k.pool.halfs(&u->out8, (size_t)u->lv[0].m * u->conv_out.n_pad));
+    RC(k.pool.halfs(&u->temb_proj, (size_t)n * u->temb_total));
+    RC(k.pool.halfs(&u->kv2, (size_t)n * cfg->ctx_len * std::max(u->kv2_all.n, 8)));
+  } else {
   WeightTable wt;
   RC(wt.build(weights, n_weights));
-  const int* c = cfg->block_out_channels;
 
   // ---- parameters ----
   RC(k.load_conv3(wt, "conv_in", 4, c[0], &u->conv_in));
@@ -1050,6 +1077,7 @@ extern "C" int l2d_unet_create(l2d_unet** out, const l2d_unet_config* cfg, const
     }
     RC(k.pool.halfs(&u->kv2, (size_t)n * cfg->ctx_len * std::max(total, 8)));
   }
+  }   // !base
   // skip buffers
   {
     int lvl_i = 0, cnt = 0;
@@ -1072,6 +1100,15 @@ extern "C" int l2d_unet_create(l2d_unet** out, const l2d_unet_config* cfg, const
   L2D_CUDA(cudaGetLastError());
   *out = u.release();
   return L2D_OK;
+}
+
+extern "C" int l2d_unet_create(l2d_unet** out, const l2d_unet_config* cfg, const l2d_tensor* weights, int n_weights) {
+  return unet_create_impl(out, cfg, weights, n_weights, nullptr);
+}
+
+extern "C" int l2d_unet_create_shared(l2d_unet** out, const l2d_unet_config* cfg, const l2d_unet* base) {
+  L2D_CHECK_ARG(base != nullptr, "null base engine");
+  return unet_create_impl(out, cfg, nullptr, 0, base);
 }
 
 extern "C" int l2d_unet_step(l2d_unet* u, const l2d_unet_step_args* a, void* stream) {

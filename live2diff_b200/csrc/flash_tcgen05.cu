@@ -362,16 +362,10 @@ flash_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
       };
       auto pass2 = [&](auto masked) {   // p = 2^(s*c - m*c), row sum in fp32, P -> fp16 in the UMMA K-major swizzled layout
         constexpr bool MASKED = decltype(masked)::value;
-#pragma unroll 1
-        for (int cc = 0; cc < 4; ++cc) {
-          uint32_t v[32];
-          ft_tmem_ld32(s_addr + cc * 32, v);
-          ft_tmem_ld_wait();
-          if (cc == 3) {   // S has been read for the last time: the MMA warp may overwrite it (tile j + SBUF)
-            ft_tc_fence_before();
-            __syncwarp();
-            if (lane == 0) ft_mbar_arrive(s_empty(t, a));
-          }
+        // TMEM loads are software-pipelined through two register buffers: chunk cc+1 is in flight while chunk cc is being
+        // exponentiated (tcgen05.wait::ld waits for everything outstanding, so the wait sits AFTER the compute)
+        uint32_t va[32], vb[32];
+        auto emit = [&](const uint32_t (&v)[32], int cc) {
           uint32_t pk[16];
 #pragma unroll
           for (int e = 0; e < 32; e += 2) {
@@ -391,7 +385,23 @@ flash_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
             *reinterpret_cast<uint4*>(myP + (ch >> 3) * FT_TILE + r * 128 + (((ch & 7) ^ (r & 7)) << 4)) =
                 make_uint4(pk[4 * i], pk[4 * i + 1], pk[4 * i + 2], pk[4 * i + 3]);
           }
-        }
+        };
+        ft_tmem_ld32(s_addr, va);
+        ft_tmem_ld_wait();
+        ft_tmem_ld32(s_addr + 32, vb);
+        emit(va, 0);
+        ft_tmem_ld_wait();
+        ft_tmem_ld32(s_addr + 64, va);
+        emit(vb, 1);
+        ft_tmem_ld_wait();
+        ft_tmem_ld32(s_addr + 96, vb);
+        emit(va, 2);
+        ft_tmem_ld_wait();
+        // S has been read for the last time: the MMA warp may overwrite it (tile j + SBUF)
+        ft_tc_fence_before();
+        __syncwarp();
+        if (lane == 0) ft_mbar_arrive(s_empty(t, a));
+        emit(vb, 3);
       };
       if (nvalid < 128) pass1(std::true_type{});
       else pass1(std::false_type{});

@@ -553,6 +553,10 @@ kv_attn_mma_kernel(const __grid_constant__ CUtensorMap tmap, const KvAttnParams 
           for (int r = 0; r < 4; ++r) a[r] = km_hadd2(a[r], pe[r]);             // V + V_pe -> fp16
           float o[4];
           km_mma0(o, a, pb0, pb1);
+          // The stores below overwrite bytes of the V window that OTHER lanes of this warp supplied to the ldmatrix above.
+          // The data dependency ldmatrix -> HADD2 -> mma -> store already orders them in hardware; the __syncwarp makes the
+          // ordering formal for the memory model (compute-sanitizer racecheck reported the pair as a WAR hazard without it).
+          __syncwarp();
           // lane (g, t): o[0] = O^T[dt*16+g][2t], o[1] = [..][2t+1], o[2] = O^T[dt*16+8+g][2t], o[3] = [..][2t+1]
           *reinterpret_cast<uint32_t*>(vplane + ooff) = h2_as_u32(__floats2half2_rn(o[0], o[1]));
           *reinterpret_cast<uint32_t*>(vplane + ooff + 8 * 128) = h2_as_u32(__floats2half2_rn(o[2], o[3]));   // slot g + 8

@@ -34,20 +34,8 @@ class UNetStepOutput(dict):
             raise AttributeError(k) from e
 
 
-def create_engine(state_dict: Dict[str, torch.Tensor], dims: UNetDims, n_rows: int, latent_h: int, latent_w: int,
-                  ctx_len: int, use_cuda_graph: bool, warmup_frames: int, device: torch.device) -> C.c_void_p:
-    """l2d_unet_create over the reference's state_dict (validated against `unet_param_spec`); the engine keeps
-    repacked copies, the caller keeps its tensors.  warmup_frames > 0 builds the warm-up engine (unet_warmup.py)."""
-    spec = unet_param_spec(dims)
-    missing = [k for k in spec if k not in state_dict]
-    if missing:
-        raise KeyError(f"state_dict is missing {len(missing)} tensors, e.g. {missing[:3]}")
-    named = {}
-    for k, shape in spec.items():
-        t = state_dict[k]
-        if tuple(t.shape) != tuple(shape):
-            raise ValueError(f"{k}: shape {tuple(t.shape)} != expected {tuple(shape)}")
-        named[k] = t.detach().to(device=device, dtype=torch.float16).contiguous()
+def engine_config(dims: UNetDims, n_rows: int, latent_h: int, latent_w: int, ctx_len: int, use_cuda_graph: bool,
+                  warmup_frames: int) -> L2DUnetConfig:
     cfg = L2DUnetConfig()
     nlev = len(dims.block_out_channels)
     cfg.n_levels = nlev
@@ -64,6 +52,34 @@ def create_engine(state_dict: Dict[str, torch.Tensor], dims: UNetDims, n_rows: i
     cfg.norm_eps = dims.norm_eps
     cfg.use_cuda_graph = int(use_cuda_graph)
     cfg.warmup_frames = int(warmup_frames)
+    return cfg
+
+
+def create_shared_engine(base_handle, dims: UNetDims, n_rows: int, latent_h: int, latent_w: int, ctx_len: int,
+                         use_cuda_graph: bool, warmup_frames: int, device: torch.device) -> C.c_void_p:
+    """l2d_unet_create_shared: an engine over the base engine's repacked weights (no second copy)."""
+    cfg = engine_config(dims, n_rows, latent_h, latent_w, ctx_len, use_cuda_graph, warmup_frames)
+    handle = C.c_void_p()
+    with torch.cuda.device(device):
+        check(lib().l2d_unet_create_shared(C.byref(handle), C.byref(cfg), base_handle))
+    return handle
+
+
+def create_engine(state_dict: Dict[str, torch.Tensor], dims: UNetDims, n_rows: int, latent_h: int, latent_w: int,
+                  ctx_len: int, use_cuda_graph: bool, warmup_frames: int, device: torch.device) -> C.c_void_p:
+    """l2d_unet_create over the reference's state_dict (validated against `unet_param_spec`); the engine keeps
+    repacked copies, the caller keeps its tensors.  warmup_frames > 0 builds the warm-up engine (unet_warmup.py)."""
+    spec = unet_param_spec(dims)
+    missing = [k for k in spec if k not in state_dict]
+    if missing:
+        raise KeyError(f"state_dict is missing {len(missing)} tensors, e.g. {missing[:3]}")
+    named = {}
+    for k, shape in spec.items():
+        t = state_dict[k]
+        if tuple(t.shape) != tuple(shape):
+            raise ValueError(f"{k}: shape {tuple(t.shape)} != expected {tuple(shape)}")
+        named[k] = t.detach().to(device=device, dtype=torch.float16).contiguous()
+    cfg = engine_config(dims, n_rows, latent_h, latent_w, ctx_len, use_cuda_graph, warmup_frames)
     arr, keep = make_tensor_table(named)
     handle = C.c_void_p()
     with torch.cuda.device(device):

@@ -24,20 +24,29 @@ from typing import Dict, List, Optional
 import torch
 
 from ._lib import L2DUnetStepArgs, check, current_stream, lib
-from .unet_step import UNetStepOutput, create_engine
+from .unet_step import UNetStepOutput, create_engine, create_shared_engine
 from .weights import UNetDims
 
 
 class B200UNetWarmup:
-    def __init__(self, state_dict: Dict[str, torch.Tensor], dims: UNetDims, frames: int, latent_h: int, latent_w: int,
-                 ctx_len: int = 77, device: Optional[torch.device] = None):
+    def __init__(self, state_dict: Optional[Dict[str, torch.Tensor]], dims: UNetDims, frames: int, latent_h: int, latent_w: int,
+                 ctx_len: int = 77, device: Optional[torch.device] = None, share_weights_with=None):
+        """`share_weights_with`: a `B200UNetStep` built from the same state_dict -- the warm-up engine then reads that
+        engine's repacked weights (no second 2.6 GiB copy; `state_dict` may be None) and keeps it alive."""
         if not torch.cuda.is_available():
             raise RuntimeError("B200UNetWarmup needs a CUDA device; live2diff_b200 has no CPU fallback")
         if not 1 <= frames <= min(8, dims.window_size):
             raise ValueError("warm-up clip length must be in 1..min(8, window)")
         self.dims, self.frames, self.h, self.w, self.ctx_len = dims, frames, latent_h, latent_w, ctx_len
         self.device = torch.device(device or "cuda")
-        self._handle = create_engine(state_dict, dims, frames, latent_h, latent_w, ctx_len, False, frames, self.device)
+        self._base = share_weights_with
+        if share_weights_with is not None:
+            if share_weights_with.dims != dims:
+                raise ValueError("share_weights_with: the streaming engine was built for different UNetDims")
+            self._handle = create_shared_engine(share_weights_with._handle, dims, frames, latent_h, latent_w, ctx_len, False,
+                                                frames, self.device)
+        else:
+            self._handle = create_engine(state_dict, dims, frames, latent_h, latent_w, ctx_len, False, frames, self.device)
         self.dtype = torch.float16
         dev = self.device
         self._sample = torch.empty(frames, 4, 1, latent_h, latent_w, dtype=torch.float16, device=dev)

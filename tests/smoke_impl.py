@@ -42,3 +42,18 @@ def run_smoke(dev):
           f"{worst:.3e}; {launches} kernels launched by libl2d_b200.so")
     assert worst < 2e-2, worst
     assert launches > 0
+    # the VAE legs of the frame: TAESD encode + decode of one 64x64 image against the oracle restatement
+    from live2diff_b200.taesd import B200TinyVAE, random_taesd_state_dict
+    from oracle import taesd_oracle as T
+
+    vsd = random_taesd_state_dict(3)
+    vae = B200TinyVAE(vsd, 64, 64, device=dev)
+    img = (torch.rand(1, 3, 64, 64, generator=gen) * 2 - 1).half()
+    z = vae.encode(img.to(dev)).latents
+    rec = vae.decode(z, return_dict=False)[0]
+    z_ref = T.encode(vsd, img.float())
+    rec_ref = T.decode(vsd, z.float().cpu())
+    ez = float((z.float().cpu() - z_ref).abs().max()) / max(float(z_ref.abs().max()), 1.0)
+    er = float((rec.float().cpu() - rec_ref).abs().max()) / max(float(rec_ref.abs().max()), 1.0)
+    print(f"[smoke] TAESD 64x64: encode rel-to-scale error {ez:.3e}, decode {er:.3e}")
+    assert ez < 2e-2 and er < 2e-2, (ez, er)

@@ -156,7 +156,10 @@ def test_pipeline_warmup_loop_vs_oracle():
     n, h, w, f = 2, 16, 16, d.sink_size
     sd = random_state_dict(d, seed=9)
     unet = B200UNetStep(sd, d, n, h, w, use_cuda_graph=False)
-    warm = B200UNetWarmup(sd, d, f, h, w)
+    # the warm-up engine is a view over the streaming engine's repacked weights (l2d_unet_create_shared): workspace only
+    warm = B200UNetWarmup(None, d, f, h, w, share_weights_with=unet)
+    own = B200UNetWarmup(sd, d, f, h, w)
+    assert warm.device_bytes < 0.6 * own.device_bytes, (warm.device_bytes, own.device_bytes)
     pipe = B200StreamPipeline(unet, [30, 40])
     gen = torch.Generator().manual_seed(4)
     prompt = torch.randn(1, 77, 96, generator=gen).half()
@@ -165,6 +168,14 @@ def test_pipeline_warmup_loop_vs_oracle():
     dep = torch.randn(1, 4, f, h, w, generator=gen).half()
     noise = [torch.randn(1, 4, f, h, w, generator=gen).half()]
     x0 = pipe.warmup_denoise(warm, x.to(DEV), dep.to(DEV), noise=[z.to(DEV) for z in noise])
+    # the engine with its own weight copy gives the same bits as the shared-weight view
+    rows_a = [torch.zeros(s_[1:], dtype=torch.float16, device=DEV) for s_ in d.kv_cache_shapes(1, h, w)]
+    rows_b = [r.clone() for r in rows_a]
+    t1 = torch.tensor([399], device=DEV)
+    ya = warm(x.to(DEV), t1, depth_sample=dep.to(DEV), encoder_hidden_states=prompt.to(DEV), kv_cache=rows_a)["sample"]
+    yb = own(x.to(DEV), t1, depth_sample=dep.to(DEV), encoder_hidden_states=prompt.to(DEV), kv_cache=rows_b)["sample"]
+    assert torch.equal(ya, yb) and all(torch.equal(p_, q_) for p_, q_ in zip(rows_a, rows_b))
+    del own
     # oracle loop (fp32, fp16-rounded constants like the reference's prepare())
     od = odims(d)
     sub, c_skip, c_out, a, b = [v.half().float() if v.is_floating_point() else v for v in S.stream_constants([30, 40])]
