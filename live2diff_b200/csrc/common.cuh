@@ -132,17 +132,30 @@ __device__ __forceinline__ float warp_max(float v) {
   return v;
 }
 
-__device__ __forceinline__ float silu_f(float x) { return x / (1.0f + __expf(-x)); }
+// single-instruction MUFU forms (1 ulp): an IEEE divide / __frcp_rn costs 8-10 instructions with a slow-path branch, which
+// is what the GEGLU and SiLU epilogues are made of; the result is rounded to fp16 (2^-11) right after
+__device__ __forceinline__ float rcp_approx(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+// x * sigmoid(x); x -> -inf: ex2 -> +inf, rcp -> 0, result -0; x -> +inf: ex2 -> 0, result x
+__device__ __forceinline__ float silu_f(float x) { return x * rcp_approx(1.0f + ex2_approx(-1.4426950408889634f * x)); }
 // exact-erf GELU (diffusers GEGLU uses F.gelu default).  erf via Abramowitz-Stegun 7.1.26 (|abs err| <= 1.5e-7, two
 // orders below an fp16 ulp of the result) with MUFU rcp/ex2: ~14 instructions instead of erff's ~40.
 __device__ __forceinline__ float erf_as_f(float x) {
   const float ax = fabsf(x);
-  const float t = __frcp_rn(fmaf(0.3275911f, ax, 1.0f));
+  const float t = rcp_approx(fmaf(0.3275911f, ax, 1.0f));
   float p = fmaf(1.061405429f, t, -1.453152027f);
   p = fmaf(p, t, 1.421413741f);
   p = fmaf(p, t, -0.284496736f);
   p = fmaf(p, t, 0.254829592f);
-  const float e = exp2f(-ax * ax * 1.4426950408889634f);
+  const float e = ex2_approx(-ax * ax * 1.4426950408889634f);
   return copysignf(fmaf(-p * t, e, 1.0f), x);
 }
 __device__ __forceinline__ float gelu_erf_f(float x) { return 0.5f * x * (1.0f + erf_as_f(x * 0.70710678118654752f)); }

@@ -626,8 +626,14 @@ gemm_f16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid
 #pragma unroll
             for (int e = 0; e < 8; ++e) {
               // the reference rounds the projection to fp16 before h * gelu(g) (GEGLU.forward on an fp16 Linear output)
-              const float ah = fmaf(__uint_as_float(rh[hlf * 8 + e]), ln_rstd, fmaf(-ln_mr, sh[e], bh[e]));
-              const float ag = fmaf(__uint_as_float(rgt[hlf * 8 + e]), ln_rstd, fmaf(-ln_mr, sg[e], bg[e]));
+              float ah, ag;
+              if (epi.ln_stats) {
+                ah = fmaf(__uint_as_float(rh[hlf * 8 + e]), ln_rstd, fmaf(-ln_mr, sh[e], bh[e]));
+                ag = fmaf(__uint_as_float(rgt[hlf * 8 + e]), ln_rstd, fmaf(-ln_mr, sg[e], bg[e]));
+              } else {
+                ah = __uint_as_float(rh[hlf * 8 + e]) + bh[e];
+                ag = __uint_as_float(rgt[hlf * 8 + e]) + bg[e];
+              }
               const float hval = __half2float(__float2half_rn(ah));
               const float gval = __half2float(__float2half_rn(ag));
               v[hlf * 8 + e] = hval * gelu_erf_f(gval);

@@ -230,9 +230,6 @@ kv_attn_mma_kernel(const __grid_constant__ CUtensorMap tmap, const KvAttnParams 
   if (warp == 8) {   // ---- TMA producer: planes in order K(0) V(0) K(1) V(1) ...; plane s lives in buffer s % NB ----
     if (lane == 0) {
       const int planes = 2 * my_tiles;
-      // the first burst (NB planes from every SM) would put ~20 MB in front of the math warps' small dependent loads
-      // (index tensors -> PE rows): let those be queued first
-      km_mbar_wait(go_bar, 0);
       int plane_col = 0;                                         // first channel of the tile's slice
       auto plane_row = [&](int s) {
         const int tile = t_begin + (s >> 1);
@@ -240,7 +237,12 @@ kv_attn_mma_kernel(const __grid_constant__ CUtensorMap tmap, const KvAttnParams 
         plane_col = (nv % S) * C;
         return (((nv / S) * 2 + (s & 1)) * hwp + p0) * KM_L;
       };
+      // The K plane of the first tile is needed before anything else: it is requested at once.  The rest of the first burst
+      // (NB planes from every SM, ~20 MB) would sit in front of the math warps' small dependent loads (index tensors -> PE
+      // rows), so it waits until those are queued.  (L2D_K1_EAGER_PLANES, developer A/B: planes requested before that.)
+      const int eager = p.eager_planes;
       for (int s = 0; s < planes; ++s) {
+        if (s == eager) km_mbar_wait(go_bar, 0);
         const int b = s % NB, use = s / NB;
         if (use > 0) km_mbar_wait(empty_bar(b), (uint32_t)(use - 1) & 1u);
         const int row0 = plane_row(s);
@@ -677,6 +679,13 @@ int kv_attn_mma_launch(const KvAttnParams& p0, cudaStream_t stream) {
   }
   p.c_slices = sliced ? 2 : 1;
   p.c_full = c_full;
+  {
+    static const int eager = [] {
+      const char* e = getenv("L2D_K1_EAGER_PLANES");
+      return e ? atoi(e) : 1;
+    }();
+    p.eager_planes = eager;
+  }
   p.T = p.C / 8;
   p.hd8 = hd / 8;
   int P = 1280 / p.C;                        // 80 KB of K+V per tile: 4 / 2 / 1 (half-)pixels at C = 320 / 640 / 1280

@@ -26,6 +26,7 @@ struct KvAttnParams {
   int c_slices;  // tensor-core kernel: channel slices per row (1 = whole rows); a slice holds whole heads and is scheduled like
                  // a row of its own (own PE windows); C / heads / T then describe ONE slice and c_full the row pitch
   int c_full;
+  int eager_planes;  // tensor-core kernel: planes the producer requests before the row's schedule / PE loads are queued
   int pdl;  // 1: launched behind the QKV GEMM inside the engine (reads of the cache / PE tables may precede the PDL wait);
             // 0 (stand-alone l2d_kv_attn): fully serialised launch, the caller may have just written the cache
 };

@@ -10,8 +10,8 @@ import sys
 
 COLS = [
     ("us", "gpu__time_duration.sum", 1e-3),
-    ("tensor%", "sm__pipe_tensor_op_hmma_cycles_active.avg.pct_of_peak_sustained_active", 1),
-    ("tensor2%", "sm__inst_executed_pipe_tensor.avg.pct_of_peak_sustained_active", 1),
+    ("tensor%", "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active", 1),
+    ("xu%", "sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active", 1),
     ("issue%", "sm__inst_issued.avg.pct_of_peak_sustained_active", 1),
     ("dramRdMB", "dram__bytes_read.sum", 1e-6),
     ("dramWrMB", "dram__bytes_write.sum", 1e-6),
@@ -35,6 +35,9 @@ def main(path):
     rows = list(csv.reader(l for l in open(path) if not l.startswith("==")))
     header, units = rows[0], rows[1]
     idx = {h: i for i, h in enumerate(header)}
+    for h, i in list(idx.items()):          # some metrics carry a section prefix ("FBSP.TriageCompute.dram__throughput...")
+        if "." in h and h.split(".", 2)[-1] not in idx and h.count(".") >= 3:
+            idx.setdefault(h.split(".", 2)[-1], i)
     name_i, grid_i = idx.get("Kernel Name"), idx.get("Grid Size")
     scale_unit = {"nsecond": 1.0, "ns": 1.0, "usecond": 1e3, "us": 1e3, "msecond": 1e6, "byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
     print(f"{'kernel':46s} {'grid':>14s} " + " ".join(f"{c[0]:>8s}" for c in COLS))
