@@ -10,14 +10,18 @@
 //   warp 1     TMEM allocator + single-thread tcgen05.mma issuer:
 //                S_j = Q . K_j^T   (M = 128 queries, N = 128 keys, K = hd padded to 16s; both operands K-major) into one
 //                                  of two S accumulators in TMEM, so that S_{j+1} is computed while S_j is in the softmax
-//                T_j = P_j . V_j   (M = 128, N = hd rounded to 16, K = 128 keys; A = P from shared memory, K-major;
-//                                  B = the V tile exactly as TMA delivered it = MN-major, 128B swizzle)
-//   warps 2-5  softmax + correction + epilogue: thread = one query row (tcgen05.ld 32x32b: TMEM lane = row), so row max /
-//              row sum need no shuffles; P is rounded to fp16 (like the fused SDPA kernels the reference dispatches to)
-//              and written into shared memory in the UMMA K-major swizzled layout; the running output lives in registers
-//              (o = o * corr + T_j, flash-attention's online softmax in fp32), the 1/l normalisation is applied once.
+//                O  += P_j . V_j   (M = 128, N = hd rounded up to whole 64-channel swizzle atoms, K = 128 keys; A = P from
+//                                  shared memory, K-major; B = the V tile exactly as TMA delivered it = MN-major, 128B
+//                                  swizzle); O stays in TMEM across ALL key tiles (accumulate flag)
+//   warps 2-5  softmax + epilogue (a second quartet, warps 6-9, when the CTA carries two query tiles): thread = one query
+//              row (tcgen05.ld 32x32b: TMEM lane = row), so row max / row sum need no shuffles; P is rounded to fp16 (like
+//              the fused SDPA kernels the reference dispatches to) and written into shared memory in the UMMA K-major
+//              swizzled layout.  S is read from TMEM exactly once per tile: the exp uses the row max of the EARLIER tiles
+//              as its reference and the tile is redone (O and l rescaled in TMEM / registers) only when a row outgrows the
+//              reference by more than 2^8 -- the TMEM read port (64 B / clk / SM), not MUFU or the tensor core, was what
+//              bounded the classic two-pass form.  The 1/l normalisation is applied once at the end.
 // hd = 40: the K extent of Q.K^T is padded to 48 by zeroing columns 40..47 of the Q tile in shared memory (the K tile's
-// columns 40..47 then hold the next head's values, finite, times zero); T's columns 40..47 are ignored.
+// columns 40..47 then hold the next head's values, finite, times zero); O's columns 40..63 are never read.
 // Keys beyond skv in the last tile (cross-attention: 77 keys) are masked to -inf before the softmax; their V rows are
 // other rows of the same tensor or TMA zero fill, always finite.
 #include <cuda.h>
@@ -109,6 +113,13 @@ __device__ __forceinline__ float ft_ex2(float x) {   // arguments <= 0: no overf
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
+__device__ __forceinline__ void ft_tmem_st16(uint32_t addr, const uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};" ::"r"(addr),
+      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]),
+      "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+      : "memory");
+}
 __device__ __forceinline__ void ft_tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // UMMA shared-memory descriptors (cute::UMMA::SmemDescriptor bit layout, version 1, SWIZZLE_128B):
@@ -173,11 +184,10 @@ flash_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
   uint8_t* sP = sV + ST * Cfg::TILE_BYTES;             // [NQ] P tiles of 2 x 16 KB
   uint64_t* bars = reinterpret_cast<uint64_t*>(sP + NQ * 2 * FT_TILE);
   const uint32_t bar0 = ft_smem_u32(bars);
-  // barrier map: q_full, q_ready | per query tile t: p_full, o_full, o_empty, s_full[2], s_empty[2] | k/v full/empty[ST]
+  // barrier map: q_full, q_ready | per query tile t: p_full, o_full, (unused), s_full[2], s_empty[2] | k/v full/empty[ST]
   const uint32_t q_full = bar0, q_ready = bar0 + 8;
   auto p_full = [&](int t) { return bar0 + 16 + 56u * t; };
   auto o_full = [&](int t) { return bar0 + 24 + 56u * t; };
-  auto o_empty = [&](int t) { return bar0 + 32 + 56u * t; };
   auto s_full = [&](int t, int a) { return bar0 + 40 + 56u * t + 8u * a; };
   auto s_empty = [&](int t, int a) { return bar0 + 56 + 56u * t + 8u * a; };
   const uint32_t kv0 = bar0 + 16 + 56u * NQ;
@@ -202,7 +212,6 @@ flash_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
     for (int t = 0; t < NQ; ++t) {
       ft_mbar_init(p_full(t), 4);
       ft_mbar_init(o_full(t), 1);
-      ft_mbar_init(o_empty(t), 4);
       for (int a = 0; a < 2; ++a) {
         ft_mbar_init(s_full(t, a), 1);
         ft_mbar_init(s_empty(t, a), 4);
@@ -277,14 +286,13 @@ flash_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
         const int s = j % ST;
         if (t == 0) ft_mbar_wait(v_full(s), (uint32_t)(j / ST) & 1u);
         ft_mbar_wait(p_full(t), (uint32_t)j & 1u);
-        if (j > 0) ft_mbar_wait(o_empty(t), (uint32_t)(j - 1) & 1u);   // T_{j-1} has been folded into the register accumulator
         ft_tc_fence_after();
         const uint32_t pa = ft_smem_u32(sP + t * 2 * FT_TILE), va = ft_smem_u32(sV + s * Cfg::TILE_BYTES);
 #pragma unroll
         for (int kk = 0; kk < 8; ++kk) {   // 128 keys = 8 k16 steps: P block kk/4, +32 B per step; V: 16 key rows = 2 KB per step
           const uint64_t da = ft_desc(pa + (uint32_t)(kk >> 2) * FT_TILE + (uint32_t)(kk & 3) * 32, 0);
           const uint64_t db = ft_desc(va + (uint32_t)kk * 2048, FT_TILE);
-          ft_umma(tmem_base + tm_o(t), da, db, idesc_o, kk != 0);
+          ft_umma(tmem_base + tm_o(t), da, db, idesc_o, (j | kk) != 0);   // O accumulates across the key tiles
         }
         if (t == NQ - 1) ft_commit(v_empty(s));   // every query tile has read V_j
         ft_commit(o_full(t));
@@ -317,20 +325,18 @@ flash_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
     __syncwarp();
     if (lane == 0) ft_mbar_arrive(q_ready);
 
-    float m_run = -INFINITY, l_run = 0.f, corr_pending = 0.f;
-    float o_acc[ON];
-#pragma unroll
-    for (int i = 0; i < ON; ++i) o_acc[i] = 0.f;
+    // Online softmax with a LAZY reference (flash-attention 4's conditional rescale).  The kernel is bound by the TMEM read
+    // port (64 B / clk / SM) as much as by MUFU: reading S twice (row max, then exp) plus the P.V tile every key tile is
+    // 152 KB = 2375 cycles per 128 x 128 tile, which is what the two-pass version measured.  So S is read ONCE: tile j is
+    // exponentiated against the reference m_ref the row already has (the max of the earlier tiles) while its own max is
+    // tracked on the side; only if some row of the warp exceeds its reference by more than 2^LAZY is the tile redone
+    // against the new max (P <= 2^8 fits fp16 with the same relative precision, l and O are fp32).  And O is accumulated
+    // by the tensor core in TMEM across key tiles (accumulate flag), not folded through registers: it is touched by the
+    // softmax threads only on such a redo (O *= 2^(m_old - m_new), l likewise) and once at the end.
+    float m_ref = -INFINITY, l_run = 0.f;
     const float c = p.scale_log2;
-
-    auto fold_t = [&](float corr) {   // o = o * corr + T   (T = P.V of the previous tile, in TMEM)
-      uint32_t tt[ON];
-#pragma unroll
-      for (int cc = 0; cc < ON / 16; ++cc) ft_tmem_ld16(t_lane + tm_o(t) + cc * 16, *reinterpret_cast<uint32_t(*)[16]>(&tt[cc * 16]));
-      ft_tmem_ld_wait();
-#pragma unroll
-      for (int e = 0; e < ON; ++e) o_acc[e] = fmaf(o_acc[e], corr, __uint_as_float(tt[e]));
-    };
+    constexpr float LAZY = 8.f;
+    const uint32_t o_addr = t_lane + tm_o(t);
 
     for (int j = 0; j < nk; ++j) {
       const int a = j % SBUF;
@@ -338,109 +344,154 @@ flash_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
       ft_mbar_wait(s_full(t, a), (uint32_t)(j / SBUF) & 1u);
       ft_tc_fence_after();
       const uint32_t s_addr = t_lane + tm_s(t, a);
-      // Both passes exist twice: the full-tile version has NO per-element bounds checks (they doubled the instruction
+      // Every pass exists twice: the full-tile version has NO per-element bounds checks (they doubled the instruction
       // count of the hot loop when they were predicated in), the masked one runs for the last key tile only.
-      float mx = -INFINITY, corr = 0.f, mneg = 0.f, rs = 0.f;
-      auto pass1 = [&](auto masked) {   // row max of the raw scores (two 32-column loads in flight)
+      float mx = -INFINITY, mneg = 0.f, rs = 0.f;
+      bool p_free = j == 0;   // P_{j-1} has been consumed by the tensor core (first store of this tile waits for it)
+      uint32_t va[32], vb[32];
+      auto row_max = [&](auto masked) {   // first key tile only: there is no reference yet, take the tile's true max
         constexpr bool MASKED = decltype(masked)::value;
 #pragma unroll 1
         for (int cc = 0; cc < 2; ++cc) {
-          uint32_t v0[32], v1[32];
-          ft_tmem_ld32(s_addr + cc * 64, v0);
-          ft_tmem_ld32(s_addr + cc * 64 + 32, v1);
+          ft_tmem_ld32(s_addr + cc * 64, va);
+          ft_tmem_ld32(s_addr + cc * 64 + 32, vb);
           ft_tmem_ld_wait();
 #pragma unroll
           for (int e = 0; e < 32; ++e) {
             if (MASKED) {
-              if (cc * 64 + e < nvalid) mx = fmaxf(mx, __uint_as_float(v0[e]));
-              if (cc * 64 + 32 + e < nvalid) mx = fmaxf(mx, __uint_as_float(v1[e]));
+              if (cc * 64 + e < nvalid) mx = fmaxf(mx, __uint_as_float(va[e]));
+              if (cc * 64 + 32 + e < nvalid) mx = fmaxf(mx, __uint_as_float(vb[e]));
             } else {
-              mx = fmaxf(mx, fmaxf(__uint_as_float(v0[e]), __uint_as_float(v1[e])));
+              mx = fmaxf(mx, fmaxf(__uint_as_float(va[e]), __uint_as_float(vb[e])));
             }
           }
         }
       };
-      auto pass2 = [&](auto masked) {   // p = 2^(s*c - m*c), row sum in fp32, P -> fp16 in the UMMA K-major swizzled layout
+      // p = 2^(s*c - m_ref*c), row sum in fp32, P -> fp16 in the UMMA K-major swizzled layout, tile max on the side
+      auto emit = [&](auto masked, const uint32_t (&v)[32], int cc) {
         constexpr bool MASKED = decltype(masked)::value;
-        // TMEM loads are software-pipelined through two register buffers: chunk cc+1 is in flight while chunk cc is being
-        // exponentiated (tcgen05.wait::ld waits for everything outstanding, so the wait sits AFTER the compute)
-        uint32_t va[32], vb[32];
-        auto emit = [&](const uint32_t (&v)[32], int cc) {
-          uint32_t pk[16];
+        uint32_t pk[16];
 #pragma unroll
-          for (int e = 0; e < 32; e += 2) {
-            float p0 = ft_ex2(fmaf(__uint_as_float(v[e]), c, mneg));
-            float p1 = ft_ex2(fmaf(__uint_as_float(v[e + 1]), c, mneg));
-            if (MASKED) {
-              if (cc * 32 + e >= nvalid) p0 = 0.f;
-              if (cc * 32 + e + 1 >= nvalid) p1 = 0.f;
-            }
-            rs += p0 + p1;
-            pk[e >> 1] = h2_as_u32(__floats2half2_rn(p0, p1));
+        for (int e = 0; e < 32; e += 2) {
+          float p0 = ft_ex2(fmaf(__uint_as_float(v[e]), c, mneg));
+          float p1 = ft_ex2(fmaf(__uint_as_float(v[e + 1]), c, mneg));
+          if (MASKED) {
+            if (cc * 32 + e >= nvalid) p0 = 0.f;
+            if (cc * 32 + e + 1 >= nvalid) p1 = 0.f;
           }
-          // keys cc*32 .. +31 = 16-byte chunks 4cc .. 4cc+3 of this row: block (4cc+i)/8, swizzled chunk ((4cc+i)%8) ^ (r%8)
+          rs += p0 + p1;
+          pk[e >> 1] = h2_as_u32(__floats2half2_rn(p0, p1));
+        }
+        if (!p_free) {   // the tensor core reads P_{j-1} until P_{j-1} . V_{j-1} completes
+          ft_mbar_wait(o_full(t), (uint32_t)(j - 1) & 1u);
+          p_free = true;
+        }
+        // keys cc*32 .. +31 = 16-byte chunks 4cc .. 4cc+3 of this row: block (4cc+i)/8, swizzled chunk ((4cc+i)%8) ^ (r%8)
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const int ch = cc * 4 + i;
-            *reinterpret_cast<uint4*>(myP + (ch >> 3) * FT_TILE + r * 128 + (((ch & 7) ^ (r & 7)) << 4)) =
-                make_uint4(pk[4 * i], pk[4 * i + 1], pk[4 * i + 2], pk[4 * i + 3]);
+        for (int i = 0; i < 4; ++i) {
+          const int ch = cc * 4 + i;
+          *reinterpret_cast<uint4*>(myP + (ch >> 3) * FT_TILE + r * 128 + (((ch & 7) ^ (r & 7)) << 4)) =
+              make_uint4(pk[4 * i], pk[4 * i + 1], pk[4 * i + 2], pk[4 * i + 3]);
+        }
+      };
+      auto chunk_max = [&](auto masked, const uint32_t (&v)[32], int cc) {
+        constexpr bool MASKED = decltype(masked)::value;
+#pragma unroll
+        for (int e = 0; e < 32; e += 2) {
+          if (MASKED) {
+            if (cc * 32 + e < nvalid) mx = fmaxf(mx, __uint_as_float(v[e]));
+            if (cc * 32 + e + 1 < nvalid) mx = fmaxf(mx, __uint_as_float(v[e + 1]));
+          } else {
+            mx = fmaxf(mx, fmaxf(__uint_as_float(v[e]), __uint_as_float(v[e + 1])));
           }
-        };
+        }
+      };
+      // chunks 0..2 exponentiated, chunk 3 loaded and included in the max.  TMEM loads are software-pipelined through two
+      // register buffers: chunk cc+1 is in flight while chunk cc is being exponentiated (tcgen05.wait::ld waits for
+      // everything outstanding, so the wait sits AFTER the compute).
+      auto head = [&](auto masked) {
         ft_tmem_ld32(s_addr, va);
         ft_tmem_ld_wait();
         ft_tmem_ld32(s_addr + 32, vb);
-        emit(va, 0);
+        chunk_max(masked, va, 0);
+        emit(masked, va, 0);
         ft_tmem_ld_wait();
         ft_tmem_ld32(s_addr + 64, va);
-        emit(vb, 1);
+        chunk_max(masked, vb, 1);
+        emit(masked, vb, 1);
         ft_tmem_ld_wait();
         ft_tmem_ld32(s_addr + 96, vb);
-        emit(va, 2);
+        chunk_max(masked, va, 2);
+        emit(masked, va, 2);
         ft_tmem_ld_wait();
-        // S has been read for the last time: the MMA warp may overwrite it (tile j + SBUF)
-        ft_tc_fence_before();
-        __syncwarp();
-        if (lane == 0) ft_mbar_arrive(s_empty(t, a));
-        emit(vb, 3);
+        chunk_max(masked, vb, 3);
       };
-      if (nvalid < 128) pass1(std::true_type{});
-      else pass1(std::false_type{});
-      const float m_new = fmaxf(m_run, mx);
-      corr = ft_ex2((m_run - m_new) * c);   // 0 for the first tile (m_run = -inf)
-      mneg = -m_new * c;
-      m_run = m_new;
-      // ---- fold the previous tile's P.V into the register accumulator ----
-      if (j > 0) {
-        ft_mbar_wait(o_full(t), (uint32_t)(j - 1) & 1u);
-        ft_tc_fence_after();
-        fold_t(corr_pending);
-        ft_tc_fence_before();
-        __syncwarp();
-        if (lane == 0) ft_mbar_arrive(o_empty(t));
+      if (j == 0) {
+        if (nvalid < 128) row_max(std::true_type{});
+        else row_max(std::false_type{});
+        m_ref = mx;
       }
-      corr_pending = corr;
-      if (nvalid < 128) pass2(std::true_type{});
-      else pass2(std::false_type{});
-      l_run = fmaf(l_run, corr, rs);
+      mneg = -m_ref * c;
+      if (nvalid < 128) head(std::true_type{});
+      else head(std::false_type{});
+      if (__any_sync(0xffffffffu, fmaf(mx, c, mneg) > LAZY)) {
+        // some row of this warp outgrew its reference: move every row of the warp to its new max, rescale the history
+        // (rows whose max did not move get the factor 2^0 = 1, exact), and redo the tile.  j > 0 here (tile 0 started
+        // from its true max) and P_{j-1} . V_{j-1} has completed (the first P store waited for it), so O is stable.
+        const float m_new = fmaxf(m_ref, mx);
+        const float corr = ft_ex2((m_ref - m_new) * c);
+        ft_tc_fence_after();   // (the o_full wait inside the first P store ordered P_{j-1} . V_{j-1} before this point)
+#pragma unroll
+        for (int cc = 0; cc < ON / 16; ++cc) {
+          uint32_t tt[16];
+          ft_tmem_ld16(o_addr + cc * 16, tt);
+          ft_tmem_ld_wait();
+#pragma unroll
+          for (int e = 0; e < 16; ++e) tt[e] = __float_as_uint(__uint_as_float(tt[e]) * corr);
+          ft_tmem_st16(o_addr + cc * 16, tt);
+        }
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+        l_run *= corr;
+        m_ref = m_new;
+        mneg = -m_ref * c;
+        rs = 0.f;
+        if (nvalid < 128) head(std::true_type{});
+        else head(std::false_type{});
+      }
+      // S has been read for the last time: the MMA warp may overwrite it (tile j + SBUF)
+      ft_tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ft_mbar_arrive(s_empty(t, a));
+      if (nvalid < 128) emit(std::true_type{}, vb, 3);
+      else emit(std::false_type{}, vb, 3);
+      l_run += rs;
       // P_j written: hand it to the MMA warp
       ft_fence_proxy_async();
       __syncwarp();
       if (lane == 0) ft_mbar_arrive(p_full(t));
     }
-    // ---- last tile's P.V, normalise, store ----
+    // ---- last tile's P.V has landed: normalise, store ----
     ft_mbar_wait(o_full(t), (uint32_t)(nk - 1) & 1u);
     ft_tc_fence_after();
-    fold_t(corr_pending);
     const float inv = 1.f / l_run;
     const int row = m0 + t * 128 + r;
     __half* orow = p.o + ((size_t)b * p.sq + row) * p.ldo + col0;
-    if (row < p.sq) {
+    constexpr int OUT16 = (HD + 15) / 16;
 #pragma unroll
-      for (int i = 0; i < HD / 8; ++i) {
-        float f[8];
+    for (int cc = 0; cc < OUT16; ++cc) {
+      uint32_t tt[16];
+      ft_tmem_ld16(o_addr + cc * 16, tt);
+      ft_tmem_ld_wait();
+      if (row < p.sq) {
 #pragma unroll
-        for (int e = 0; e < 8; ++e) f[e] = o_acc[i * 8 + e] * inv;
-        *reinterpret_cast<uint4*>(orow + i * 8) = pack8(f);
+        for (int i = 0; i < 2; ++i) {
+          if (cc * 16 + i * 8 < HD) {
+            float f[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(tt[i * 8 + e]) * inv;
+            *reinterpret_cast<uint4*>(orow + cc * 16 + i * 8) = pack8(f);
+          }
+        }
       }
     }
   }

@@ -96,6 +96,69 @@ __device__ __forceinline__ int* gn_counters(float* ws, int n_img, int G) {
   return reinterpret_cast<int*>(ws + (size_t)n_img * GN_MAX_SPLIT * G * 2 + (size_t)n_img * 2 * GN_MAX_C);
 }
 
+// Merge the slab partials of image n (Chan's formula as two weighted sums over the slabs, slab order fixed) and write the
+// per-channel scale / shift to ab[c] / ab[ab_stride + c] (global or shared).  Latency-bound: every lane first issues ALL
+// of its partial loads (<= 8 independent 8-byte loads), so the merge costs one L2 round trip instead of one per slab batch.
+// A group is handled by `lpg` lanes (16 when there are more groups than warps: two groups per warp, one pass).
+__device__ __forceinline__ void gn_merge_groups(const float* partial, int n, int G, int split, int per, int hw, int cpg, float eps,
+                                                const __half* __restrict__ gamma, const __half* __restrict__ beta, float* ab,
+                                                int ab_stride) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  const int lpg = G > nwarps ? 16 : 32, gpw = 32 / lpg;
+  const int sub = lane / lpg, l = lane - sub * lpg;
+  constexpr int MAXI = GN_MAX_SPLIT / 16;
+  for (int gb = warp * gpw; gb < G; gb += nwarps * gpw) {     // warp-uniform trip count
+    const int g = gb + sub;
+    const bool gv = g < G;
+    float cnt_s[MAXI], mu_s[MAXI], m2_s[MAXI];
+#pragma unroll
+    for (int i = 0; i < MAXI; ++i) {
+      const int s2 = l + lpg * i;
+      const bool v = gv && s2 < split;
+      const int q0 = s2 * per, q1 = min(hw, q0 + per);
+      cnt_s[i] = v ? (float)max(q1 - q0, 0) * (float)cpg : 0.f;
+      float2 pm = make_float2(0.f, 0.f);
+      if (v) pm = __ldcg(reinterpret_cast<const float2*>(partial + (((size_t)n * GN_MAX_SPLIT + s2) * G + g) * 2));
+      mu_s[i] = pm.x;
+      m2_s[i] = pm.y;
+    }
+    float wsum = 0.f, wmean = 0.f;
+#pragma unroll
+    for (int i = 0; i < MAXI; ++i) {
+      wsum += cnt_s[i];
+      wmean = fmaf(cnt_s[i], mu_s[i], wmean);
+    }
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1) {     // offsets < 16 stay inside a 16-lane half; the 32-lane case adds offset 16 below
+      wsum += __shfl_xor_sync(0xffffffffu, wsum, o);
+      wmean += __shfl_xor_sync(0xffffffffu, wmean, o);
+    }
+    if (lpg == 32) {
+      wsum += __shfl_xor_sync(0xffffffffu, wsum, 16);
+      wmean += __shfl_xor_sync(0xffffffffu, wmean, 16);
+    }
+    const float mean = wsum > 0.f ? wmean / wsum : 0.f;
+    float m2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < MAXI; ++i) {
+      const float d = mu_s[i] - mean;
+      m2 += m2_s[i] + cnt_s[i] * d * d;
+    }
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1) m2 += __shfl_xor_sync(0xffffffffu, m2, o);
+    if (lpg == 32) m2 += __shfl_xor_sync(0xffffffffu, m2, 16);
+    if (gv) {
+      const float rstd = rsqrtf(m2 / wsum + eps);
+      for (int i = l; i < cpg; i += lpg) {
+        const int c = g * cpg + i;
+        const float ga = __half2float(gamma[c]) * rstd;
+        ab[c] = ga;
+        ab[ab_stride + c] = __half2float(beta[c]) - mean * ga;
+      }
+    }
+  }
+}
+
 __global__ void __launch_bounds__(512) groupnorm_stats_kernel(GnSrc src, const __half* __restrict__ gamma,
                                                                const __half* __restrict__ beta, float* __restrict__ ws,
                                                                int hw, int G, int split, float eps) {
@@ -177,64 +240,7 @@ __global__ void __launch_bounds__(512) groupnorm_stats_kernel(GnSrc src, const _
   __syncthreads();
   if (!s_last) return;
   __threadfence();
-  // Merge (Chan's formula as two weighted sums over the slabs).  Latency-bound: every lane first issues ALL of its
-  // partial loads (<= 8 independent 8-byte loads), so the merge costs one L2 round trip instead of one per slab batch.
-  // A group is handled by `lpg` lanes (16 when there are more groups than warps: two groups per warp, one pass).
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
-  float* ab = gn_ab(ws, n_img, G, n);
-  const int lpg = G > nwarps ? 16 : 32, gpw = 32 / lpg;
-  const int sub = lane / lpg, l = lane - sub * lpg;
-  constexpr int MAXI = GN_MAX_SPLIT / 16;
-  for (int gb = warp * gpw; gb < G; gb += nwarps * gpw) {     // warp-uniform trip count
-    const int g = gb + sub;
-    const bool gv = g < G;
-    float cnt_s[MAXI], mu_s[MAXI], m2_s[MAXI];
-#pragma unroll
-    for (int i = 0; i < MAXI; ++i) {
-      const int s2 = l + lpg * i;
-      const bool v = gv && s2 < split;
-      const int q0 = s2 * per, q1 = min(hw, q0 + per);
-      cnt_s[i] = v ? (float)max(q1 - q0, 0) * (float)cpg : 0.f;
-      float2 pm = make_float2(0.f, 0.f);
-      if (v) pm = __ldcg(reinterpret_cast<const float2*>(partial + (((size_t)n * GN_MAX_SPLIT + s2) * G + g) * 2));
-      mu_s[i] = pm.x;
-      m2_s[i] = pm.y;
-    }
-    float wsum = 0.f, wmean = 0.f;
-#pragma unroll
-    for (int i = 0; i < MAXI; ++i) {
-      wsum += cnt_s[i];
-      wmean = fmaf(cnt_s[i], mu_s[i], wmean);
-    }
-#pragma unroll
-    for (int o = 8; o > 0; o >>= 1) {     // offsets < 16 stay inside a 16-lane half; the 32-lane case adds offset 16 below
-      wsum += __shfl_xor_sync(0xffffffffu, wsum, o);
-      wmean += __shfl_xor_sync(0xffffffffu, wmean, o);
-    }
-    if (lpg == 32) {
-      wsum += __shfl_xor_sync(0xffffffffu, wsum, 16);
-      wmean += __shfl_xor_sync(0xffffffffu, wmean, 16);
-    }
-    const float mean = wsum > 0.f ? wmean / wsum : 0.f;
-    float m2 = 0.f;
-#pragma unroll
-    for (int i = 0; i < MAXI; ++i) {
-      const float d = mu_s[i] - mean;
-      m2 += m2_s[i] + cnt_s[i] * d * d;
-    }
-#pragma unroll
-    for (int o = 8; o > 0; o >>= 1) m2 += __shfl_xor_sync(0xffffffffu, m2, o);
-    if (lpg == 32) m2 += __shfl_xor_sync(0xffffffffu, m2, 16);
-    if (gv) {
-      const float rstd = rsqrtf(m2 / wsum + eps);
-      for (int i = l; i < cpg; i += lpg) {
-        const int c = g * cpg + i;
-        const float ga = __half2float(gamma[c]) * rstd;
-        ab[c] = ga;
-        ab[GN_MAX_C + c] = __half2float(beta[c]) - mean * ga;
-      }
-    }
-  }
+  gn_merge_groups(partial, n, G, split, per, hw, cpg, eps, gamma, beta, gn_ab(ws, n_img, G, n), GN_MAX_C);
 }
 
 // Apply: y = act(x * scale_c + shift_c); mode 0 writes NHWC, mode 1 writes the 3x3 im2col matrix (pad 1, given
@@ -298,6 +304,179 @@ __global__ void __launch_bounds__(256) groupnorm_apply_kernel(const GnApplyParam
       }
       *reinterpret_cast<uint4*>(p.y + ((size_t)n * ho * wo + opix) * K + (size_t)tap * C + ch * 8) = o;
     }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// One-kernel GroupNorm (mode 0): grid (split, N) with split * N <= #SMs, so every CTA is resident at once and the grid can
+// meet at a barrier in global memory.  Each CTA pulls its slab of pixels x all channels into shared memory with ONE bulk
+// copy per source tensor (cp.async.bulk, the slab is contiguous in NHWC), reduces it to per-group (mean, M2) partials in
+// the same fixed order as the statistics kernel, publishes them, waits until the other slabs of its image have done the
+// same, merges the partials itself (every CTA computes the identical scale / shift -- no broadcast step) and normalises
+// its slab out of shared memory.  The activation is read from HBM/L2 once, and one launch plus the scale/shift round trip
+// through global memory are gone.  Bit-identical to the two-kernel path when `split` is the same; deterministic always.
+// ---------------------------------------------------------------------------------------------
+struct GnFusedParams {
+  GnSrc src;
+  const __half* gamma;
+  const __half* beta;
+  __half* y;
+  float* ws;
+  int hw, G, split, per, silu;
+  float eps;
+};
+
+__device__ __forceinline__ uint32_t gn_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__global__ void __launch_bounds__(512) groupnorm_fused_kernel(const GnFusedParams p) {
+  extern __shared__ __align__(128) uint8_t gsm[];
+  __shared__ __align__(8) uint64_t s_bar;
+  const int c1 = p.src.c1, c2 = p.src.c2, C = c1 + c2, nch = C >> 3, nch1 = c1 >> 3;
+  const int n = blockIdx.y, sp = blockIdx.x, n_img = gridDim.y;
+  const int p0 = sp * p.per, p1 = min(p.hw, p0 + p.per), npix = p1 - p0;
+  const int R = blockDim.x / nch;  // pixel lanes
+  __half* slab1 = reinterpret_cast<__half*>(gsm);
+  __half* slab2 = slab1 + (size_t)p.per * c1;
+  float* s_sum = reinterpret_cast<float*>(gsm + (((size_t)p.per * C * 2 + 127) & ~(size_t)127));   // [R][C]
+  float* s_sq = s_sum + (size_t)R * C;                                                             // [R][C]
+  const uint32_t bar = gn_smem_u32(&s_bar);
+  pdl_launch();
+  if (threadIdx.x == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  pdl_wait();   // the activation belongs to the previous kernel until here
+  if (threadIdx.x == 0) {
+    const uint32_t b1 = (uint32_t)npix * c1 * 2, b2 = (uint32_t)npix * c2 * 2;
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(b1 + b2) : "memory");
+    constexpr uint32_t PIECE = 32768;   // bulk copies in <= 32 KB pieces
+    const uint8_t* g1 = reinterpret_cast<const uint8_t*>(p.src.x1 + ((size_t)n * p.hw + p0) * c1);
+    for (uint32_t o = 0; o < b1; o += PIECE) {
+      const uint32_t sz = min(PIECE, b1 - o);
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                       gn_smem_u32(slab1) + o),
+                   "l"(g1 + o), "r"(sz), "r"(bar)
+                   : "memory");
+    }
+    if (c2 > 0) {
+      const uint8_t* g2 = reinterpret_cast<const uint8_t*>(p.src.x2 + ((size_t)n * p.hw + p0) * c2);
+      for (uint32_t o = 0; o < b2; o += PIECE) {
+        const uint32_t sz = min(PIECE, b2 - o);
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                         gn_smem_u32(slab2) + o),
+                     "l"(g2 + o), "r"(sz), "r"(bar)
+                     : "memory");
+      }
+    }
+  }
+  __syncthreads();   // barrier initialised before anyone polls it
+  {
+    uint32_t done = 0, spins = 0;
+    while (true) {
+      asm volatile(
+          "{\n\t.reg .pred q;\n\t"
+          "mbarrier.try_wait.parity.shared::cta.b64 q, [%1], 0;\n\t"
+          "selp.u32 %0, 1, 0, q;\n\t}"
+          : "=r"(done)
+          : "r"(bar)
+          : "memory");
+      if (done) break;
+      if (++spins > (1u << 26)) __trap();   // never hang the GPU on a protocol bug
+    }
+  }
+  auto slab_chunk = [&](int pix, int ch) -> uint4 {   // 8 channels of pixel `pix` of the slab
+    return ch < nch1 ? *reinterpret_cast<const uint4*>(slab1 + (size_t)pix * c1 + ch * 8)
+                     : *reinterpret_cast<const uint4*>(slab2 + (size_t)pix * c2 + (ch - nch1) * 8);
+  };
+  const int r = threadIdx.x / nch, ch = threadIdx.x - r * nch;
+  if (r < R) {
+    float a[8] = {0, 0, 0, 0, 0, 0, 0, 0}, b[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    // same per-thread pixel order as groupnorm_stats_kernel (r, r + R, r + 2R, ...): same sums bit for bit
+    for (int q = r; q < npix; q += R) {
+      float v[8];
+      unpack8(slab_chunk(q, ch), v);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        a[e] += v[e];
+        b[e] = fmaf(v[e], v[e], b[e]);
+      }
+    }
+    float* ds = s_sum + (size_t)r * C + ch * 8;
+    float* dq = s_sq + (size_t)r * C + ch * 8;
+    *reinterpret_cast<float4*>(ds) = make_float4(a[0], a[1], a[2], a[3]);
+    *reinterpret_cast<float4*>(ds + 4) = make_float4(a[4], a[5], a[6], a[7]);
+    *reinterpret_cast<float4*>(dq) = make_float4(b[0], b[1], b[2], b[3]);
+    *reinterpret_cast<float4*>(dq + 4) = make_float4(b[4], b[5], b[6], b[7]);
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float ts = s_sum[c], tq = s_sq[c];
+    for (int r2 = 1; r2 < R; ++r2) {
+      ts += s_sum[(size_t)r2 * C + c];
+      tq += s_sq[(size_t)r2 * C + c];
+    }
+    s_sum[c] = ts;
+    s_sq[c] = tq;
+  }
+  __syncthreads();
+  const int cpg = C / p.G;
+  const float cnt = (float)npix * (float)cpg;
+  float* partial = p.ws;
+  for (int g = threadIdx.x; g < p.G; g += blockDim.x) {
+    float s = 0.f, q = 0.f;
+    for (int i = 0; i < cpg; ++i) {
+      s += s_sum[g * cpg + i];
+      q += s_sq[g * cpg + i];
+    }
+    const float mean = cnt > 0.f ? s / cnt : 0.f;
+    const float m2 = fmaxf(q - s * mean, 0.f);
+    float* o = partial + (((size_t)n * GN_MAX_SPLIT + sp) * p.G + g) * 2;
+    o[0] = mean;
+    o[1] = m2;
+  }
+  // ---- grid barrier over the slabs of image n: arrive, then wait for the others' partials ----
+  int* arrive = gn_counters(p.ws, n_img, p.G) + n;
+  int* depart = gn_counters(p.ws, n_img, p.G) + n_img + n;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    atomicAdd(arrive, 1);
+    uint32_t spins = 0;
+    while (true) {
+      int seen;
+      asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(seen) : "l"(arrive) : "memory");
+      if (seen >= p.split) break;
+      __nanosleep(32);
+      if (++spins > (1u << 24)) __trap();   // a slab that is not resident would be a launch-geometry bug: fail, do not hang
+    }
+  }
+  __syncthreads();
+  // every CTA merges the partials of its image itself (scale / shift land in shared memory, over the reduction scratch)
+  float* ab = s_sum;
+  gn_merge_groups(partial, n, p.G, p.split, p.per, p.hw, cpg, p.eps, p.gamma, p.beta, ab, C);
+  __syncthreads();
+  if (threadIdx.x == 0) {   // the last CTA of the image to get here re-arms the two counters for the next launch
+    const int prev = atomicAdd(depart, 1);
+    if (prev == p.split - 1) {
+      *arrive = 0;
+      *depart = 0;
+    }
+  }
+  const int total = npix * nch;
+  for (int i = threadIdx.x; i < total; i += blockDim.x) {
+    const int q = i / nch, c8 = i - q * nch;
+    float v[8];
+    unpack8(slab_chunk(q, c8), v);
+    const float4 a0 = *reinterpret_cast<const float4*>(ab + c8 * 8), a1 = *reinterpret_cast<const float4*>(ab + c8 * 8 + 4);
+    const float4 b0 = *reinterpret_cast<const float4*>(ab + C + c8 * 8), b1 = *reinterpret_cast<const float4*>(ab + C + c8 * 8 + 4);
+    const float A[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+    const float B[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const float t = fmaf(v[e], A[e], B[e]);
+      v[e] = p.silu ? silu_f(t) : t;
+    }
+    *reinterpret_cast<uint4*>(p.y + ((size_t)n * p.hw + p0 + q) * C + c8 * 8) = pack8(v);
   }
 }
 
@@ -412,6 +591,33 @@ int groupnorm_launch(const __half* x1, int c1, const __half* x2, int c2, const _
   const int split = pick_split(hw, nch > 0 ? nch : 1, threads);
   GnSrc src{x1, x2, c1, c2};
   if (nch > threads || C > GN_MAX_C) return fail(L2D_ERR_INVALID, "groupnorm: C > 4096");
+  // ---- one-kernel path: every slab of every image resident at once (grid <= #SMs), slab + scratch in shared memory ----
+  static const int fused_on = [] { const char* e = getenv("L2D_GN_FUSED"); return e ? atoi(e) : 1; }();
+  static int num_sms = 0;
+  if (num_sms == 0) {
+    int dev = 0;
+    L2D_CUDA(cudaGetDevice(&dev));
+    L2D_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
+  }
+  if (fused_on && mode == 0 && nch > 0 && n_img <= num_sms && ((c1 | c2) & 7) == 0) {
+    int fs = std::min(std::min(num_sms / n_img, GN_MAX_SPLIT), hw);
+    const int per = (hw + fs - 1) / fs;
+    fs = (hw + per - 1) / per;   // no empty slabs
+    const int lanes_f = threads / nch;
+    const size_t slab = ((size_t)per * C * 2 + 127) & ~(size_t)127;
+    const size_t fsmem = slab + std::max((size_t)2 * lanes_f * C, (size_t)2 * C) * sizeof(float);
+    if (fsmem <= 200 * 1024) {
+      static size_t cfg_fused = 0;
+      if (fsmem > 48 * 1024 && fsmem > cfg_fused) {
+        L2D_CUDA(cudaFuncSetAttribute(groupnorm_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        cfg_fused = 200 * 1024;
+      }
+      GnFusedParams fp{src, gamma, beta, y, ws, hw, G, fs, per, silu, eps};
+      launch_pdl_if(pdl_family(4), groupnorm_fused_kernel, dim3(fs, n_img), dim3(threads), fsmem, st, fp);
+      L2D_LAUNCH_CHECK();
+      return L2D_OK;
+    }
+  }
   static size_t cfg_stats = 0;
   const int lanes = threads / (nch > 0 ? nch : 1) > 0 ? threads / (nch > 0 ? nch : 1) : 1;
   const size_t smem = (size_t)2 * lanes * C * sizeof(float);   // <= 32 KB: lanes * C <= 8 * threads
@@ -448,7 +654,7 @@ extern "C" int l2d_layernorm(const void* x, const void* gamma, const void* beta,
 
 extern "C" int64_t l2d_groupnorm_workspace_bytes(int n_img, int groups) {
   return ((int64_t)n_img * GN_MAX_SPLIT * groups * 2 + (int64_t)n_img * 2 * GN_MAX_C) * sizeof(float) +
-         (int64_t)n_img * sizeof(int) + 64;
+         (int64_t)2 * n_img * sizeof(int) + 64;   // counters: arrive [N] | depart [N]
 }
 
 extern "C" int l2d_groupnorm(const void* x1, int c1, const void* x2, int c2, const void* gamma, const void* beta,

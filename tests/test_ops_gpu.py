@@ -122,6 +122,24 @@ def test_groupnorm_nhwc(n, c, h, w, silu, eps):
     strict(ops.groupnorm(_nhwc(x), g, b, n, h, w, 32, eps, silu=silu), _nhwc(ref), "groupnorm")
 
 
+@pytest.mark.parametrize("n,c1,c2,h,w", [(2, 640, 320, 32, 32), (2, 640, 320, 64, 64), (4, 320, 0, 64, 64), (2, 1280, 1280, 16, 16),
+                                         (1, 320, 0, 64, 64), (3, 64, 0, 5, 7), (2, 1280, 640, 32, 32), (2, 320, 0, 96, 64)])
+def test_groupnorm_one_kernel_path(n, c1, c2, h, w):
+    """NHWC output (no im2col) takes the one-kernel path when every slab of every image can be resident at once: slab in
+    shared memory via bulk copies, partial statistics, a grid barrier per image, merge + normalise from shared memory.
+    Shapes: concat sources, the largest level-0 slab (960 channels), four images, odd pixel counts, config 3's plane."""
+    from live2diff_b200 import ops
+
+    x1, x2 = rnd(n, c1, h, w, seed=41, scale=1.3) + 0.2, (rnd(n, c2, h, w, seed=42) - 0.4 if c2 else None)
+    x = x1 if x2 is None else torch.cat([x1, x2], dim=1)
+    c = c1 + c2
+    g, b = rnd(c, seed=43) * 0.1 + 1, rnd(c, seed=44) * 0.1
+    ref = F.silu(F.group_norm(x.float(), 32, g.float(), b.float(), 1e-5))
+    for _ in range(2):
+        out = ops.groupnorm(_nhwc(x1), g, b, n, h, w, 32, 1e-5, silu=True, x2=None if x2 is None else _nhwc(x2))
+    strict(out, _nhwc(ref), f"groupnorm one-kernel n{n} c{c1}+{c2} {h}x{w}")
+
+
 def _im2col_ref(x_nchw, stride=1):
     """[N,C,H,W] -> [N*Ho*Wo, 9*C] with columns ordered (tap, channel) -- the engine's weight repack order."""
     n, c, h, w = x_nchw.shape
@@ -271,6 +289,36 @@ def test_attention_fused_qkv_views(hd, sq):
     ref16 = F.scaled_dot_product_attention(split(q), split(k), split(v))
     merge = lambda t: t.transpose(1, 2).reshape(b * sq, c)
     referee(out, merge(ref32), merge(ref16), f"attention fused-qkv views hd{hd} s{sq}")
+
+
+@pytest.mark.parametrize("hd,sq,skv", [(40, 512, 1024), (80, 256, 640), (40, 256, 333)])
+@pytest.mark.parametrize("growth", [0.25, 2.0, 12.0])
+def test_attention_row_max_grows_across_key_tiles(hd, sq, skv, growth):
+    """The tcgen05 kernel exponentiates key tile j against the row max of the EARLIER tiles and only redoes a tile when a
+    row outgrows that reference by more than 2^8.  Keys whose scale rises tile after tile drive the row max up by `growth`
+    (log2 units of the scaled score, roughly) per 128-key tile: 0.25 and 2 stay on the stale-reference path, 12 forces
+    the redo (O and l rescaled in TMEM) on most tiles; a few rows also get one dominant late key."""
+    from live2diff_b200 import ops
+
+    b, heads = 2, 8
+    c = heads * hd
+    q, v = rnd(b * sq, c, seed=31), rnd(b * skv, c, seed=33)
+    k = rnd(b * skv, c, seed=32).float()
+    q = (q.float() * 0 + torch.sign(q.float())).half()          # +-1 queries: score = sum of +-k, spread ~ sqrt(hd) * |k|
+    tile = (torch.arange(b * skv, device=k.device) % skv) // 128
+    k = k * (growth * (tile.float() + 1.0) * 0.7)[:, None]       # score scale grows linearly with the key tile index
+    k[skv - 3] *= 3.0                                             # one dominant key in the last tile of image 0
+    k = k.half()
+    out = ops.attention(q, k, v, b, heads, sq, skv, hd)
+
+    def split(t, s):
+        return t.view(b, s, heads, hd).transpose(1, 2)
+
+    ref32 = F.scaled_dot_product_attention(split(q.float(), sq), split(k.float(), skv), split(v.float(), skv))
+    ref16 = F.scaled_dot_product_attention(split(q, sq), split(k, skv), split(v, skv))
+    merge = lambda t: t.transpose(1, 2).reshape(b * sq, c)
+    assert torch.isfinite(out.float()).all()
+    referee(out, merge(ref32), merge(ref16), f"attention growing max x{growth} hd{hd} s{sq}x{skv}")
 
 
 def test_gemm_splitk_workspace_is_restored():
