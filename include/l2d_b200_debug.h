@@ -26,6 +26,11 @@ void l2d_unet_set_ablation(l2d_unet* u, int family_mask);
 void l2d_stream_invalidate_graph(l2d_stream* s);
 /* Resident CTAs per SM of the tcgen05 spatial-attention kernel (head_dim 40 -> 2 expected, 80 -> 1). */
 int l2d_debug_flash_ctas_per_sm(int hd);
+/* When non-NULL, CTA (0,0,0) of the tcgen05 attention kernel writes clock64() stamps of its first 16 key tiles:
+ * timeline[(w*16 + j)*8 + k] for softmax warp w (0..7; 0-3 = query tile 0) -- k = 0 tile start, 1 S_j available, 2 scores in
+ * registers, 3 max / lazy check / P.V wait done, 4 exp token acquired, 5 exponentials issued, 6 P_j handed over -- and
+ * timeline[1024 + (t*16 + j)*2 + {0,1}] = the MMA thread's issue times of S_j and P_j.V_j for query tile t.  >= 1088 int64. */
+void l2d_flash_set_debug(void* timeline);
 
 #ifdef __cplusplus
 }

@@ -102,6 +102,7 @@ DEBUG_SIGNATURES = {
     "l2d_unet_set_ablation": (None, [vp, i32]),
     "l2d_stream_invalidate_graph": (None, [vp]),
     "l2d_debug_flash_ctas_per_sm": (i32, [i32]),
+    "l2d_flash_set_debug": (None, [vp]),
 }
 
 ABI_VERSION = 3

@@ -83,6 +83,25 @@ __device__ __forceinline__ void ft_umma(uint32_t tmem_d, uint64_t desc_a, uint64
       ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// A operand from TMEM (lane = row, one 32-bit column = two consecutive K elements), B from shared memory
+__device__ __forceinline__ void ft_umma_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// one lane of a converged warp (always the lowest: tcgen05.commit tracks the MMAs of the thread that executes it)
+__device__ __forceinline__ bool ft_elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void ft_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
@@ -140,11 +159,15 @@ __host__ __device__ constexpr uint32_t ft_idesc(int n, int b_mn_major) {
   return (1u << 4) | ((uint32_t)b_mn_major << 16) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
 }
 
+long long* g_ft_dbg = nullptr;   // l2d_flash_set_debug
+
 struct FtParams {
   __half* o;
   int64_t ldo;
   int sq, skv, heads;
   float scale_log2;   // log2(e) / sqrt(hd)
+  int pingpong;       // NQ == 2: the two query tiles take turns on the MUFU pipe (L2D_FLASH_PINGPONG, default 1)
+  long long* dbg;     // developer timeline of CTA (0,0,0), see l2d_flash_set_debug; nullptr = off
 };
 
 constexpr int FT_TILE = 128 * 128;   // bytes of one [128 rows x 64 fp16] swizzled block
@@ -163,11 +186,11 @@ struct FtCfg {
   static constexpr int ON_MMA = NBLK * 64;          // MMA N of P.V: whole 64-channel swizzle atoms of the V tile
   static constexpr int STAGES = 2;                  // K / V ring depth
   static constexpr int SBUF = 2 / NQ;               // S accumulators per query tile (NQ * SBUF = 2 x 128 TMEM columns)
-  static constexpr int TMEM_COLS = 512;             // S: 256, T: NQ x ON_MMA <= 256
+  static constexpr int TMEM_COLS = 512;             // S: 256 | O: NQ x ON_MMA <= 128 | P (fp16 pairs): NQ x 64
   static constexpr int THREADS = 64 + NQ * 128;     // TMA warp, MMA warp, 4 softmax warps per query tile
   static constexpr int TILE_BYTES = NBLK * FT_TILE;
-  static constexpr int SMEM = TILE_BYTES * (NQ + 2 * STAGES) + NQ * 2 * FT_TILE /* P */ + 256 /* barriers */ + 1024 /* align */;
-  static_assert(NQ * ON_MMA <= 256 && (NQ == 1 || NQ == 2), "TMEM layout");
+  static constexpr int SMEM = TILE_BYTES * (NQ + 2 * STAGES) + 256 /* barriers */ + 1024 /* align */;
+  static_assert(NQ * ON_MMA <= 128 && (NQ == 1 || NQ == 2), "TMEM layout");
 };
 
 template <int HD, int NQ>
@@ -181,8 +204,7 @@ flash_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
   uint8_t* sQ = smem;                                  // [NQ] query tiles
   uint8_t* sK = sQ + NQ * Cfg::TILE_BYTES;
   uint8_t* sV = sK + ST * Cfg::TILE_BYTES;
-  uint8_t* sP = sV + ST * Cfg::TILE_BYTES;             // [NQ] P tiles of 2 x 16 KB
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + NQ * 2 * FT_TILE);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sV + ST * Cfg::TILE_BYTES);
   const uint32_t bar0 = ft_smem_u32(bars);
   // barrier map: q_full, q_ready | per query tile t: p_full, o_full, (unused), s_full[2], s_empty[2] | k/v full/empty[ST]
   const uint32_t q_full = bar0, q_ready = bar0 + 8;
@@ -236,6 +258,7 @@ flash_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
   // TMEM columns: S accumulator (tile t, buffer a) at (t * SBUF + a) * 128; T of tile t at 256 + t * ON_MMA
   auto tm_s = [&](int t, int a) { return (uint32_t)((t * SBUF + a) * 128); };
   auto tm_o = [&](int t) { return (uint32_t)(256 + t * Cfg::ON_MMA); };
+  auto tm_p = [&](int t) { return (uint32_t)(384 + t * 64); };   // P_j as fp16 pairs: 128 keys = 64 columns
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -265,44 +288,56 @@ flash_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
+    // The WHOLE warp walks the loop (convergent control flow) and one elected lane executes the tcgen05 instructions, so the
+    // descriptor arithmetic stays in uniform registers; inside an `if (lane == 0)` region the compiler wraps every UTCHMMA
+    // in a per-lane waterfall loop, and the timeline showed this thread -- ~150 cycles per MMA against a tensor-core floor
+    // of 32-64 -- pacing the whole kernel.
+    {
+      long long* mdbg = (p.dbg && lane == 0 && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) ? p.dbg + 8 * 16 * 8 : nullptr;
       constexpr uint32_t idesc_s = ft_idesc(128, 0);
       constexpr uint32_t idesc_o = ft_idesc(Cfg::ON_MMA, 1);
+      const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
       auto issue_s = [&](int t, int j) {
         const int s = j % ST, a = j % SBUF;
         if (t == 0) ft_mbar_wait(k_full(s), (uint32_t)(j / ST) & 1u);
         ft_mbar_wait(s_empty(t, a), ((uint32_t)(j / SBUF) & 1u) ^ 1u);   // the softmax has drained this S accumulator (tile j-SBUF)
         ft_tc_fence_after();
         const uint32_t qa = ft_smem_u32(sQ + t * Cfg::TILE_BYTES), ka = ft_smem_u32(sK + s * Cfg::TILE_BYTES);
+        if (ft_elect_one()) {
 #pragma unroll
-        for (int k = 0; k < KSTEPS; ++k) {
-          const uint32_t off = (uint32_t)(k >> 2) * FT_TILE + (uint32_t)(k & 3) * 32;
-          ft_umma(tmem_base + tm_s(t, a), ft_desc(qa + off, 0), ft_desc(ka + off, 0), idesc_s, k != 0);
+          for (int k = 0; k < KSTEPS; ++k) {
+            const uint32_t off = (uint32_t)(k >> 2) * FT_TILE + (uint32_t)(k & 3) * 32;
+            ft_umma(tmem_u + tm_s(t, a), ft_desc(qa + off, 0), ft_desc(ka + off, 0), idesc_s, k != 0);
+          }
+          if (t == NQ - 1) ft_commit(k_empty(s));   // every query tile has read K_j
+          ft_commit(s_full(t, a));
         }
-        if (t == NQ - 1) ft_commit(k_empty(s));   // every query tile has read K_j
-        ft_commit(s_full(t, a));
+        __syncwarp();
+        if (mdbg && j < 16) mdbg[(t * 16 + j) * 2] = clock64();       // S_j issued
       };
       auto issue_pv = [&](int t, int j) {
         const int s = j % ST;
         if (t == 0) ft_mbar_wait(v_full(s), (uint32_t)(j / ST) & 1u);
         ft_mbar_wait(p_full(t), (uint32_t)j & 1u);
         ft_tc_fence_after();
-        const uint32_t pa = ft_smem_u32(sP + t * 2 * FT_TILE), va = ft_smem_u32(sV + s * Cfg::TILE_BYTES);
+        const uint32_t va = ft_smem_u32(sV + s * Cfg::TILE_BYTES);
+        if (ft_elect_one()) {
 #pragma unroll
-        for (int kk = 0; kk < 8; ++kk) {   // 128 keys = 8 k16 steps: P block kk/4, +32 B per step; V: 16 key rows = 2 KB per step
-          const uint64_t da = ft_desc(pa + (uint32_t)(kk >> 2) * FT_TILE + (uint32_t)(kk & 3) * 32, 0);
-          const uint64_t db = ft_desc(va + (uint32_t)kk * 2048, FT_TILE);
-          ft_umma(tmem_base + tm_o(t), da, db, idesc_o, (j | kk) != 0);   // O accumulates across the key tiles
+          for (int kk = 0; kk < 8; ++kk) {   // 128 keys = 8 k16 steps: P +8 TMEM columns per step; V: 16 key rows = 2 KB per step
+            const uint64_t db = ft_desc(va + (uint32_t)kk * 2048, FT_TILE);
+            ft_umma_ts(tmem_u + tm_o(t), tmem_u + tm_p(t) + (uint32_t)kk * 8, db, idesc_o, (j | kk) != 0);   // O accumulates across the key tiles
+          }
+          if (t == NQ - 1) ft_commit(v_empty(s));   // every query tile has read V_j
+          ft_commit(o_full(t));
         }
-        if (t == NQ - 1) ft_commit(v_empty(s));   // every query tile has read V_j
-        ft_commit(o_full(t));
+        __syncwarp();
+        if (mdbg && j < 16) mdbg[(t * 16 + j) * 2 + 1] = clock64();   // P_j . V_j issued
       };
       ft_mbar_wait(q_ready, 0);
       for (int t = 0; t < NQ; ++t) issue_s(t, 0);
       for (int j = 0; j < nk; ++j) {
         for (int t = 0; t < NQ; ++t) {
-          // (with one S buffer per tile this waits until the softmax of tile j has read S_j for the last time -- about two
-          //  thirds into its tile -- so S_{j+1} is still ready before the softmax threads come back for it)
+          // S_{j+1} first: its accumulator was handed back when the softmax pulled S_j into registers, P_j comes later
           if (j + 1 < nk) issue_s(t, j + 1);
           issue_pv(t, j);
         }
@@ -315,7 +350,6 @@ flash_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
     const int r = q * 32 + lane;               // query row inside the tile
     const uint32_t t_lane = tmem_base + ((uint32_t)(q * 32) << 16);
     uint8_t* myQ = sQ + t * Cfg::TILE_BYTES;
-    uint8_t* myP = sP + t * 2 * FT_TILE;
     ft_mbar_wait(q_full, 0);
     if (HD % 16 != 0) {   // zero columns HD .. KSTEPS*16-1 of this row (hd = 40: chunk 5 of block 0)
       constexpr int chunk = HD / 8;
@@ -325,122 +359,77 @@ flash_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
     __syncwarp();
     if (lane == 0) ft_mbar_arrive(q_ready);
 
-    // Online softmax with a LAZY reference (flash-attention 4's conditional rescale).  The kernel is bound by the TMEM read
-    // port (64 B / clk / SM) as much as by MUFU: reading S twice (row max, then exp) plus the P.V tile every key tile is
-    // 152 KB = 2375 cycles per 128 x 128 tile, which is what the two-pass version measured.  So S is read ONCE: tile j is
-    // exponentiated against the reference m_ref the row already has (the max of the earlier tiles) while its own max is
-    // tracked on the side; only if some row of the warp exceeds its reference by more than 2^LAZY is the tile redone
-    // against the new max (P <= 2^8 fits fp16 with the same relative precision, l and O are fp32).  And O is accumulated
-    // by the tensor core in TMEM across key tiles (accumulate flag), not folded through registers: it is touched by the
-    // softmax threads only on such a redo (O *= 2^(m_old - m_new), l likewise) and once at the end.
+    // Online softmax with a LAZY reference (flash-attention 4's conditional rescale).  A tile's scores (128 fp32 per row) are
+    // pulled from TMEM into registers in one go -- S is read exactly once and its accumulator goes back to the tensor core
+    // at the START of the tile, so S_{j+1} = Q.K^T runs under the exp pass of tile j instead of after it (the ncu stall
+    // profile of the version that kept S in TMEM until the end of the pass had the softmax warps waiting on s_full for a
+    // quarter of all samples).  The exp uses the reference m_ref the row already has (the max of the earlier tiles) unless
+    // some row of the warp exceeds its reference by more than 2^LAZY; only then are O (in TMEM, accumulated by the tensor
+    // core across all key tiles) and l rescaled to the new max.  P <= 2^8 fits fp16 with the same relative precision; l and
+    // O are fp32.
     float m_ref = -INFINITY, l_run = 0.f;
     const float c = p.scale_log2;
     constexpr float LAZY = 8.f;
     const uint32_t o_addr = t_lane + tm_o(t);
+    // NQ == 2: a tile's work has two phases that use different units -- pulling 64 KB of scores through the TMEM read port
+    // (64 B / clk / SM: ~1000 cycles for the tile's four warps) and 16 K exponentials on the MUFU pipe (16 / clk / SM: ~1000
+    // cycles).  Left alone the two query tiles drift into phase, contend for one unit and then for the other (measured:
+    // the sum of both).  A token passed through two named barriers between warp w of tile 0 and warp w + 4 of tile 1 (same
+    // scheduler) makes the exp phases alternate strictly, so one tile's loads run under the other's exponentials
+    // (flash-attention 3's ping-pong schedule).
+    const int bar_mine = 1 + t * 4 + (warp & 3), bar_other = 1 + (t ^ 1) * 4 + (warp & 3);
+    const bool pp = NQ == 2 && p.pingpong;
+    if (pp && t == 1) asm volatile("bar.arrive %0, 64;" ::"r"(bar_other) : "memory");   // tile 0 goes first
 
+    long long* dbg = (p.dbg && lane == 0 && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) ? p.dbg + (warp - 2) * 16 * 8 : nullptr;
     for (int j = 0; j < nk; ++j) {
       const int a = j % SBUF;
       const int nvalid = min(128, p.skv - j * 128);
+      long long* stamp = (dbg && j < 16) ? dbg + j * 8 : nullptr;
+      if (stamp) stamp[0] = clock64();   // tile start
       ft_mbar_wait(s_full(t, a), (uint32_t)(j / SBUF) & 1u);
       ft_tc_fence_after();
+      if (stamp) stamp[1] = clock64();   // S_j available
       const uint32_t s_addr = t_lane + tm_s(t, a);
-      // Every pass exists twice: the full-tile version has NO per-element bounds checks (they doubled the instruction
-      // count of the hot loop when they were predicated in), the masked one runs for the last key tile only.
-      float mx = -INFINITY, mneg = 0.f, rs = 0.f;
-      bool p_free = j == 0;   // P_{j-1} has been consumed by the tensor core (first store of this tile waits for it)
-      uint32_t va[32], vb[32];
-      auto row_max = [&](auto masked) {   // first key tile only: there is no reference yet, take the tile's true max
-        constexpr bool MASKED = decltype(masked)::value;
-#pragma unroll 1
-        for (int cc = 0; cc < 2; ++cc) {
-          ft_tmem_ld32(s_addr + cc * 64, va);
-          ft_tmem_ld32(s_addr + cc * 64 + 32, vb);
-          ft_tmem_ld_wait();
+      uint32_t v0[32], v1[32], v2[32], v3[32];
+      ft_tmem_ld32(s_addr, v0);
+      ft_tmem_ld32(s_addr + 32, v1);
+      ft_tmem_ld32(s_addr + 64, v2);
+      ft_tmem_ld32(s_addr + 96, v3);
+      ft_tmem_ld_wait();
+      if (stamp) stamp[2] = clock64();   // scores in registers
+      // the scores are in registers: hand the accumulator back (tile j + SBUF may overwrite it)
+      ft_tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ft_mbar_arrive(s_empty(t, a));
+      if (nvalid < 128) {   // last tile of a ragged key length (cross-attention: 77 keys): masked scores never win the max, exp -> 0
 #pragma unroll
-          for (int e = 0; e < 32; ++e) {
-            if (MASKED) {
-              if (cc * 64 + e < nvalid) mx = fmaxf(mx, __uint_as_float(va[e]));
-              if (cc * 64 + 32 + e < nvalid) mx = fmaxf(mx, __uint_as_float(vb[e]));
-            } else {
-              mx = fmaxf(mx, fmaxf(__uint_as_float(va[e]), __uint_as_float(vb[e])));
-            }
-          }
+        for (int e = 0; e < 32; ++e) {
+          if (e >= nvalid) v0[e] = 0xff800000u;
+          if (32 + e >= nvalid) v1[e] = 0xff800000u;
+          if (64 + e >= nvalid) v2[e] = 0xff800000u;
+          if (96 + e >= nvalid) v3[e] = 0xff800000u;
         }
-      };
-      // p = 2^(s*c - m_ref*c), row sum in fp32, P -> fp16 in the UMMA K-major swizzled layout, tile max on the side
-      auto emit = [&](auto masked, const uint32_t (&v)[32], int cc) {
-        constexpr bool MASKED = decltype(masked)::value;
-        uint32_t pk[16];
-#pragma unroll
-        for (int e = 0; e < 32; e += 2) {
-          float p0 = ft_ex2(fmaf(__uint_as_float(v[e]), c, mneg));
-          float p1 = ft_ex2(fmaf(__uint_as_float(v[e + 1]), c, mneg));
-          if (MASKED) {
-            if (cc * 32 + e >= nvalid) p0 = 0.f;
-            if (cc * 32 + e + 1 >= nvalid) p1 = 0.f;
-          }
-          rs += p0 + p1;
-          pk[e >> 1] = h2_as_u32(__floats2half2_rn(p0, p1));
-        }
-        if (!p_free) {   // the tensor core reads P_{j-1} until P_{j-1} . V_{j-1} completes
-          ft_mbar_wait(o_full(t), (uint32_t)(j - 1) & 1u);
-          p_free = true;
-        }
-        // keys cc*32 .. +31 = 16-byte chunks 4cc .. 4cc+3 of this row: block (4cc+i)/8, swizzled chunk ((4cc+i)%8) ^ (r%8)
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const int ch = cc * 4 + i;
-          *reinterpret_cast<uint4*>(myP + (ch >> 3) * FT_TILE + r * 128 + (((ch & 7) ^ (r & 7)) << 4)) =
-              make_uint4(pk[4 * i], pk[4 * i + 1], pk[4 * i + 2], pk[4 * i + 3]);
-        }
-      };
-      auto chunk_max = [&](auto masked, const uint32_t (&v)[32], int cc) {
-        constexpr bool MASKED = decltype(masked)::value;
-#pragma unroll
-        for (int e = 0; e < 32; e += 2) {
-          if (MASKED) {
-            if (cc * 32 + e < nvalid) mx = fmaxf(mx, __uint_as_float(v[e]));
-            if (cc * 32 + e + 1 < nvalid) mx = fmaxf(mx, __uint_as_float(v[e + 1]));
-          } else {
-            mx = fmaxf(mx, fmaxf(__uint_as_float(v[e]), __uint_as_float(v[e + 1])));
-          }
-        }
-      };
-      // chunks 0..2 exponentiated, chunk 3 loaded and included in the max.  TMEM loads are software-pipelined through two
-      // register buffers: chunk cc+1 is in flight while chunk cc is being exponentiated (tcgen05.wait::ld waits for
-      // everything outstanding, so the wait sits AFTER the compute).
-      auto head = [&](auto masked) {
-        ft_tmem_ld32(s_addr, va);
-        ft_tmem_ld_wait();
-        ft_tmem_ld32(s_addr + 32, vb);
-        chunk_max(masked, va, 0);
-        emit(masked, va, 0);
-        ft_tmem_ld_wait();
-        ft_tmem_ld32(s_addr + 64, va);
-        chunk_max(masked, vb, 1);
-        emit(masked, vb, 1);
-        ft_tmem_ld_wait();
-        ft_tmem_ld32(s_addr + 96, vb);
-        chunk_max(masked, va, 2);
-        emit(masked, va, 2);
-        ft_tmem_ld_wait();
-        chunk_max(masked, vb, 3);
-      };
-      if (j == 0) {
-        if (nvalid < 128) row_max(std::true_type{});
-        else row_max(std::false_type{});
-        m_ref = mx;
       }
-      mneg = -m_ref * c;
-      if (nvalid < 128) head(std::true_type{});
-      else head(std::false_type{});
-      if (__any_sync(0xffffffffu, fmaf(mx, c, mneg) > LAZY)) {
-        // some row of this warp outgrew its reference: move every row of the warp to its new max, rescale the history
-        // (rows whose max did not move get the factor 2^0 = 1, exact), and redo the tile.  j > 0 here (tile 0 started
-        // from its true max) and P_{j-1} . V_{j-1} has completed (the first P store waited for it), so O is stable.
+      float mx = -INFINITY;
+#pragma unroll
+      for (int e = 0; e < 32; e += 2) {
+        mx = fmaxf(mx, fmaxf(__uint_as_float(v0[e]), __uint_as_float(v0[e + 1])));
+        mx = fmaxf(mx, fmaxf(__uint_as_float(v1[e]), __uint_as_float(v1[e + 1])));
+        mx = fmaxf(mx, fmaxf(__uint_as_float(v2[e]), __uint_as_float(v2[e + 1])));
+        mx = fmaxf(mx, fmaxf(__uint_as_float(v3[e]), __uint_as_float(v3[e + 1])));
+      }
+      if (j > 0) {   // P_{j-1} . V_{j-1} has completed: P may be overwritten and O is stable
+        ft_mbar_wait(o_full(t), (uint32_t)(j - 1) & 1u);
+        ft_tc_fence_after();
+      }
+      if (j == 0) {
+        m_ref = mx;   // no history yet: the first tile's own max is the reference
+      } else if (__any_sync(0xffffffffu, fmaf(mx, c, -m_ref * c) > LAZY)) {
+        // some row of this warp outgrew its reference: move every row of the warp to its new max and rescale the history
+        // (rows whose max did not move get the factor 2^0 = 1, exact)
         const float m_new = fmaxf(m_ref, mx);
         const float corr = ft_ex2((m_ref - m_new) * c);
-        ft_tc_fence_after();   // (the o_full wait inside the first P store ordered P_{j-1} . V_{j-1} before this point)
 #pragma unroll
         for (int cc = 0; cc < ON / 16; ++cc) {
           uint32_t tt[16];
@@ -451,25 +440,44 @@ flash_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
           ft_tmem_st16(o_addr + cc * 16, tt);
         }
         asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+        ft_tc_fence_before();
         l_run *= corr;
         m_ref = m_new;
-        mneg = -m_ref * c;
-        rs = 0.f;
-        if (nvalid < 128) head(std::true_type{});
-        else head(std::false_type{});
       }
-      // S has been read for the last time: the MMA warp may overwrite it (tile j + SBUF)
-      ft_tc_fence_before();
-      __syncwarp();
-      if (lane == 0) ft_mbar_arrive(s_empty(t, a));
-      if (nvalid < 128) emit(std::true_type{}, vb, 3);
-      else emit(std::false_type{}, vb, 3);
+      const float mneg = -m_ref * c;
+      float rs = 0.f;
+      const uint32_t p_addr = t_lane + tm_p(t);
+      // p = 2^(s*c - m_ref*c), row sum in fp32, P -> fp16 pairs written to TMEM (tcgen05.st: lane = row, column = key pair),
+      // where the tensor core reads it as the A operand of P.V -- P never touches shared memory
+      auto emit = [&](const uint32_t (&v)[32], int cc) {
+        uint32_t pk[16];
+#pragma unroll
+        for (int e = 0; e < 32; e += 2) {
+          const float p0 = ft_ex2(fmaf(__uint_as_float(v[e]), c, mneg));
+          const float p1 = ft_ex2(fmaf(__uint_as_float(v[e + 1]), c, mneg));
+          rs += p0 + p1;
+          pk[e >> 1] = h2_as_u32(__floats2half2_rn(p0, p1));
+        }
+        ft_tmem_st16(p_addr + cc * 16, pk);
+      };
+      if (stamp) stamp[3] = clock64();   // max / lazy check / P.V_{j-1} wait done
+      if (pp) asm volatile("bar.sync %0, 64;" ::"r"(bar_mine) : "memory");     // my turn on the MUFU pipe
+      if (stamp) stamp[4] = clock64();   // token acquired
+      emit(v0, 0);
+      emit(v1, 1);
+      emit(v2, 2);
+      emit(v3, 3);
+      if (stamp) stamp[5] = clock64();   // exponentials + P stores issued
+      if (pp) asm volatile("bar.arrive %0, 64;" ::"r"(bar_other) : "memory");  // the other tile's turn
       l_run += rs;
       // P_j written: hand it to the MMA warp
-      ft_fence_proxy_async();
+      asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+      ft_tc_fence_before();
       __syncwarp();
       if (lane == 0) ft_mbar_arrive(p_full(t));
+      if (stamp) stamp[6] = clock64();   // P_j handed over
     }
+    if (pp && t == 0) asm volatile("bar.sync %0, 64;" ::"r"(bar_mine) : "memory");   // absorb tile 1's last hand-over
     // ---- last tile's P.V has landed: normalise, store ----
     ft_mbar_wait(o_full(t), (uint32_t)(nk - 1) & 1u);
     ft_tc_fence_after();
@@ -519,7 +527,8 @@ int ft_launch(const __half* q, int64_t ldq, const __half* k, int64_t ldk, const 
   if (rc != L2D_OK) return rc;
   rc = get_tmap_2d(v, (int64_t)batch * skv, (int64_t)heads * HD, ldv, 128, &tv);
   if (rc != L2D_OK) return rc;
-  FtParams p{o, ldo, sq, skv, heads, 1.4426950408889634f / sqrtf((float)HD)};
+  static const int pingpong = [] { const char* e = getenv("L2D_FLASH_PINGPONG"); return e ? atoi(e) : 1; }();
+  FtParams p{o, ldo, sq, skv, heads, 1.4426950408889634f / sqrtf((float)HD), pingpong, g_ft_dbg};
   launch_pdl_if(pdl_family(2), flash_tcgen05_kernel<HD, NQ>, dim3(sq / (128 * NQ), heads, batch), dim3(Cfg::THREADS),
                 (size_t)Cfg::SMEM, st, tq, tk, tv, p);
   L2D_LAUNCH_CHECK();
@@ -527,6 +536,8 @@ int ft_launch(const __half* q, int64_t ldq, const __half* k, int64_t ldk, const 
 }
 
 }  // namespace
+
+void set_flash_debug(long long* ptr) { g_ft_dbg = ptr; }
 
 int flash_tcgen05_ctas_per_sm(int hd) {
   int n = 0;
@@ -564,7 +575,8 @@ bool attention_tcgen05_supported(const void* q, const void* k, const void* v, co
 
 int attention_tcgen05_launch(const __half* q, int64_t ldq, const __half* k, int64_t ldk, const __half* v, int64_t ldv, __half* o,
                              int64_t ldo, int batch, int heads, int sq, int skv, int hd, cudaStream_t st) {
-  if (hd == 40 && sq % 256 == 0) return ft_launch<40, 2>(q, ldq, k, ldk, v, ldv, o, ldo, batch, heads, sq, skv, st);
+  static const int force_nq1 = [] { const char* e = getenv("L2D_FLASH_NQ"); return e && atoi(e) == 1; }();   // developer A/B
+  if (hd == 40 && sq % 256 == 0 && !force_nq1) return ft_launch<40, 2>(q, ldq, k, ldk, v, ldv, o, ldo, batch, heads, sq, skv, st);
   if (hd == 40) return ft_launch<40, 1>(q, ldq, k, ldk, v, ldv, o, ldo, batch, heads, sq, skv, st);
   if (hd == 80) return ft_launch<80, 1>(q, ldq, k, ldk, v, ldv, o, ldo, batch, heads, sq, skv, st);
   return fail(L2D_ERR_INVALID, "attention(tcgen05): unsupported head_dim");
@@ -574,3 +586,5 @@ int attention_tcgen05_launch(const __half* q, int64_t ldq, const __half* k, int6
 
 // developer hook (include/l2d_b200_debug.h): resident CTAs per SM of the tcgen05 attention kernel for head_dim 40 / 80
 extern "C" int l2d_debug_flash_ctas_per_sm(int hd) { return l2d::flash_tcgen05_ctas_per_sm(hd); }
+// developer hook: per-tile clock64 stamps of CTA (0,0,0) of the tcgen05 attention kernel (profiles/flash_timeline.py)
+extern "C" void l2d_flash_set_debug(void* timeline) { l2d::set_flash_debug(static_cast<long long*>(timeline)); }

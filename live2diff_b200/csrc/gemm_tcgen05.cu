@@ -102,6 +102,16 @@ __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t desc_a, uint6
       ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// one lane of a converged warp (the lowest: the same lane every time, as tcgen05.commit tracks the issuing thread's MMAs)
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
@@ -323,8 +333,13 @@ gemm_f16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
+    // The WHOLE warp walks the loop (convergent control flow) and one elected lane executes the tcgen05 instructions: the
+    // operands of UTCHMMA live in uniform registers, and descriptor arithmetic done by all lanes of a converged warp is
+    // provably uniform.  Inside an `if (lane == 0)` region it is not, and the compiler wraps every MMA in a per-lane
+    // "waterfall" loop (ELECT / UTCHMMA / BRA.U.ANY) that cost ~40 cycles per instruction on top of the tensor-core floor.
+    {
       constexpr uint32_t idesc = make_idesc(BN);
+      const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
       int it = 0;
       for (int i = 0; i < my_tiles; ++i) {
         const Tile tl = decode(i);
@@ -332,24 +347,28 @@ gemm_f16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid
         // the epilogue must have drained this accumulator stage (tile i-NACC)
         mbar_wait(smem_u32(&tmem_empty_bar[as]), ((uint32_t)(i / NACC) & 1u) ^ 1u);
         tc_fence_after();
-        const uint32_t tacc = tmem_base + (uint32_t)(as * BN);
+        const uint32_t tacc = tmem_u + (uint32_t)(as * BN);
         for (int kb = 0; kb < tl.num_kb; ++kb, ++it) {
           const int s = it % STAGES;
           const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
           mbar_wait(smem_u32(&full_bar[s]), ph);
-          if (dbg && it == 0) dbg[2] = clock64();        // first operand stage landed
+          if (dbg && it == 0 && lane == 0) dbg[2] = clock64();        // first operand stage landed
           tc_fence_after();
           const uint64_t da = make_sw128_desc(smem_u32(smem_a + s * S::A_BYTES));
           const uint64_t db = make_sw128_desc(smem_u32(smem_b + s * S::B_BYTES));
+          if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < BK / 16; ++k) {
-            // advance 16 elements (32 B) along K inside the swizzle atom: +2 in the (>>4) address field
-            umma_f16(tacc, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (kb | k) != 0);
+            for (int k = 0; k < BK / 16; ++k) {
+              // advance 16 elements (32 B) along K inside the swizzle atom: +2 in the (>>4) address field
+              umma_f16(tacc, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (kb | k) != 0);
+            }
+            umma_commit(smem_u32(&empty_bar[s]));  // slot free once these MMAs have read it
           }
-          umma_commit(smem_u32(&empty_bar[s]));  // slot free once these MMAs have read it
+          __syncwarp();
         }
-        umma_commit(smem_u32(&tmem_full_bar[as]));   // accumulator complete (fires immediately when num_kb == 0)
-        if (dbg && i == 0) dbg[3] = clock64();        // last MMA of the first tile issued
+        if (elect_one()) umma_commit(smem_u32(&tmem_full_bar[as]));   // accumulator complete (fires immediately when num_kb == 0)
+        __syncwarp();
+        if (dbg && i == 0 && lane == 0) dbg[3] = clock64();        // last MMA of the first tile issued
       }
     }
   } else {

@@ -32,6 +32,7 @@ ops.conv3x3(x.reshape(-1, 64), 2, 16, 16, r(64, 9 * 64) * 0.05, bias=r(64))     
 for hd, skv in ((40, 256), (80, 128), (40, 77), (160, 64)):
     c = 8 * hd
     ops.attention(r(2 * 128, c), r(2 * skv, c), r(2 * skv, c), 2, 8, 128, skv, hd)
+ops.attention(r(2 * 256, 320), r(2 * 384, 320), r(2 * 384, 320), 2, 8, 256, 384, 40)   # two query tiles per CTA
 # K1
 for L, c, hw in ((16, 320, 32), (16, 1280, 8), (32, 320, 16), (32, 640, 8), (4, 64, 16), (32, 1280, 4)):
     n = 2
@@ -42,6 +43,9 @@ for L, c, hw in ((16, 320, 32), (16, 1280, 8), (32, 320, 16), (32, 640, 8), (4, 
     ops.kv_attn(r(n, hw, c), r(n, hw, c), r(n, hw, c), cache, r(L, c), r(L, c), r(L, c), mask, pi, up, 8)
 # norms
 ops.layernorm(r(64, 320), r(320), r(320))
+ops.groupnorm(r(2 * 16 * 16, 320), r(320), r(320), 2, 16, 16, 32, 1e-5, silu=True)                              # one-kernel path
+ops.groupnorm(r(2 * 8 * 8, 128), r(192), r(192), 2, 8, 8, 32, 1e-5, silu=True, x2=r(2 * 8 * 8, 64))             # concat sources
+ops.groupnorm(r(2 * 8 * 8, 64), r(64), r(64), 2, 8, 8, 32, 1e-5, silu=True, im2col=True, stride=2)              # two-kernel path
 # TAESD
 vae = B200TinyVAE(random_taesd_state_dict(0), 64, 64, device=dev)
 z = vae.encode(torch.rand(1, 3, 64, 64, device=dev).half() * 2 - 1).latents
