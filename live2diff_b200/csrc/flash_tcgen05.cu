@@ -4,22 +4,25 @@
 // attn1 / attn2 of BasicTransformerBlock (live2diff/animatediff/models/attention.py:173-194, 243, 251-253); heads = 8,
 // hd = 40 / 80 at the two levels where S is large (64x64 and 32x32 latents: S = 4096 / 1024).
 //
-// One CTA = one 128-query tile of one (batch, head); it walks the keys in tiles of 128:
+// One CTA = one or two 128-query tiles of one (batch, head); it walks the keys in tiles of 128:
 //   warp 0     TMA producer: Q once, then K_j / V_j tiles ([128 rows x 64 columns] boxes, 128B swizzle) into two
 //              independent rings (K is consumed one tile ahead of V)
-//   warp 1     TMEM allocator + single-thread tcgen05.mma issuer:
-//                S_j = Q . K_j^T   (M = 128 queries, N = 128 keys, K = hd padded to 16s; both operands K-major) into one
-//                                  of two S accumulators in TMEM, so that S_{j+1} is computed while S_j is in the softmax
-//                O  += P_j . V_j   (M = 128, N = hd rounded up to whole 64-channel swizzle atoms, K = 128 keys; A = P from
-//                                  shared memory, K-major; B = the V tile exactly as TMA delivered it = MN-major, 128B
-//                                  swizzle); O stays in TMEM across ALL key tiles (accumulate flag)
+//   warp 1     TMEM allocator + tcgen05.mma issuer.  The whole warp walks the issue loop and ONE ELECTED LANE executes the
+//              MMAs and commits, so that descriptor arithmetic stays in uniform registers (inside an `if (lane == 0)` region
+//              the compiler wraps every UTCHMMA in a per-lane waterfall loop, ~150 cycles per MMA against a floor of 32-64):
+//                S_j = Q . K_j^T   (M = 128 queries, N = 128 keys, K = hd padded to 16s; both operands K-major in shared memory)
+//                O  += P_j . V_j   (M = 128, N = hd rounded up to whole 64-channel swizzle atoms, K = 128 keys; A = P read
+//                                  from TENSOR MEMORY, B = the V tile exactly as TMA delivered it = MN-major, 128B swizzle);
+//                                  O stays in TMEM across ALL key tiles (accumulate flag)
 //   warps 2-5  softmax + epilogue (a second quartet, warps 6-9, when the CTA carries two query tiles): thread = one query
-//              row (tcgen05.ld 32x32b: TMEM lane = row), so row max / row sum need no shuffles; P is rounded to fp16 (like
-//              the fused SDPA kernels the reference dispatches to) and written into shared memory in the UMMA K-major
-//              swizzled layout.  S is read from TMEM exactly once per tile: the exp uses the row max of the EARLIER tiles
-//              as its reference and the tile is redone (O and l rescaled in TMEM / registers) only when a row outgrows the
-//              reference by more than 2^8 -- the TMEM read port (64 B / clk / SM), not MUFU or the tensor core, was what
-//              bounded the classic two-pass form.  The 1/l normalisation is applied once at the end.
+//              row (tcgen05.ld 32x32b: TMEM lane = row), so row max / row sum need no shuffles.  A tile's 128 scores are pulled
+//              into registers in one go (S is read from TMEM once and its accumulator goes back to the tensor core at the
+//              START of the tile); the exp uses the row max of the EARLIER tiles as its reference and O / l are rescaled
+//              only when a row outgrows the reference by more than 2^8 (lazy rescale); P is rounded to fp16 (like the fused
+//              SDPA kernels the reference dispatches to) and written back to TMEM with tcgen05.st as fp16 pairs -- it never
+//              touches shared memory.  The 1/l normalisation is applied once at the end.  (Measured and not used, see
+//              profiles/README.md: a polynomial exp2 on the FMA pipe for one exponential in four; strict alternation of
+//              the two quartets' exp phases through a named-barrier token, kept behind L2D_FLASH_PINGPONG=1.)
 // hd = 40: the K extent of Q.K^T is padded to 48 by zeroing columns 40..47 of the Q tile in shared memory (the K tile's
 // columns 40..47 then hold the next head's values, finite, times zero); O's columns 40..63 are never read.
 // Keys beyond skv in the last tile (cross-attention: 77 keys) are masked to -inf before the softmax; their V rows are
@@ -166,7 +169,7 @@ struct FtParams {
   int64_t ldo;
   int sq, skv, heads;
   float scale_log2;   // log2(e) / sqrt(hd)
-  int pingpong;       // NQ == 2: the two query tiles take turns on the MUFU pipe (L2D_FLASH_PINGPONG, default 1)
+  int pingpong;       // NQ == 2: the two query tiles take turns on the MUFU pipe (L2D_FLASH_PINGPONG=1; default 0: measured slower)
   long long* dbg;     // developer timeline of CTA (0,0,0), see l2d_flash_set_debug; nullptr = off
 };
 
@@ -371,12 +374,10 @@ flash_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
     const float c = p.scale_log2;
     constexpr float LAZY = 8.f;
     const uint32_t o_addr = t_lane + tm_o(t);
-    // NQ == 2: a tile's work has two phases that use different units -- pulling 64 KB of scores through the TMEM read port
-    // (64 B / clk / SM: ~1000 cycles for the tile's four warps) and 16 K exponentials on the MUFU pipe (16 / clk / SM: ~1000
-    // cycles).  Left alone the two query tiles drift into phase, contend for one unit and then for the other (measured:
-    // the sum of both).  A token passed through two named barriers between warp w of tile 0 and warp w + 4 of tile 1 (same
-    // scheduler) makes the exp phases alternate strictly, so one tile's loads run under the other's exponentials
-    // (flash-attention 3's ping-pong schedule).
+    // NQ == 2, optional (L2D_FLASH_PINGPONG=1): a token passed through two named barriers between warp w of tile 0 and warp
+    // w + 4 of tile 1 (same scheduler) makes the two tiles' exp phases alternate strictly (flash-attention 3's ping-pong).
+    // Measured 114 vs 111 us without it at the level-0 shape: the exp phase is bound by one warp's dependent instruction
+    // stream, not by MUFU throughput, so two overlapping exp phases are faster than two serialised ones.
     const int bar_mine = 1 + t * 4 + (warp & 3), bar_other = 1 + (t ^ 1) * 4 + (warp & 3);
     const bool pp = NQ == 2 && p.pingpong;
     if (pp && t == 1) asm volatile("bar.arrive %0, 64;" ::"r"(bar_other) : "memory");   // tile 0 goes first
@@ -527,7 +528,7 @@ int ft_launch(const __half* q, int64_t ldq, const __half* k, int64_t ldk, const 
   if (rc != L2D_OK) return rc;
   rc = get_tmap_2d(v, (int64_t)batch * skv, (int64_t)heads * HD, ldv, 128, &tv);
   if (rc != L2D_OK) return rc;
-  static const int pingpong = [] { const char* e = getenv("L2D_FLASH_PINGPONG"); return e ? atoi(e) : 1; }();
+  static const int pingpong = [] { const char* e = getenv("L2D_FLASH_PINGPONG"); return e ? atoi(e) : 0; }();
   FtParams p{o, ldo, sq, skv, heads, 1.4426950408889634f / sqrtf((float)HD), pingpong, g_ft_dbg};
   launch_pdl_if(pdl_family(2), flash_tcgen05_kernel<HD, NQ>, dim3(sq / (128 * NQ), heads, batch), dim3(Cfg::THREADS),
                 (size_t)Cfg::SMEM, st, tq, tk, tv, p);

@@ -345,7 +345,8 @@ __global__ void __launch_bounds__(512) groupnorm_fused_kernel(const GnFusedParam
     asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar) : "memory");
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  pdl_wait();   // the activation belongs to the previous kernel until here
+  __syncthreads();   // barrier initialised before anyone arms or polls it (polls before the expect_tx below see the phase pending)
+  pdl_wait();        // the activation belongs to the previous kernel until here
   if (threadIdx.x == 0) {
     const uint32_t b1 = (uint32_t)npix * c1 * 2, b2 = (uint32_t)npix * c2 * 2;
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(b1 + b2) : "memory");
@@ -369,7 +370,6 @@ __global__ void __launch_bounds__(512) groupnorm_fused_kernel(const GnFusedParam
       }
     }
   }
-  __syncthreads();   // barrier initialised before anyone polls it
   {
     uint32_t done = 0, spins = 0;
     while (true) {
