@@ -178,9 +178,9 @@ constexpr int FT_TILE = 128 * 128;   // bytes of one [128 rows x 64 fp16] swizzl
 // NQ = 128-query tiles per CTA.  The driver keeps kernels that use tcgen05 at ONE CTA per SM whatever their shared-memory
 // and TMEM footprint (measured: cudaOccupancyMaxActiveBlocksPerMultiprocessor = 1 even at 48 KB / 256 columns), so the
 // latency hiding that two co-resident CTAs would give is built into one: with NQ = 2 two query tiles share every K/V tile
-// and run their own softmax warp quartets; while one tile's chain (S ready -> softmax -> P ready -> P.V -> T ready) waits on
-// the tensor core or a barrier, the other's exp pass keeps the MUFU pipe busy.  hd = 80 has no room for the second Q / P
-// tile (192 KB already) and keeps NQ = 1 with two S accumulators instead.
+// and run their own softmax warp quartets; while one tile's chain (S ready -> scores to registers -> exp -> P ready -> P.V)
+// waits on the tensor core or a barrier, the other's exp pass keeps the MUFU pipe busy (one tile per CTA: 179 vs 112 us at
+// the level-0 shape).  hd = 80 keeps NQ = 1: two query tiles would need 2 x 128 TMEM columns for O on top of S (256) and P.
 template <int HD, int NQ>
 struct FtCfg {
   static constexpr int KSTEPS = (HD + 15) / 16;     // k16 steps of Q.K^T

@@ -9,11 +9,11 @@
 // Structure (one 128 x BN output tile per CTA, 320 threads):
 //   warp 0   : TMA producer  -- cp.async.bulk.tensor 2D loads of A[128x64] and W[BNx64] tiles
 //              (128B swizzle) into a STAGES-deep shared-memory ring, mbarrier complete_tx
-//   warp 1   : TMEM allocator + MMA issuer -- one elected lane issues tcgen05.mma.cta_group::1
-//              .kind::f16 (M=128, N=BN, K=16) from shared-memory descriptors; tcgen05.commit
-//              releases ring slots and finally signals the accumulator-ready barrier
+//   warp 1   : TMEM allocator + MMA issuer -- the converged warp walks the k-loop, one elected lane issues
+//              tcgen05.mma.cta_group::1.kind::f16 (M=128, N=BN, K=16) from shared-memory descriptors (kept in
+//              uniform registers); tcgen05.commit releases ring slots and finally signals the accumulator-ready barrier
 //   warps 2-9: epilogue -- tcgen05.ld 32x32b TMEM -> registers, fused bias / per-image bias (temb) /
-//              SiLU / GEGLU / residual, 128-bit global stores
+//              SiLU / ReLU / GEGLU / residual, 256-bit global loads and stores
 // Partial tiles rely on TMA out-of-bounds zero fill (loads) and predicated stores.
 #include <cuda.h>
 
