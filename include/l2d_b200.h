@@ -82,7 +82,9 @@ int l2d_layernorm(const void* x, const void* gamma, const void* beta, void* y, i
 
 /* GroupNorm over NHWC x = concat_channels(x1[N,hw,C1], x2[N,hw,C2]) (x2 may be NULL, C2 = 0), `groups`
  * groups, optional SiLU.  `workspace` >= l2d_groupnorm_workspace_bytes(...) bytes, zero-filled ONCE by the caller
- * (it holds arrival counters that every launch leaves at zero).
+ * (it holds arrival counters that every launch leaves at zero); launches that share a workspace must be ordered on one
+ * stream.  mode 0 runs as ONE kernel whose CTAs (<= #SMs, all resident) meet at a barrier in the workspace, so it must
+ * not be launched concurrently with a kernel that never yields its SMs.
  * mode 0: y[N,hw,C] ; mode 1: y = im2col3x3(pad 1, stride `stride`) of the normalised tensor,
  * rows = N*(h/stride)*(w/stride), cols = 9*C ordered (tap, channel). */
 int64_t l2d_groupnorm_workspace_bytes(int n_img, int groups);
